@@ -1,0 +1,152 @@
+/*
+ * inmf_b200.h -- C ABI of libinmf_b200.so: hand-written sm_100a kernels for pyliger's integrative-NMF
+ * hot path (optimize_ALS, online_iNMF, nnlsm_blockpivot).
+ *
+ * pyliger itself has no FFI: the reference implements this path in numpy
+ * (/root/reference/src/pyliger/factorization/).  Every entry point below names the reference call
+ * site(s) it replaces.  The host side that mirrors the pyliger Python API lives in pyliger_b200/ and
+ * binds these symbols with ctypes (INTEGRATION.md shows the stub a pyliger maintainer would add).
+ *
+ * Conventions
+ *   - extern "C", plain C types only.  Every function returns 0 on success, < 0 on error;
+ *     inmf_last_error() returns a thread-local message.
+ *   - The caller owns all memory.  Pointers are DEVICE pointers unless stated otherwise.  No hidden
+ *     allocations, no host synchronisation: all work is enqueued on `stream` (a cudaStream_t).
+ *   - `_f32` / `_f64` suffix = element type T of X values, H, W, V, B and right-hand sides.
+ *     Small k x k Gram matrices, A, and scalar accumulators are always double.
+ *   - Layout: every dense operand is "entity-major" with the k factors contiguous:
+ *       Wt, Vt[s], St[s], B[s], Mt[s] : genes x k (Mt padded to ldm >= k columns)
+ *       H, R                          : cells x k
+ *     i.e. the transposes of optimize_ALS's k x g matrices and exactly online_iNMF's g x k ones.
+ *   - X is CSR over ALL datasets concatenated by rows: rowptr int64[n_total+1], colidx int32[nnz],
+ *     vals T[nnz]; a "segment" is one dataset (or one mini-batch window of it).
+ *   - seg_desc: device int64[nseg][4] = { out_off, row_base, win_start, win_mod }.  Output row
+ *     q in [out_off[s], out_off[s+1]) of segment s reads CSR row
+ *         row_base + (win_start + (q - out_off)) % win_mod .
+ *     (ALS: win_start = 0, win_mod = n_s.  Online mini-batch t: win_start = t*mb_s mod n_s, the
+ *     wrap-around of _online_iNMF.py:511-552.)  seg_desc has nseg+1 rows; only out_off of the last
+ *     row is read.
+ *   - k <= 64.
+ */
+#ifndef INMF_B200_H
+#define INMF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define INMF_MAX_K 64
+#define INMF_BPP_NSTATS 8 /* not_converged, factorizations, backup_flips, pivot_failures, rounds_sum, rounds_max, columns, reserved */
+
+int32_t inmf_version(void);
+const char* inmf_last_error(void);
+
+/* Batched block-principal-pivoting NNLS; one problem per column, G shared per segment.
+ * Replaces nnlsm_blockpivot + normal_eq_comb (_utilities.py:181-358) for all six call sites
+ * (_iNMF_ANLS.py:136,143,149; _online_iNMF.py:315,420,498).
+ *   G        double[nseg][k][k]   normal matrices (AtA)
+ *   R        T, column c at R + c*ldr (k contiguous values of AtB[:, c])
+ *   X        T out, column c at X + c*ldx (X may alias R: in-place solve)
+ *   Y        T out or NULL (G x - r, zero on the passive set)
+ *   mask     uint64 per column or NULL: final passive set; if warm != 0 it is also the start set
+ *            (the reference's `init` argument, _utilities.py:222-225)
+ *   seg_off  device int64[nseg+1] column ranges;  max_seg_cols = max segment length (host value)
+ *   stats    device int64[INMF_BPP_NSTATS], accumulated (caller zeroes)
+ */
+int32_t inmf_bpp_f32(const double* G, const float* R, int64_t ldr, float* X, int64_t ldx, float* Y,
+                     int64_t ldy, uint64_t* mask, int32_t warm, const int64_t* seg_off, int32_t nseg,
+                     int64_t max_seg_cols, int32_t k, int64_t* stats, void* stream);
+int32_t inmf_bpp_f64(const double* G, const double* R, int64_t ldr, double* X, int64_t ldx, double* Y,
+                     int64_t ldy, uint64_t* mask, int32_t warm, const int64_t* seg_off, int32_t nseg,
+                     int64_t max_seg_cols, int32_t k, int64_t* stats, void* stream);
+
+/* H-update preparation per segment s (replaces the hstack/AtA of _iNMF_ANLS.py:137 +
+ * _utilities.py:212 and _online_iNMF.py:421): Mt[s] = Wt + Vt[s] (zero padded to ldm),
+ * Gwv[s] = Mt'Mt, Gvv[s] = Vt'Vt, G[s] = Gwv[s] + lambda*Gvv[s].  Vt may be NULL (projection, V = 0).
+ * Outputs are overwritten. */
+int32_t inmf_prep_f32(const float* Wt, const float* Vt, float* Mt, int64_t ldm, double* G, double* Gwv,
+                      double* Gvv, double lambda, int32_t nseg, int64_t g, int32_t k, void* stream);
+int32_t inmf_prep_f64(const double* Wt, const double* Vt, double* Mt, int64_t ldm, double* G, double* Gwv,
+                      double* Gvv, double lambda, int32_t nseg, int64_t g, int32_t k, void* stream);
+
+/* R[q, :] = X[row(q), :] * Mt[s]  -- the AtB of the H-update, CSR streamed once
+ * (_iNMF_ANLS.py:138 + _utilities.py:217; _online_iNMF.py:422-424, 499-503). */
+int32_t inmf_spmm_f32(const int64_t* rowptr, const int32_t* colidx, const float* vals, const float* Mt,
+                      int64_t ldm, int64_t g, float* R, int64_t ldr, const int64_t* seg_desc,
+                      int32_t nseg, int64_t max_seg_rows, int32_t k, void* stream);
+int32_t inmf_spmm_f64(const int64_t* rowptr, const int32_t* colidx, const double* vals, const double* Mt,
+                      int64_t ldm, int64_t g, double* R, int64_t ldr, const int64_t* seg_desc,
+                      int32_t nseg, int64_t max_seg_rows, int32_t k, void* stream);
+
+/* Sufficient statistics of one pass over the cells (accumulating; caller zeroes):
+ *   St[s] (g x k) += sum_q X[row(q), :]' H[q, :],   HtH[s] (k x k, double) += sum_q H[q,:]' H[q,:]
+ * Replaces the dense X - H@W / vstack products of _iNMF_ANLS.py:144-152 and the H H', X H' of
+ * _online_iNMF.py:592-594. */
+int32_t inmf_stats_f32(const int64_t* rowptr, const int32_t* colidx, const float* vals, const float* H,
+                       int64_t ldh, float* St, double* HtH, int64_t g, const int64_t* seg_desc,
+                       int32_t nseg, int64_t max_seg_rows, int32_t k, void* stream);
+int32_t inmf_stats_f64(const int64_t* rowptr, const int32_t* colidx, const double* vals, const double* H,
+                       int64_t ldh, double* St, double* HtH, int64_t g, const int64_t* seg_desc,
+                       int32_t nseg, int64_t max_seg_rows, int32_t k, void* stream);
+
+/* ||X_s||_F^2 per segment (double[nseg], overwritten); constant term of the objective. */
+int32_t inmf_sqnorm_f32(const int64_t* rowptr, const float* vals, const int64_t* seg_desc, int32_t nseg,
+                        double* out, void* stream);
+int32_t inmf_sqnorm_f64(const int64_t* rowptr, const double* vals, const int64_t* seg_desc, int32_t nseg,
+                        double* out, void* stream);
+
+/* V-update normal equations (_iNMF_ANLS.py:142-146): Gv[s] = (1+lambda) HtH[s],
+ * Rv[s][c,:] = St[s][c,:] - Wt[c,:] HtH[s]. */
+int32_t inmf_rhs_v_f32(const float* St, const float* Wt, const double* HtH, float* Rv, double* Gv,
+                       double lambda, int32_t nseg, int64_t g, int32_t k, void* stream);
+int32_t inmf_rhs_v_f64(const double* St, const double* Wt, const double* HtH, double* Rv, double* Gv,
+                       double lambda, int32_t nseg, int64_t g, int32_t k, void* stream);
+/* W-update normal equations (_iNMF_ANLS.py:149-152): Gw = sum_s HtH[s],
+ * Rw[c,:] = sum_s ( St[s][c,:] - Vt[s][c,:] HtH[s] ). */
+int32_t inmf_rhs_w_f32(const float* St, const float* Vt, const double* HtH, float* Rw, double* Gw,
+                       int32_t nseg, int64_t g, int32_t k, void* stream);
+int32_t inmf_rhs_w_f64(const double* St, const double* Vt, const double* HtH, double* Rw, double* Gw,
+                       int32_t nseg, int64_t g, int32_t k, void* stream);
+
+/* Objective from statistics (_iNMF_ANLS.py:157-162 without n x g temporaries):
+ * obj = sum_s xnorm2[s] - 2<St[s],Mt[s]> + <HtH[s],Gwv[s]> + lambda <HtH[s],Gvv[s]>;  *obj overwritten. */
+int32_t inmf_objective_f32(const float* St, const float* Mt, int64_t ldm, const double* HtH,
+                           const double* Gwv, const double* Gvv, const double* xnorm2, double lambda,
+                           int32_t nseg, int64_t g, int32_t k, double* obj, void* stream);
+int32_t inmf_objective_f64(const double* St, const double* Mt, int64_t ldm, const double* HtH,
+                           const double* Gwv, const double* Gvv, const double* xnorm2, double lambda,
+                           int32_t nseg, int64_t g, int32_t k, double* obj, void* stream);
+
+/* Online statistics epilogue, _update_A_B (_online_iNMF.py:563-601), for nseg datasets at once.
+ *   HHt double[nseg][k][k], XHt T[nseg][g][k]: RAW mini-batch sums from inmf_stats
+ *   inv_mb double[nseg] (device): 1 / miniBatch_sizes[s];  scale = scale_param;  rollover != 0 when
+ *   epoch > 0 and epoch - epoch_prev == 1.  A, A_old are double; B, B_old are T. */
+int32_t inmf_update_ab_f32(double* A, double* A_old, float* B, float* B_old, const double* HHt,
+                           const float* XHt, const double* inv_mb, double scale, int32_t rollover,
+                           int32_t nseg, int64_t g, int32_t k, void* stream);
+int32_t inmf_update_ab_f64(double* A, double* A_old, double* B, double* B_old, const double* HHt,
+                           const double* XHt, const double* inv_mb, double scale, int32_t rollover,
+                           int32_t nseg, int64_t g, int32_t k, void* stream);
+
+/* HALS sweeps of W then every V_s, row (gene) parallel, n_inner times
+ * (_update_W_HALS / _update_V_HALS, _utilities.py:102-129; loop _online_iNMF.py:444-460).
+ * The first n_prev entries of A/B/Vt are the previous datasets of scenario 2
+ * (_online_iNMF.py:450-455): they enter the W sums but their V is not updated. */
+int32_t inmf_hals_f32(const double* A, const float* B, float* Wt, float* Vt, double lambda, int32_t n_prev,
+                      int32_t nall, int64_t g, int32_t k, int32_t n_inner, void* stream);
+int32_t inmf_hals_f64(const double* A, const double* B, double* Wt, double* Vt, double lambda,
+                      int32_t n_prev, int32_t nall, int64_t g, int32_t k, int32_t n_inner, void* stream);
+
+/* Dense normal-equation products for the raw-input form of nnlsm_blockpivot (_utilities.py:212-217):
+ * A is m x n row-major, B is m x cols row-major.  G (double n x n) = A'A;  Rt (T, cols x n) = (A'B)'. */
+int32_t inmf_normal_eq_f32(const float* A, const float* B, int64_t m, int32_t n, int64_t cols, double* G,
+                           float* Rt, void* stream);
+int32_t inmf_normal_eq_f64(const double* A, const double* B, int64_t m, int32_t n, int64_t cols, double* G,
+                           double* Rt, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* INMF_B200_H */

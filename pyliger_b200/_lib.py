@@ -1,0 +1,81 @@
+"""ctypes binding of libinmf_b200.so (the C ABI in include/inmf_b200.h).
+
+There is NO fallback: if the shared library is missing, or a call returns an error, this raises.
+The library is built in-tree by ``pyliger_b200/build.py`` (``python -m pyliger_b200.build`` or
+``__graft_entry__.build()``) and travels with the repository snapshot to the GPU box.
+"""
+import ctypes
+import os
+
+from .build import LIB_PATH
+
+_c = ctypes
+_I32, _I64, _F64, _PTR = _c.c_int32, _c.c_int64, _c.c_double, _c.c_void_p
+
+# name -> argtypes (without the _f32/_f64 suffix; P = device pointer or stream)
+_TYPED = {
+    "inmf_bpp": [_PTR, _PTR, _I64, _PTR, _I64, _PTR, _I64, _PTR, _I32, _PTR, _I32, _I64, _I32, _PTR, _PTR],
+    "inmf_prep": [_PTR, _PTR, _PTR, _I64, _PTR, _PTR, _PTR, _F64, _I32, _I64, _I32, _PTR],
+    "inmf_spmm": [_PTR, _PTR, _PTR, _PTR, _I64, _I64, _PTR, _I64, _PTR, _I32, _I64, _I32, _PTR],
+    "inmf_stats": [_PTR, _PTR, _PTR, _PTR, _I64, _PTR, _PTR, _I64, _PTR, _I32, _I64, _I32, _PTR],
+    "inmf_sqnorm": [_PTR, _PTR, _PTR, _I32, _PTR, _PTR],
+    "inmf_rhs_v": [_PTR, _PTR, _PTR, _PTR, _PTR, _F64, _I32, _I64, _I32, _PTR],
+    "inmf_rhs_w": [_PTR, _PTR, _PTR, _PTR, _PTR, _I32, _I64, _I32, _PTR],
+    "inmf_objective": [_PTR, _PTR, _I64, _PTR, _PTR, _PTR, _PTR, _F64, _I32, _I64, _I32, _PTR, _PTR],
+    "inmf_update_ab": [_PTR, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR, _F64, _I32, _I32, _I64, _I32, _PTR],
+    "inmf_hals": [_PTR, _PTR, _PTR, _PTR, _F64, _I32, _I32, _I64, _I32, _I32, _PTR],
+    "inmf_normal_eq": [_PTR, _PTR, _I64, _I32, _I64, _PTR, _PTR, _PTR],
+}
+
+EXPORTED_SYMBOLS = ["inmf_version", "inmf_last_error"] + [
+    "%s_%s" % (n, t) for n in _TYPED for t in ("f32", "f64")
+]
+
+_lib = None
+
+
+class InmfError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (once). Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise InmfError(
+            "libinmf_b200.so not found at %s: build it with `python -m pyliger_b200.build` "
+            "(nvcc, sm_100a). pyliger_b200 has no CPU fallback." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.inmf_version.restype = _I32
+    lib.inmf_version.argtypes = []
+    lib.inmf_last_error.restype = _c.c_char_p
+    lib.inmf_last_error.argtypes = []
+    for name, argtypes in _TYPED.items():
+        for suffix in ("f32", "f64"):
+            fn = getattr(lib, "%s_%s" % (name, suffix))
+            fn.restype = _I32
+            fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def _ptr(x):
+    """torch tensor / int / None -> device address."""
+    if x is None:
+        return None
+    if isinstance(x, int):
+        return x
+    return x.data_ptr()
+
+
+def call(name, suffix, *args):
+    """Invoke ``<name>_<suffix>``; tensors are passed by data pointer. Raises InmfError on failure."""
+    lib = load()
+    fn = getattr(lib, "%s_%s" % (name, suffix))
+    conv = [_ptr(a) if not isinstance(a, (float, bool)) else a for a in args]
+    rc = fn(*conv)
+    if rc != 0:
+        raise InmfError("%s_%s failed (%d): %s" % (name, suffix, rc, lib.inmf_last_error().decode()))
+    return rc

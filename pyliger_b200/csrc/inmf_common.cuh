@@ -1,0 +1,89 @@
+// Shared helpers for the iNMF kernels (sm_100a).  See include/inmf_b200.h for the ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "inmf_b200.h"
+
+#define INMF_FULL_MASK 0xffffffffu
+
+extern thread_local char g_inmf_err[512];
+
+#define INMF_CUDA_CHECK(call)                                                                   \
+    do {                                                                                        \
+        cudaError_t e_ = (call);                                                                \
+        if (e_ != cudaSuccess) {                                                                \
+            snprintf(g_inmf_err, sizeof(g_inmf_err), "%s:%d: %s -> %s", __FILE__, __LINE__, #call, \
+                     cudaGetErrorString(e_));                                                   \
+            return -1;                                                                          \
+        }                                                                                       \
+    } while (0)
+
+#define INMF_REQUIRE(cond, msg)                                                                 \
+    do {                                                                                        \
+        if (!(cond)) {                                                                          \
+            snprintf(g_inmf_err, sizeof(g_inmf_err), "%s:%d: invalid argument: %s", __FILE__,     \
+                     __LINE__, msg);                                                            \
+            return -2;                                                                          \
+        }                                                                                       \
+    } while (0)
+
+#define INMF_LAUNCH_CHECK() INMF_CUDA_CHECK(cudaGetLastError())
+
+static inline int inmf_num_sms() {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+            sms = 148;
+    }
+    return sms;
+}
+
+template <typename T>
+__device__ __forceinline__ T inmf_rsqrt(T x);
+template <>
+__device__ __forceinline__ float inmf_rsqrt<float>(float x) {
+    return rsqrtf(x);
+}
+template <>
+__device__ __forceinline__ double inmf_rsqrt<double>(double x) {
+    return 1.0 / sqrt(x);
+}
+
+template <typename T>
+__device__ __forceinline__ T inmf_abs(T x) {
+    return x < T(0) ? -x : x;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(INMF_FULL_MASK, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(INMF_FULL_MASK, v, o);
+    return v;
+}
+
+// Segment window descriptor (see header): seg_desc[s] = {out_off, row_base, win_start, win_mod}.
+struct SegWin {
+    int64_t out_off, row_base, win_start, win_mod, nrows;
+};
+__device__ __forceinline__ SegWin load_seg(const int64_t* __restrict__ seg_desc, int s) {
+    SegWin w;
+    w.out_off = seg_desc[4 * s + 0];
+    w.row_base = seg_desc[4 * s + 1];
+    w.win_start = seg_desc[4 * s + 2];
+    w.win_mod = seg_desc[4 * s + 3];
+    w.nrows = seg_desc[4 * (s + 1)] - w.out_off;
+    return w;
+}
+__device__ __forceinline__ int64_t seg_row(const SegWin& w, int64_t j) {
+    int64_t r = w.win_start + j;
+    if (r >= w.win_mod) r %= w.win_mod;
+    return w.row_base + r;
+}

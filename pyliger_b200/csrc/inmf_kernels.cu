@@ -1,0 +1,829 @@
+// libinmf_b200.so -- kernels + C ABI for pyliger's iNMF hot path on B200 (sm_100a).
+// ABI and reference citations: include/inmf_b200.h.  Design notes: DESIGN.md.
+#include "bpp.cuh"
+#include "inmf_common.cuh"
+
+thread_local char g_inmf_err[512] = "";
+
+extern "C" int32_t inmf_version(void) { return 100; }
+extern "C" const char* inmf_last_error(void) { return g_inmf_err; }
+
+// =================================================================================================
+// K3: batched BPP
+// =================================================================================================
+template <typename T>
+__global__ void bpp_kernel(const double* __restrict__ G, const T* R, int64_t ldr, T* X, int64_t ldx,
+                           T* __restrict__ Y, int64_t ldy, uint64_t* __restrict__ mask, int warm, const int64_t* __restrict__ seg_off, int k,
+                           long long* __restrict__ stats) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* smem = reinterpret_cast<T*>(smem_raw);
+    const int seg = blockIdx.y;
+    const int64_t c_begin = seg_off[seg];
+    const int64_t ncols = seg_off[seg + 1] - c_begin;
+    const int nwarps = blockDim.x >> 5;
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    if ((int64_t)blockIdx.x * nwarps >= ncols) return;
+
+    const int ldg = k | 1;
+    T* Gs = smem;
+    const double* Gseg = G + (size_t)seg * k * k;
+    for (int t = threadIdx.x; t < k * k; t += blockDim.x) Gs[(t / k) * ldg + (t % k)] = (T)Gseg[t];
+    __syncthreads();
+    size_t goff = ((size_t)k * ldg + 3) & ~(size_t)3;
+    BppWarpScratch<T> sc = bpp_carve<T>(smem + goff + (size_t)warp * bpp_warp_scratch_elems<T>(k), k);
+
+    long long n_notconv = 0, n_fact = 0, n_backup = 0, n_fail = 0, n_rounds = 0, max_rounds = 0, n_cols = 0;
+    for (int64_t c = (int64_t)blockIdx.x * nwarps + warp; c < ncols; c += (int64_t)gridDim.x * nwarps) {
+        const int64_t col = c_begin + c;
+        const T* r = R + col * ldr;
+        const T r0 = (lane < k) ? r[lane] : T(0);
+        const T r1 = (lane + 32 < k) ? r[lane + 32] : T(0);
+        uint64_t P = (warm && mask) ? mask[col] : 0ull;
+        T x0, x1, y0, y1;
+        BppCounters cnt = {0, 0, 0, 0, true};
+        bpp_column<T>(Gs, ldg, sc, k, r0, r1, P, warm != 0, x0, x1, y0, y1, cnt);
+        T* x = X + col * ldx;
+        if (lane < k) x[lane] = x0;
+        if (lane + 32 < k) x[lane + 32] = x1;
+        if (Y) {
+            T* y = Y + col * ldy;
+            if (lane < k) y[lane] = y0;
+            if (lane + 32 < k) y[lane + 32] = y1;
+        }
+        if (mask && lane == 0) mask[col] = P;
+        if (lane == 0) {
+            n_cols++;
+            n_notconv += cnt.ok ? 0 : 1;
+            n_fact += cnt.nfact;
+            n_backup += cnt.nbackup;
+            n_fail += cnt.nfail;
+            n_rounds += cnt.rounds;
+            max_rounds = max_rounds > cnt.rounds ? max_rounds : cnt.rounds;
+        }
+    }
+    if (stats && lane == 0 && n_cols) {
+        atomicAdd((unsigned long long*)&stats[0], (unsigned long long)n_notconv);
+        atomicAdd((unsigned long long*)&stats[1], (unsigned long long)n_fact);
+        atomicAdd((unsigned long long*)&stats[2], (unsigned long long)n_backup);
+        atomicAdd((unsigned long long*)&stats[3], (unsigned long long)n_fail);
+        atomicAdd((unsigned long long*)&stats[4], (unsigned long long)n_rounds);
+        atomicMax(&stats[5], max_rounds);
+        atomicAdd((unsigned long long*)&stats[6], (unsigned long long)n_cols);
+    }
+}
+
+template <typename T>
+static int32_t bpp_launch(const double* G, const T* R, int64_t ldr, T* X, int64_t ldx, T* Y, int64_t ldy,
+                          uint64_t* mask, int32_t warm, const int64_t* seg_off, int32_t nseg,
+                          int64_t max_seg_cols, int32_t k, int64_t* stats, void* stream) {
+    INMF_REQUIRE(k >= 1 && k <= INMF_MAX_K, "k must be in [1, 64]");
+    INMF_REQUIRE(nseg >= 1 && nseg <= 65535, "nseg out of range");
+    INMF_REQUIRE(ldr >= k && ldx >= k && (Y == nullptr || ldy >= k), "leading dimensions must be >= k");
+    if (max_seg_cols <= 0) return 0;
+    const int ldg = k | 1;
+    const size_t goff = ((size_t)k * ldg + 3) & ~(size_t)3;
+    const size_t per_warp = bpp_warp_scratch_elems<T>(k) * sizeof(T);
+    int nwarps = 8;
+    while (nwarps > 1 && goff * sizeof(T) + nwarps * per_warp > 64 * 1024) nwarps >>= 1;
+    const size_t smem = goff * sizeof(T) + nwarps * per_warp;
+    INMF_REQUIRE(smem <= 227 * 1024, "shared memory budget exceeded");
+    static bool attr_done[2] = {false, false};
+    const int ti = sizeof(T) == 8;
+    if (!attr_done[ti]) {
+        INMF_CUDA_CHECK(cudaFuncSetAttribute(bpp_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             227 * 1024));
+        attr_done[ti] = true;
+    }
+    int64_t blocks = (max_seg_cols + nwarps - 1) / nwarps;
+    const int64_t cap = (int64_t)inmf_num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    dim3 grid((unsigned)blocks, (unsigned)nseg);
+    bpp_kernel<T><<<grid, nwarps * 32, smem, (cudaStream_t)stream>>>(
+        G, R, ldr, X, ldx, Y, ldy, mask, warm, seg_off, k, (long long*)stats);
+    INMF_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int32_t inmf_bpp_f32(const double* G, const float* R, int64_t ldr, float* X, int64_t ldx, float* Y,
+                                int64_t ldy, uint64_t* mask, int32_t warm, const int64_t* seg_off,
+                                int32_t nseg, int64_t max_seg_cols, int32_t k, int64_t* stats, void* stream) {
+    return bpp_launch<float>(G, R, ldr, X, ldx, Y, ldy, mask, warm, seg_off, nseg, max_seg_cols, k, stats,
+                             stream);
+}
+extern "C" int32_t inmf_bpp_f64(const double* G, const double* R, int64_t ldr, double* X, int64_t ldx,
+                                double* Y, int64_t ldy, uint64_t* mask, int32_t warm, const int64_t* seg_off,
+                                int32_t nseg, int64_t max_seg_cols, int32_t k, int64_t* stats, void* stream) {
+    return bpp_launch<double>(G, R, ldr, X, ldx, Y, ldy, mask, warm, seg_off, nseg, max_seg_cols, k, stats,
+                              stream);
+}
+
+// =================================================================================================
+// Tall-skinny Gram helper: out(k x k, double) += tile' * tile for a row tile staged in shared memory.
+// Each thread owns a 4x4 block of the output.
+// =================================================================================================
+#define GRAM_TILE_ROWS 64
+
+template <typename T>
+__device__ __forceinline__ void tile_gram_accumulate(const T* __restrict__ tile, int ldt, int rows, int k,
+                                                     double* __restrict__ out, double scale) {
+    const int nb = (k + 3) >> 2;
+    for (int blk = threadIdx.x; blk < nb * nb; blk += blockDim.x) {
+        const int bi = blk / nb, bj = blk % nb;
+        T acc[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) acc[a][b] = T(0);
+        for (int r = 0; r < rows; ++r) {
+            const T* row = tile + (size_t)r * ldt;
+            T va[4], vb[4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                va[a] = row[4 * bi + a];
+                vb[a] = row[4 * bj + a];
+            }
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) acc[a][b] += va[a] * vb[b];
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int i = 4 * bi + a, j = 4 * bj + b;
+                if (i < k && j < k) atomicAdd(&out[(size_t)i * k + j], scale * (double)acc[a][b]);
+            }
+    }
+}
+
+// =================================================================================================
+// K1: H-update preparation (Mt, Gwv, Gvv) and G = Gwv + lambda Gvv
+// =================================================================================================
+template <typename T>
+__global__ void prep_kernel(const T* __restrict__ Wt, const T* __restrict__ Vt, T* __restrict__ Mt, int64_t ldm,
+                            double* __restrict__ Gwv, double* __restrict__ Gvv, int64_t g, int k) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* tm = reinterpret_cast<T*>(smem_raw);
+    const int ldt = (int)ldm;  // multiple of 4, >= k
+    T* tv = tm + (size_t)GRAM_TILE_ROWS * ldt;
+    const int s = blockIdx.y;
+    const T* V = Vt ? Vt + (size_t)s * g * k : nullptr;
+    T* M = Mt + (size_t)s * g * ldm;
+    for (int64_t r0 = (int64_t)blockIdx.x * GRAM_TILE_ROWS; r0 < g; r0 += (int64_t)gridDim.x * GRAM_TILE_ROWS) {
+        const int rows = (int)((g - r0 < GRAM_TILE_ROWS) ? (g - r0) : GRAM_TILE_ROWS);
+        for (int t = threadIdx.x; t < GRAM_TILE_ROWS * ldt; t += blockDim.x) {
+            const int r = t / ldt, j = t % ldt;
+            T w = T(0), v = T(0);
+            if (r < rows && j < k) {
+                w = Wt[(r0 + r) * k + j];
+                if (V) v = V[(r0 + r) * k + j];
+            }
+            tm[t] = w + v;
+            tv[t] = v;
+            if (r < rows) M[(r0 + r) * ldm + j] = w + v;
+        }
+        __syncthreads();
+        tile_gram_accumulate<T>(tm, ldt, rows, k, Gwv + (size_t)s * k * k, 1.0);
+        if (V) tile_gram_accumulate<T>(tv, ldt, rows, k, Gvv + (size_t)s * k * k, 1.0);
+        __syncthreads();
+    }
+}
+
+__global__ void combine_g_kernel(const double* __restrict__ Gwv, const double* __restrict__ Gvv,
+                                 double* __restrict__ G, double lambda, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) G[i] = Gwv[i] + lambda * Gvv[i];
+}
+
+template <typename T>
+static int32_t prep_launch(const T* Wt, const T* Vt, T* Mt, int64_t ldm, double* G, double* Gwv, double* Gvv,
+                           double lambda, int32_t nseg, int64_t g, int32_t k, void* stream) {
+    INMF_REQUIRE(k >= 1 && k <= INMF_MAX_K, "k must be in [1, 64]");
+    INMF_REQUIRE(ldm >= k && ldm % 4 == 0 && ldm <= 64, "ldm must be a multiple of 4 in [k, 64]");
+    INMF_REQUIRE(nseg >= 1 && g >= 1, "empty problem");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t kk = (size_t)nseg * k * k * sizeof(double);
+    INMF_CUDA_CHECK(cudaMemsetAsync(Gwv, 0, kk, st));
+    INMF_CUDA_CHECK(cudaMemsetAsync(Gvv, 0, kk, st));
+    int64_t tiles = (g + GRAM_TILE_ROWS - 1) / GRAM_TILE_ROWS;
+    if (tiles > 1024) tiles = 1024;
+    const size_t smem = 2 * (size_t)GRAM_TILE_ROWS * ldm * sizeof(T);
+    static bool attr_done[2] = {false, false};
+    const int ti = sizeof(T) == 8;
+    if (!attr_done[ti]) {
+        INMF_CUDA_CHECK(cudaFuncSetAttribute(prep_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             100 * 1024));
+        attr_done[ti] = true;
+    }
+    prep_kernel<T><<<dim3((unsigned)tiles, (unsigned)nseg), 256, smem, st>>>(Wt, Vt, Mt, ldm, Gwv, Gvv, g, k);
+    INMF_LAUNCH_CHECK();
+    const int n = nseg * k * k;
+    combine_g_kernel<<<(n + 255) / 256, 256, 0, st>>>(Gwv, Gvv, G, lambda, n);
+    INMF_LAUNCH_CHECK();
+    return 0;
+}
+extern "C" int32_t inmf_prep_f32(const float* Wt, const float* Vt, float* Mt, int64_t ldm, double* G,
+                                 double* Gwv, double* Gvv, double lambda, int32_t nseg, int64_t g, int32_t k,
+                                 void* stream) {
+    return prep_launch<float>(Wt, Vt, Mt, ldm, G, Gwv, Gvv, lambda, nseg, g, k, stream);
+}
+extern "C" int32_t inmf_prep_f64(const double* Wt, const double* Vt, double* Mt, int64_t ldm, double* G,
+                                 double* Gwv, double* Gvv, double lambda, int32_t nseg, int64_t g, int32_t k,
+                                 void* stream) {
+    return prep_launch<double>(Wt, Vt, Mt, ldm, G, Gwv, Gvv, lambda, nseg, g, k, stream);
+}
+
+// =================================================================================================
+// K2: CSR SpMM  R[q,:] = X[row(q),:] * Mt[s]      (warp per cell, lanes over factors)
+// =================================================================================================
+template <typename T>
+__global__ void spmm_rows_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                                 const T* __restrict__ vals, const T* __restrict__ Mt, int64_t ldm, int64_t g,
+                                 T* __restrict__ R, int64_t ldr, const int64_t* __restrict__ seg_desc, int k) {
+    const int s = blockIdx.y;
+    const SegWin w = load_seg(seg_desc, s);
+    const int nwarps = blockDim.x >> 5;
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const T* __restrict__ M = Mt + (size_t)s * g * ldm;
+    const bool has0 = lane < k, has1 = lane + 32 < k;
+    for (int64_t j = (int64_t)blockIdx.x * nwarps + warp; j < w.nrows; j += (int64_t)gridDim.x * nwarps) {
+        const int64_t row = seg_row(w, j);
+        const int64_t beg = rowptr[row], end = rowptr[row + 1];
+        T acc0 = T(0), acc1 = T(0);
+        for (int64_t p = beg; p < end; p += 32) {
+            const bool mine = p + lane < end;
+            const int32_t c = mine ? colidx[p + lane] : 0;
+            const T v = mine ? vals[p + lane] : T(0);
+            const int cnt = (end - p < 32) ? (int)(end - p) : 32;
+            for (int t = 0; t < cnt; ++t) {
+                const int32_t cc = __shfl_sync(INMF_FULL_MASK, c, t);
+                const T vv = __shfl_sync(INMF_FULL_MASK, v, t);
+                const T* m = M + (size_t)cc * ldm;
+                if (has0) acc0 += vv * m[lane];
+                if (has1) acc1 += vv * m[lane + 32];
+            }
+        }
+        T* out = R + (w.out_off + j) * ldr;
+        if (has0) out[lane] = acc0;
+        if (has1) out[lane + 32] = acc1;
+    }
+}
+
+template <typename T>
+static int32_t spmm_launch(const int64_t* rowptr, const int32_t* colidx, const T* vals, const T* Mt, int64_t ldm,
+                           int64_t g, T* R, int64_t ldr, const int64_t* seg_desc, int32_t nseg,
+                           int64_t max_seg_rows, int32_t k, void* stream) {
+    INMF_REQUIRE(k >= 1 && k <= INMF_MAX_K, "k must be in [1, 64]");
+    INMF_REQUIRE(ldm >= k && ldr >= k, "leading dimensions must be >= k");
+    INMF_REQUIRE(nseg >= 1 && nseg <= 65535, "nseg out of range");
+    if (max_seg_rows <= 0) return 0;
+    const int nwarps = 8;
+    int64_t blocks = (max_seg_rows + nwarps - 1) / nwarps;
+    const int64_t cap = (int64_t)inmf_num_sms() * 32;
+    if (blocks > cap) blocks = cap;
+    spmm_rows_kernel<T><<<dim3((unsigned)blocks, (unsigned)nseg), nwarps * 32, 0, (cudaStream_t)stream>>>(
+        rowptr, colidx, vals, Mt, ldm, g, R, ldr, seg_desc, k);
+    INMF_LAUNCH_CHECK();
+    return 0;
+}
+extern "C" int32_t inmf_spmm_f32(const int64_t* rowptr, const int32_t* colidx, const float* vals,
+                                 const float* Mt, int64_t ldm, int64_t g, float* R, int64_t ldr,
+                                 const int64_t* seg_desc, int32_t nseg, int64_t max_seg_rows, int32_t k,
+                                 void* stream) {
+    return spmm_launch<float>(rowptr, colidx, vals, Mt, ldm, g, R, ldr, seg_desc, nseg, max_seg_rows, k, stream);
+}
+extern "C" int32_t inmf_spmm_f64(const int64_t* rowptr, const int32_t* colidx, const double* vals,
+                                 const double* Mt, int64_t ldm, int64_t g, double* R, int64_t ldr,
+                                 const int64_t* seg_desc, int32_t nseg, int64_t max_seg_rows, int32_t k,
+                                 void* stream) {
+    return spmm_launch<double>(rowptr, colidx, vals, Mt, ldm, g, R, ldr, seg_desc, nseg, max_seg_rows, k, stream);
+}
+
+// =================================================================================================
+// K4/K5/K11: statistics  St[s] += X' H,  HtH[s] += H' H
+// =================================================================================================
+template <typename T>
+__global__ void stats_scatter_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                                     const T* __restrict__ vals, const T* __restrict__ H, int64_t ldh,
+                                     T* __restrict__ St, int64_t g, const int64_t* __restrict__ seg_desc, int k) {
+    const int s = blockIdx.y;
+    const SegWin w = load_seg(seg_desc, s);
+    const int nwarps = blockDim.x >> 5;
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    T* __restrict__ S = St + (size_t)s * g * k;
+    const bool has0 = lane < k, has1 = lane + 32 < k;
+    for (int64_t j = (int64_t)blockIdx.x * nwarps + warp; j < w.nrows; j += (int64_t)gridDim.x * nwarps) {
+        const int64_t row = seg_row(w, j);
+        const int64_t beg = rowptr[row], end = rowptr[row + 1];
+        const T* h = H + (w.out_off + j) * ldh;
+        const T h0 = has0 ? h[lane] : T(0);
+        const T h1 = has1 ? h[lane + 32] : T(0);
+        for (int64_t p = beg; p < end; p += 32) {
+            const bool mine = p + lane < end;
+            const int32_t c = mine ? colidx[p + lane] : 0;
+            const T v = mine ? vals[p + lane] : T(0);
+            const int cnt = (end - p < 32) ? (int)(end - p) : 32;
+            for (int t = 0; t < cnt; ++t) {
+                const int32_t cc = __shfl_sync(INMF_FULL_MASK, c, t);
+                const T vv = __shfl_sync(INMF_FULL_MASK, v, t);
+                T* dst = S + (size_t)cc * k;
+                if (has0 && h0 != T(0)) atomicAdd(dst + lane, vv * h0);
+                if (has1 && h1 != T(0)) atomicAdd(dst + lane + 32, vv * h1);
+            }
+        }
+    }
+}
+
+template <typename T>
+__global__ void gram_rows_kernel(const T* __restrict__ A, int64_t lda, const int64_t* __restrict__ seg_desc,
+                                 double* __restrict__ out, int k) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* tile = reinterpret_cast<T*>(smem_raw);
+    const int ldt = ((k + 3) & ~3) + 4;
+    const int s = blockIdx.y;
+    const int64_t r_begin = seg_desc[4 * s];
+    const int64_t nrows = seg_desc[4 * (s + 1)] - r_begin;
+    for (int64_t r0 = (int64_t)blockIdx.x * GRAM_TILE_ROWS; r0 < nrows; r0 += (int64_t)gridDim.x * GRAM_TILE_ROWS) {
+        const int rows = (int)((nrows - r0 < GRAM_TILE_ROWS) ? (nrows - r0) : GRAM_TILE_ROWS);
+        for (int t = threadIdx.x; t < GRAM_TILE_ROWS * ldt; t += blockDim.x) {
+            const int r = t / ldt, j = t % ldt;
+            tile[t] = (r < rows && j < k) ? A[(r_begin + r0 + r) * lda + j] : T(0);
+        }
+        __syncthreads();
+        tile_gram_accumulate<T>(tile, ldt, rows, k, out + (size_t)s * k * k, 1.0);
+        __syncthreads();
+    }
+}
+
+template <typename T>
+static int32_t stats_launch(const int64_t* rowptr, const int32_t* colidx, const T* vals, const T* H, int64_t ldh,
+                            T* St, double* HtH, int64_t g, const int64_t* seg_desc, int32_t nseg,
+                            int64_t max_seg_rows, int32_t k, void* stream) {
+    INMF_REQUIRE(k >= 1 && k <= INMF_MAX_K, "k must be in [1, 64]");
+    INMF_REQUIRE(ldh >= k, "ldh must be >= k");
+    INMF_REQUIRE(nseg >= 1 && nseg <= 65535, "nseg out of range");
+    if (max_seg_rows <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nwarps = 8;
+    int64_t blocks = (max_seg_rows + nwarps - 1) / nwarps;
+    const int64_t cap = (int64_t)inmf_num_sms() * 32;
+    if (blocks > cap) blocks = cap;
+    stats_scatter_kernel<T><<<dim3((unsigned)blocks, (unsigned)nseg), nwarps * 32, 0, st>>>(
+        rowptr, colidx, vals, H, ldh, St, g, seg_desc, k);
+    INMF_LAUNCH_CHECK();
+    int64_t tiles = (max_seg_rows + GRAM_TILE_ROWS - 1) / GRAM_TILE_ROWS;
+    const int64_t tcap = (int64_t)inmf_num_sms() * 8;
+    if (tiles > tcap) tiles = tcap;
+    const int ldt = ((k + 3) & ~3) + 4;
+    const size_t smem = (size_t)GRAM_TILE_ROWS * ldt * sizeof(T);
+    gram_rows_kernel<T><<<dim3((unsigned)tiles, (unsigned)nseg), 256, smem, st>>>(H, ldh, seg_desc, HtH, k);
+    INMF_LAUNCH_CHECK();
+    return 0;
+}
+extern "C" int32_t inmf_stats_f32(const int64_t* rowptr, const int32_t* colidx, const float* vals, const float* H,
+                                  int64_t ldh, float* St, double* HtH, int64_t g, const int64_t* seg_desc,
+                                  int32_t nseg, int64_t max_seg_rows, int32_t k, void* stream) {
+    return stats_launch<float>(rowptr, colidx, vals, H, ldh, St, HtH, g, seg_desc, nseg, max_seg_rows, k, stream);
+}
+extern "C" int32_t inmf_stats_f64(const int64_t* rowptr, const int32_t* colidx, const double* vals,
+                                  const double* H, int64_t ldh, double* St, double* HtH, int64_t g,
+                                  const int64_t* seg_desc, int32_t nseg, int64_t max_seg_rows, int32_t k,
+                                  void* stream) {
+    return stats_launch<double>(rowptr, colidx, vals, H, ldh, St, HtH, g, seg_desc, nseg, max_seg_rows, k, stream);
+}
+
+// =================================================================================================
+// ||X_s||^2
+// =================================================================================================
+template <typename T>
+__global__ void sqnorm_kernel(const int64_t* __restrict__ rowptr, const T* __restrict__ vals,
+                              const int64_t* __restrict__ seg_desc, double* __restrict__ out) {
+    const int s = blockIdx.y;
+    const int64_t row_base = seg_desc[4 * s + 1], n = seg_desc[4 * s + 3];
+    const int64_t beg = rowptr[row_base], end = rowptr[row_base + n];
+    double acc = 0.0;
+    for (int64_t p = beg + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < end;
+         p += (int64_t)gridDim.x * blockDim.x) {
+        const double v = (double)vals[p];
+        acc += v * v;
+    }
+    acc = warp_sum(acc);
+    __shared__ double part[32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) part[warp] = acc;
+    __syncthreads();
+    if (warp == 0) {
+        acc = (lane < (int)(blockDim.x >> 5)) ? part[lane] : 0.0;
+        acc = warp_sum(acc);
+        if (lane == 0) atomicAdd(&out[s], acc);
+    }
+}
+template <typename T>
+static int32_t sqnorm_launch(const int64_t* rowptr, const T* vals, const int64_t* seg_desc, int32_t nseg,
+                             double* out, void* stream) {
+    INMF_REQUIRE(nseg >= 1 && nseg <= 65535, "nseg out of range");
+    cudaStream_t st = (cudaStream_t)stream;
+    INMF_CUDA_CHECK(cudaMemsetAsync(out, 0, nseg * sizeof(double), st));
+    sqnorm_kernel<T><<<dim3(inmf_num_sms() * 2, nseg), 256, 0, st>>>(rowptr, vals, seg_desc, out);
+    INMF_LAUNCH_CHECK();
+    return 0;
+}
+extern "C" int32_t inmf_sqnorm_f32(const int64_t* rowptr, const float* vals, const int64_t* seg_desc,
+                                   int32_t nseg, double* out, void* stream) {
+    return sqnorm_launch<float>(rowptr, vals, seg_desc, nseg, out, stream);
+}
+extern "C" int32_t inmf_sqnorm_f64(const int64_t* rowptr, const double* vals, const int64_t* seg_desc,
+                                   int32_t nseg, double* out, void* stream) {
+    return sqnorm_launch<double>(rowptr, vals, seg_desc, nseg, out, stream);
+}
+
+// =================================================================================================
+// V / W right-hand sides from statistics (warp per gene)
+// =================================================================================================
+// out[lane], out[lane+32] of  row(1 x k) * C(k x k)   with row distributed over lanes.
+template <typename T>
+__device__ __forceinline__ void row_times_sym(const double* __restrict__ C, int k, T v0, T v1, T& o0, T& o1) {
+    const int lane = threadIdx.x & 31;
+    T a0 = T(0), a1 = T(0);
+    for (int a = 0; a < k; ++a) {
+        const T va = __shfl_sync(INMF_FULL_MASK, (a < 32) ? v0 : v1, a & 31);
+        if (lane < k) a0 += va * (T)C[(size_t)a * k + lane];
+        if (lane + 32 < k) a1 += va * (T)C[(size_t)a * k + lane + 32];
+    }
+    o0 = a0;
+    o1 = a1;
+}
+
+template <typename T>
+__global__ void rhs_v_kernel(const T* __restrict__ St, const T* __restrict__ Wt, const double* __restrict__ HtH,
+                             T* __restrict__ Rv, double* __restrict__ Gv, double lambda, int64_t g, int k) {
+    const int s = blockIdx.y;
+    const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const double* C = HtH + (size_t)s * k * k;
+    if (blockIdx.x == 0)
+        for (int t = threadIdx.x; t < k * k; t += blockDim.x) Gv[(size_t)s * k * k + t] = (1.0 + lambda) * C[t];
+    for (int64_t c = (int64_t)blockIdx.x * nwarps + warp; c < g; c += (int64_t)gridDim.x * nwarps) {
+        const T* w = Wt + c * k;
+        const T w0 = (lane < k) ? w[lane] : T(0);
+        const T w1 = (lane + 32 < k) ? w[lane + 32] : T(0);
+        T o0, o1;
+        row_times_sym<T>(C, k, w0, w1, o0, o1);
+        const T* sr = St + ((size_t)s * g + c) * k;
+        T* out = Rv + ((size_t)s * g + c) * k;
+        if (lane < k) out[lane] = sr[lane] - o0;
+        if (lane + 32 < k) out[lane + 32] = sr[lane + 32] - o1;
+    }
+}
+
+template <typename T>
+__global__ void rhs_w_kernel(const T* __restrict__ St, const T* __restrict__ Vt, const double* __restrict__ HtH,
+                             T* __restrict__ Rw, double* __restrict__ Gw, int nseg, int64_t g, int k) {
+    const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (blockIdx.x == 0)
+        for (int t = threadIdx.x; t < k * k; t += blockDim.x) {
+            double acc = 0.0;
+            for (int s = 0; s < nseg; ++s) acc += HtH[(size_t)s * k * k + t];
+            Gw[t] = acc;
+        }
+    for (int64_t c = (int64_t)blockIdx.x * nwarps + warp; c < g; c += (int64_t)gridDim.x * nwarps) {
+        T r0 = T(0), r1 = T(0);
+        for (int s = 0; s < nseg; ++s) {
+            const T* v = Vt + ((size_t)s * g + c) * k;
+            const T v0 = (lane < k) ? v[lane] : T(0);
+            const T v1 = (lane + 32 < k) ? v[lane + 32] : T(0);
+            T o0, o1;
+            row_times_sym<T>(HtH + (size_t)s * k * k, k, v0, v1, o0, o1);
+            const T* sr = St + ((size_t)s * g + c) * k;
+            if (lane < k) r0 += sr[lane] - o0;
+            if (lane + 32 < k) r1 += sr[lane + 32] - o1;
+        }
+        T* out = Rw + c * k;
+        if (lane < k) out[lane] = r0;
+        if (lane + 32 < k) out[lane + 32] = r1;
+    }
+}
+
+template <typename T>
+static int32_t rhs_v_launch(const T* St, const T* Wt, const double* HtH, T* Rv, double* Gv, double lambda,
+                            int32_t nseg, int64_t g, int32_t k, void* stream) {
+    INMF_REQUIRE(k >= 1 && k <= INMF_MAX_K && nseg >= 1 && g >= 1, "bad shape");
+    int64_t blocks = (g + 7) / 8;
+    if (blocks > inmf_num_sms() * 8) blocks = inmf_num_sms() * 8;
+    rhs_v_kernel<T><<<dim3((unsigned)blocks, (unsigned)nseg), 256, 0, (cudaStream_t)stream>>>(St, Wt, HtH, Rv, Gv,
+                                                                                               lambda, g, k);
+    INMF_LAUNCH_CHECK();
+    return 0;
+}
+template <typename T>
+static int32_t rhs_w_launch(const T* St, const T* Vt, const double* HtH, T* Rw, double* Gw, int32_t nseg,
+                            int64_t g, int32_t k, void* stream) {
+    INMF_REQUIRE(k >= 1 && k <= INMF_MAX_K && nseg >= 1 && g >= 1, "bad shape");
+    int64_t blocks = (g + 7) / 8;
+    if (blocks > inmf_num_sms() * 8) blocks = inmf_num_sms() * 8;
+    rhs_w_kernel<T><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(St, Vt, HtH, Rw, Gw, nseg, g, k);
+    INMF_LAUNCH_CHECK();
+    return 0;
+}
+extern "C" int32_t inmf_rhs_v_f32(const float* St, const float* Wt, const double* HtH, float* Rv, double* Gv,
+                                  double lambda, int32_t nseg, int64_t g, int32_t k, void* stream) {
+    return rhs_v_launch<float>(St, Wt, HtH, Rv, Gv, lambda, nseg, g, k, stream);
+}
+extern "C" int32_t inmf_rhs_v_f64(const double* St, const double* Wt, const double* HtH, double* Rv, double* Gv,
+                                  double lambda, int32_t nseg, int64_t g, int32_t k, void* stream) {
+    return rhs_v_launch<double>(St, Wt, HtH, Rv, Gv, lambda, nseg, g, k, stream);
+}
+extern "C" int32_t inmf_rhs_w_f32(const float* St, const float* Vt, const double* HtH, float* Rw, double* Gw,
+                                  int32_t nseg, int64_t g, int32_t k, void* stream) {
+    return rhs_w_launch<float>(St, Vt, HtH, Rw, Gw, nseg, g, k, stream);
+}
+extern "C" int32_t inmf_rhs_w_f64(const double* St, const double* Vt, const double* HtH, double* Rw, double* Gw,
+                                  int32_t nseg, int64_t g, int32_t k, void* stream) {
+    return rhs_w_launch<double>(St, Vt, HtH, Rw, Gw, nseg, g, k, stream);
+}
+
+// =================================================================================================
+// K8: objective from statistics
+// =================================================================================================
+template <typename T>
+__global__ void objective_kernel(const T* __restrict__ St, const T* __restrict__ Mt, int64_t ldm,
+                                 const double* __restrict__ HtH, const double* __restrict__ Gwv,
+                                 const double* __restrict__ Gvv, const double* __restrict__ xnorm2, double lambda,
+                                 int64_t g, int k, double* __restrict__ obj) {
+    const int s = blockIdx.y;
+    const T* S = St + (size_t)s * g * k;
+    const T* M = Mt + (size_t)s * g * ldm;
+    double acc = 0.0;
+    const int64_t total = g * k;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t c = t / k;
+        const int j = (int)(t - c * k);
+        acc += (double)S[t] * (double)M[c * ldm + j];
+    }
+    acc *= -2.0;
+    if (blockIdx.x == 0) {
+        const double* C = HtH + (size_t)s * k * k;
+        const double* A = Gwv + (size_t)s * k * k;
+        const double* B = Gvv + (size_t)s * k * k;
+        for (int t = threadIdx.x; t < k * k; t += blockDim.x) acc += C[t] * (A[t] + lambda * B[t]);
+        if (threadIdx.x == 0) acc += xnorm2[s];
+    }
+    acc = warp_sum(acc);
+    __shared__ double part[32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) part[warp] = acc;
+    __syncthreads();
+    if (warp == 0) {
+        acc = (lane < (int)(blockDim.x >> 5)) ? part[lane] : 0.0;
+        acc = warp_sum(acc);
+        if (lane == 0) atomicAdd(obj, acc);
+    }
+}
+template <typename T>
+static int32_t objective_launch(const T* St, const T* Mt, int64_t ldm, const double* HtH, const double* Gwv,
+                                const double* Gvv, const double* xnorm2, double lambda, int32_t nseg, int64_t g,
+                                int32_t k, double* obj, void* stream) {
+    INMF_REQUIRE(k >= 1 && k <= INMF_MAX_K && nseg >= 1 && g >= 1, "bad shape");
+    cudaStream_t st = (cudaStream_t)stream;
+    INMF_CUDA_CHECK(cudaMemsetAsync(obj, 0, sizeof(double), st));
+    int64_t blocks = (g * k + 255) / 256;
+    if (blocks > 64) blocks = 64;
+    objective_kernel<T><<<dim3((unsigned)blocks, (unsigned)nseg), 256, 0, st>>>(St, Mt, ldm, HtH, Gwv, Gvv, xnorm2,
+                                                                               lambda, g, k, obj);
+    INMF_LAUNCH_CHECK();
+    return 0;
+}
+extern "C" int32_t inmf_objective_f32(const float* St, const float* Mt, int64_t ldm, const double* HtH,
+                                      const double* Gwv, const double* Gvv, const double* xnorm2, double lambda,
+                                      int32_t nseg, int64_t g, int32_t k, double* obj, void* stream) {
+    return objective_launch<float>(St, Mt, ldm, HtH, Gwv, Gvv, xnorm2, lambda, nseg, g, k, obj, stream);
+}
+extern "C" int32_t inmf_objective_f64(const double* St, const double* Mt, int64_t ldm, const double* HtH,
+                                      const double* Gwv, const double* Gvv, const double* xnorm2, double lambda,
+                                      int32_t nseg, int64_t g, int32_t k, double* obj, void* stream) {
+    return objective_launch<double>(St, Mt, ldm, HtH, Gwv, Gvv, xnorm2, lambda, nseg, g, k, obj, stream);
+}
+
+// =================================================================================================
+// K11 epilogue: _update_A_B
+// =================================================================================================
+template <typename T>
+__global__ void update_ab_kernel(double* __restrict__ A, double* __restrict__ A_old, T* __restrict__ B,
+                                 T* __restrict__ B_old, const double* __restrict__ HHt, const T* __restrict__ XHt,
+                                 const double* __restrict__ inv_mb, double scale, int rollover, int64_t g, int k) {
+    const int s = blockIdx.y;
+    const double im = inv_mb[s];
+    const int64_t nb = g * k;
+    const int kk = k * k;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < nb + kk;
+         t += (int64_t)gridDim.x * blockDim.x) {
+        if (t < nb) {
+            const size_t o = (size_t)s * nb + t;
+            double b = (double)B[o], bo = (double)B_old[o];
+            if (rollover) {
+                b = b - bo;
+                bo = scale * b;
+            } else {
+                bo = scale * bo;
+            }
+            b = scale * b + (double)XHt[o] * im;
+            B[o] = (T)b;
+            B_old[o] = (T)bo;
+        } else {
+            const int e = (int)(t - nb);
+            const size_t o = (size_t)s * kk + e;
+            double a = A[o], ao = A_old[o];
+            if (rollover) {
+                a = a - ao;
+                ao = scale * a;
+            } else {
+                ao = scale * ao;
+            }
+            a = scale * a + HHt[o] * im;
+            if ((e / k) == (e % k) && a == 0.0) a = 1e-15;  // _online_iNMF.py:596-599
+            A[o] = a;
+            A_old[o] = ao;
+        }
+    }
+}
+template <typename T>
+static int32_t update_ab_launch(double* A, double* A_old, T* B, T* B_old, const double* HHt, const T* XHt,
+                                const double* inv_mb, double scale, int32_t rollover, int32_t nseg, int64_t g,
+                                int32_t k, void* stream) {
+    INMF_REQUIRE(k >= 1 && k <= INMF_MAX_K && nseg >= 1 && g >= 1, "bad shape");
+    int64_t blocks = (g * k + k * k + 255) / 256;
+    if (blocks > inmf_num_sms() * 4) blocks = inmf_num_sms() * 4;
+    update_ab_kernel<T><<<dim3((unsigned)blocks, (unsigned)nseg), 256, 0, (cudaStream_t)stream>>>(
+        A, A_old, B, B_old, HHt, XHt, inv_mb, scale, rollover, g, k);
+    INMF_LAUNCH_CHECK();
+    return 0;
+}
+extern "C" int32_t inmf_update_ab_f32(double* A, double* A_old, float* B, float* B_old, const double* HHt,
+                                      const float* XHt, const double* inv_mb, double scale, int32_t rollover,
+                                      int32_t nseg, int64_t g, int32_t k, void* stream) {
+    return update_ab_launch<float>(A, A_old, B, B_old, HHt, XHt, inv_mb, scale, rollover, nseg, g, k, stream);
+}
+extern "C" int32_t inmf_update_ab_f64(double* A, double* A_old, double* B, double* B_old, const double* HHt,
+                                      const double* XHt, const double* inv_mb, double scale, int32_t rollover,
+                                      int32_t nseg, int64_t g, int32_t k, void* stream) {
+    return update_ab_launch<double>(A, A_old, B, B_old, HHt, XHt, inv_mb, scale, rollover, nseg, g, k, stream);
+}
+
+// =================================================================================================
+// K12/K13: HALS sweeps, warp per gene row
+// =================================================================================================
+template <typename T>
+__global__ void hals_kernel(const double* __restrict__ A, const T* __restrict__ B, T* __restrict__ Wt,
+                            T* __restrict__ Vt, double lambda, int n_prev, int nall, int64_t g, int k,
+                            int n_inner) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int per_warp = (1 + 2 * nall) * k;
+    T* ws = reinterpret_cast<T*>(smem_raw) + (size_t)warp * per_warp;
+    T* vs = ws + k;                     // [nall][k]
+    T* bs = vs + (size_t)nall * k;      // [nall][k]
+    const T eps = T(1e-16);             // nonneg(), _utilities.py:10-13
+    const T one_lam = (T)(1.0 + lambda);
+    for (int64_t w = (int64_t)blockIdx.x * nwarps + warp; w < g; w += (int64_t)gridDim.x * nwarps) {
+        for (int j = lane; j < k; j += 32) ws[j] = Wt[w * k + j];
+        for (int i = 0; i < nall; ++i)
+            for (int j = lane; j < k; j += 32) {
+                vs[i * k + j] = Vt[((size_t)i * g + w) * k + j];
+                bs[i * k + j] = B[((size_t)i * g + w) * k + j];
+            }
+        __syncwarp();
+        for (int it = 0; it < n_inner; ++it) {
+            // ---- W sweep (all datasets, previous ones included) ----
+            for (int j = 0; j < k; ++j) {
+                T part = T(0);
+                for (int a = lane; a < k; a += 32) {
+                    const T wa = ws[a];
+                    for (int i = 0; i < nall; ++i)
+                        part += (wa + vs[i * k + a]) * (T)A[((size_t)i * k + a) * k + j];
+                }
+                part = warp_sum(part);
+                if (lane == 0) {
+                    T num = -part;
+                    T den = T(0);
+                    for (int i = 0; i < nall; ++i) {
+                        num += bs[i * k + j];
+                        den += (T)A[((size_t)i * k + j) * k + j];
+                    }
+                    T nw = ws[j] + num / den;
+                    ws[j] = nw < eps ? eps : nw;
+                }
+                __syncwarp();
+            }
+            // ---- V sweep (current datasets only), j outer / dataset inner ----
+            for (int j = 0; j < k; ++j) {
+                for (int i = n_prev; i < nall; ++i) {
+                    T part = T(0);
+                    for (int a = lane; a < k; a += 32)
+                        part += (ws[a] + one_lam * vs[i * k + a]) * (T)A[((size_t)i * k + a) * k + j];
+                    part = warp_sum(part);
+                    if (lane == 0) {
+                        const T ajj = (T)A[((size_t)i * k + j) * k + j];
+                        T nv = vs[i * k + j] + (bs[i * k + j] - part) / (one_lam * ajj);
+                        vs[i * k + j] = nv < eps ? eps : nv;
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+        for (int j = lane; j < k; j += 32) Wt[w * k + j] = ws[j];
+        for (int i = n_prev; i < nall; ++i)
+            for (int j = lane; j < k; j += 32) Vt[((size_t)i * g + w) * k + j] = vs[i * k + j];
+        __syncwarp();
+    }
+}
+template <typename T>
+static int32_t hals_launch(const double* A, const T* B, T* Wt, T* Vt, double lambda, int32_t n_prev, int32_t nall,
+                           int64_t g, int32_t k, int32_t n_inner, void* stream) {
+    INMF_REQUIRE(k >= 1 && k <= INMF_MAX_K && nall >= 1 && g >= 1, "bad shape");
+    INMF_REQUIRE(n_prev >= 0 && n_prev <= nall && n_inner >= 0, "bad n_prev / n_inner");
+    const size_t per_warp = (size_t)(1 + 2 * nall) * k * sizeof(T);
+    int nwarps = 8;
+    while (nwarps > 1 && nwarps * per_warp > 96 * 1024) nwarps >>= 1;
+    const size_t smem = nwarps * per_warp;
+    INMF_REQUIRE(smem <= 227 * 1024, "too many datasets for the HALS shared-memory staging");
+    static bool attr_done[2] = {false, false};
+    const int ti = sizeof(T) == 8;
+    if (!attr_done[ti]) {
+        INMF_CUDA_CHECK(cudaFuncSetAttribute(hals_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             227 * 1024));
+        attr_done[ti] = true;
+    }
+    int64_t blocks = (g + nwarps - 1) / nwarps;
+    if (blocks > inmf_num_sms() * 8) blocks = inmf_num_sms() * 8;
+    hals_kernel<T><<<(unsigned)blocks, nwarps * 32, smem, (cudaStream_t)stream>>>(A, B, Wt, Vt, lambda, n_prev, nall,
+                                                                                g, k, n_inner);
+    INMF_LAUNCH_CHECK();
+    return 0;
+}
+extern "C" int32_t inmf_hals_f32(const double* A, const float* B, float* Wt, float* Vt, double lambda,
+                                 int32_t n_prev, int32_t nall, int64_t g, int32_t k, int32_t n_inner, void* stream) {
+    return hals_launch<float>(A, B, Wt, Vt, lambda, n_prev, nall, g, k, n_inner, stream);
+}
+extern "C" int32_t inmf_hals_f64(const double* A, const double* B, double* Wt, double* Vt, double lambda,
+                                 int32_t n_prev, int32_t nall, int64_t g, int32_t k, int32_t n_inner, void* stream) {
+    return hals_launch<double>(A, B, Wt, Vt, lambda, n_prev, nall, g, k, n_inner, stream);
+}
+
+// =================================================================================================
+// Dense normal equations for the raw-input operator form
+// =================================================================================================
+template <typename T>
+__global__ void gram_dense_kernel(const T* __restrict__ A, int64_t m, int n, double* __restrict__ G) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* tile = reinterpret_cast<T*>(smem_raw);
+    const int ldt = ((n + 3) & ~3) + 4;
+    for (int64_t r0 = (int64_t)blockIdx.x * GRAM_TILE_ROWS; r0 < m; r0 += (int64_t)gridDim.x * GRAM_TILE_ROWS) {
+        const int rows = (int)((m - r0 < GRAM_TILE_ROWS) ? (m - r0) : GRAM_TILE_ROWS);
+        for (int t = threadIdx.x; t < GRAM_TILE_ROWS * ldt; t += blockDim.x) {
+            const int r = t / ldt, j = t % ldt;
+            tile[t] = (r < rows && j < n) ? A[(r0 + r) * n + j] : T(0);
+        }
+        __syncthreads();
+        tile_gram_accumulate<T>(tile, ldt, rows, n, G, 1.0);
+        __syncthreads();
+    }
+}
+// Rt[c][j] = sum_r B[r][c] * A[r][j]; block = 64 (j) x 4 (c)
+template <typename T>
+__global__ void atb_dense_kernel(const T* __restrict__ A, const T* __restrict__ B, int64_t m, int n, int64_t cols,
+                                 T* __restrict__ Rt) {
+    const int j = threadIdx.x;
+    const int64_t c = (int64_t)blockIdx.x * blockDim.y + threadIdx.y;
+    if (j >= n || c >= cols) return;
+    double acc = 0.0;
+    for (int64_t r = 0; r < m; ++r) acc += (double)B[r * cols + c] * (double)A[r * n + j];
+    Rt[c * n + j] = (T)acc;
+}
+template <typename T>
+static int32_t normal_eq_launch(const T* A, const T* B, int64_t m, int32_t n, int64_t cols, double* G, T* Rt,
+                                void* stream) {
+    INMF_REQUIRE(n >= 1 && n <= INMF_MAX_K && m >= 1 && cols >= 0, "bad shape");
+    cudaStream_t st = (cudaStream_t)stream;
+    INMF_CUDA_CHECK(cudaMemsetAsync(G, 0, (size_t)n * n * sizeof(double), st));
+    int64_t tiles = (m + GRAM_TILE_ROWS - 1) / GRAM_TILE_ROWS;
+    if (tiles > inmf_num_sms() * 4) tiles = inmf_num_sms() * 4;
+    const int ldt = ((n + 3) & ~3) + 4;
+    gram_dense_kernel<T><<<(unsigned)tiles, 256, (size_t)GRAM_TILE_ROWS * ldt * sizeof(T), st>>>(A, m, n, G);
+    INMF_LAUNCH_CHECK();
+    if (cols > 0) {
+        atb_dense_kernel<T><<<(unsigned)((cols + 3) / 4), dim3(64, 4), 0, st>>>(A, B, m, n, cols, Rt);
+        INMF_LAUNCH_CHECK();
+    }
+    return 0;
+}
+extern "C" int32_t inmf_normal_eq_f32(const float* A, const float* B, int64_t m, int32_t n, int64_t cols, double* G,
+                                      float* Rt, void* stream) {
+    return normal_eq_launch<float>(A, B, m, n, cols, G, Rt, stream);
+}
+extern "C" int32_t inmf_normal_eq_f64(const double* A, const double* B, int64_t m, int32_t n, int64_t cols,
+                                      double* G, double* Rt, void* stream) {
+    return normal_eq_launch<double>(A, B, m, n, cols, G, Rt, stream);
+}

@@ -1,0 +1,355 @@
+"""Device-side state and step functions of the iNMF hot path.
+
+Host orchestration only: torch tensors own the device buffers, every arithmetic step is a call into
+libinmf_b200.so (``_lib.call``).  Layouts are the entity-major ones of include/inmf_b200.h:
+``Wt``/``Vt[s]`` are genes x k, ``H`` is cells x k over all datasets concatenated.
+
+Multi-GPU: every rank owns a contiguous row slice of EVERY dataset; W, V and the
+reduced statistics are replicated; one all-reduce(SUM) of ``St`` (N x g x k) and ``HtH`` (N x k x k)
+per ALS iteration / online mini-batch.  H is only gathered for the final write-back.
+"""
+import numpy as np
+import scipy.sparse as sps
+import torch
+
+from . import _lib
+
+_SUFFIX = {torch.float32: "f32", torch.float64: "f64"}
+
+
+def resolve_dtype(dtype):
+    if dtype in (torch.float32, torch.float64):
+        return dtype
+    name = np.dtype(dtype).name if not isinstance(dtype, str) else dtype
+    if name in ("float32", "f32", "fp32"):
+        return torch.float32
+    if name in ("float64", "f64", "fp64"):
+        return torch.float64
+    raise ValueError("dtype must be float32 or float64, got %r" % (dtype,))
+
+
+def require_cuda(device=None):
+    if not torch.cuda.is_available():
+        raise _lib.InmfError("pyliger_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback.")
+    _lib.load()
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    return torch.device(device)
+
+
+def shard_bounds(n, rank, world):
+    """Contiguous row slice [lo, hi) of a dataset with n cells owned by ``rank``."""
+    return (n * rank) // world, (n * (rank + 1)) // world
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def all_gather_rows(local, counts, group=None):
+    """Concatenate per-rank row blocks of unequal height (all_gather needs equal shapes: pad)."""
+    cap = max(counts)
+    padded = torch.zeros((cap,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    padded[:local.shape[0]] = local
+    parts = [torch.empty_like(padded) for _ in counts]
+    torch.distributed.all_gather(parts, padded, group=group)
+    return torch.cat([p[:c] for p, c in zip(parts, counts)], 0)
+
+
+def online_windows(total_iters, mbs, sub, n_global, row_base):
+    """seg_desc [total_iters, N+1, 4] of the online mini-batches.
+
+    Step t of dataset i covers global rows [t*mb_i, (t+1)*mb_i) mod n_i -- the reference takes its
+    h5 chunks in order without shuffling and simply continues into the next epoch
+    (_online_iNMF.py:511-552) -- and a rank handles the sub-range ``sub[i]`` = [lo, hi) of it."""
+    N = len(mbs)
+    plan = np.zeros((total_iters, N + 1, 4), dtype=np.int64)
+    sub_n = [hi - lo for lo, hi in sub]
+    plan[:, :, 0] = np.concatenate([[0], np.cumsum(sub_n)])[None, :]
+    t = np.arange(total_iters, dtype=np.int64)
+    for i in range(N):
+        n = int(n_global[i])
+        plan[:, i, 1] = row_base[i]
+        plan[:, i, 2] = (t * int(mbs[i]) + sub[i][0]) % n
+        plan[:, i, 3] = n
+    return plan
+
+
+class DeviceCSR(object):
+    """All datasets' (local row slices of) scale_data concatenated by rows on the device."""
+
+    def __init__(self, mats, dtype, device, rank=0, world=1, pin=False, replicate=False):
+        self.N = len(mats)
+        self.g = int(mats[0].shape[1])
+        self.n_global = [int(m.shape[0]) for m in mats]
+        # own[i]    = global rows whose H this rank computes (always a 1/world slice)
+        # bounds[i] = global rows resident on this rank (== own, or everything when replicated)
+        self.own = [shard_bounds(n, rank, world) for n in self.n_global]
+        self.bounds = [(0, n) for n in self.n_global] if replicate else list(self.own)
+        self.n_local = [hi - lo for lo, hi in self.bounds]
+        self.n_own = [hi - lo for lo, hi in self.own]
+        self.row_base = np.concatenate([[0], np.cumsum(self.n_local)]).astype(np.int64)
+        self.own_off = np.concatenate([[0], np.cumsum(self.n_own)]).astype(np.int64)
+        self.n_total = int(self.row_base[-1])
+        self.n_own_total = int(self.own_off[-1])
+        ndt = np.float32 if dtype == torch.float32 else np.float64
+        indptr = [np.zeros(1, dtype=np.int64)]
+        cols, vals = [], []
+        off = 0
+        for m, (lo, hi) in zip(mats, self.bounds):
+            if m.shape[1] != self.g:
+                raise ValueError("all datasets must share the same genes (columns)")
+            if not sps.isspmatrix_csr(m):
+                m = sps.csr_matrix(m)
+            if not m.has_sorted_indices:
+                m = m.sorted_indices()
+            p0, p1 = int(m.indptr[lo]), int(m.indptr[hi])
+            indptr.append(m.indptr[lo + 1:hi + 1].astype(np.int64) - p0 + off)
+            cols.append(m.indices[p0:p1].astype(np.int32, copy=False))
+            vals.append(m.data[p0:p1].astype(ndt, copy=False))
+            off += p1 - p0
+        self.nnz = off
+        self.host = (np.concatenate(indptr), np.concatenate(cols) if cols else np.zeros(0, np.int32),
+                     np.concatenate(vals) if vals else np.zeros(0, ndt))
+        self.h2d_bytes = sum(a.nbytes for a in self.host)
+        ts = [torch.from_numpy(a) for a in self.host]
+        if pin:
+            ts = [t.pin_memory() for t in ts]
+        self.rowptr, self.colidx, self.vals = [t.to(device, non_blocking=pin) for t in ts]
+
+
+class InmfEngine(object):
+    """Buffers + step functions shared by optimize_ALS and online_iNMF."""
+
+    def __init__(self, mats, k, value_lambda, dtype=torch.float64, device=None, group=None, pin=False,
+                 replicate=False, n_prev=0):
+        self.device = require_cuda(device)
+        self.dtype = resolve_dtype(dtype)
+        self.sfx = _SUFFIX[self.dtype]
+        self.group = group
+        self.world = 1
+        self.rank = 0
+        if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(group)
+            self.rank = torch.distributed.get_rank(group)
+        self.k = int(k)
+        if not 1 <= self.k <= 64:
+            raise ValueError("pyliger_b200 supports 1 <= k <= 64 factors, got %d" % self.k)
+        self.lam = float(value_lambda)
+        self.n_prev = int(n_prev)
+        with torch.cuda.device(self.device):
+            self.X = DeviceCSR(mats, self.dtype, self.device, self.rank, self.world, pin=pin,
+                               replicate=replicate)
+            self._alloc()
+
+    # ------------------------------------------------------------------ buffers
+    def _alloc(self):
+        X, k, dev, dt = self.X, self.k, self.device, self.dtype
+        N, g = X.N, X.g
+        self.N, self.g = N, g
+        self.ldm = max(4, (k + 3) // 4 * 4)
+        f64 = torch.float64
+        z = lambda *shape, dtype=dt: torch.zeros(*shape, dtype=dtype, device=dev)
+        self.Wt = z(g, k)
+        # stacked [previous datasets (online scenario 2) | current datasets]
+        self.Vt_all = z(self.n_prev + N, g, k)
+        self.Vt = self.Vt_all[self.n_prev:]
+        self.H = z(max(X.n_own_total, 1), k)
+        self.Mt = z(N, g, self.ldm)
+        self.G = z(N, k, k, dtype=f64)
+        self.Gwv = z(N, k, k, dtype=f64)
+        self.Gvv = z(N, k, k, dtype=f64)
+        self.St = z(N, g, k)
+        self.HtH = z(N, k, k, dtype=f64)
+        self.Rv = z(N, g, k)
+        self.Rw = z(g, k)
+        self.Gv = z(N, k, k, dtype=f64)
+        self.Gw = z(1, k, k, dtype=f64)
+        self.xnorm2 = z(N, dtype=f64)
+        self.obj = z(1, dtype=f64)
+        self.bpp_stats = torch.zeros(3, 8, dtype=torch.int64, device=dev)  # rows: H, V, W solves
+        self.mask_H = torch.zeros(max(X.n_own_total, 1), dtype=torch.int64, device=dev)
+        self.mask_V = torch.zeros(N * g, dtype=torch.int64, device=dev)
+        self.mask_W = torch.zeros(g, dtype=torch.int64, device=dev)
+        full = np.zeros((N + 1, 4), dtype=np.int64)
+        full[:, 0] = X.own_off
+        full[:N, 1] = X.row_base[:N]
+        full[:N, 2] = [o[0] - b[0] for o, b in zip(X.own, X.bounds)]
+        full[:N, 3] = np.maximum(X.n_local, 1)
+        self.seg_full = torch.from_numpy(full).to(dev)
+        self.max_rows_full = int(max(X.n_own)) if N else 0
+        whole = full.copy()  # every resident row exactly once (sqnorm)
+        whole[:N, 2] = 0
+        whole[:N, 3] = X.n_local
+        self.seg_genes = torch.arange(0, (N + 1) * g, g, dtype=torch.int64, device=dev)
+        self.seg_w = torch.tensor([0, g], dtype=torch.int64, device=dev)
+        _lib.call("inmf_sqnorm", self.sfx, X.rowptr, X.vals, torch.from_numpy(whole).to(dev), N, self.xnorm2,
+                  _stream())
+        if X.bounds == X.own:
+            self._allreduce(self.xnorm2)
+
+    def _allreduce(self, *tensors):
+        if self.world > 1:
+            for t in tensors:
+                torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM, group=self.group)
+
+    # ------------------------------------------------------------------ kernels
+    def prep(self, with_V=True):
+        _lib.call("inmf_prep", self.sfx, self.Wt, self.Vt if with_V else None, self.Mt, self.ldm, self.G,
+                  self.Gwv, self.Gvv, self.lam, self.N, self.g, self.k, _stream())
+
+    def solve_H(self, seg_desc=None, max_rows=None, out=None, mask=None, warm=False, nseg=None):
+        """out[q,:] = argmin_{h>=0} for every row of the windows in seg_desc (default: all local cells)."""
+        seg_desc = self.seg_full if seg_desc is None else seg_desc
+        max_rows = self.max_rows_full if max_rows is None else max_rows
+        out = self.H if out is None else out
+        nseg = self.N if nseg is None else nseg
+        if max_rows <= 0:
+            return
+        X, k = self.X, self.k
+        _lib.call("inmf_spmm", self.sfx, X.rowptr, X.colidx, X.vals, self.Mt, self.ldm, self.g, out, k,
+                  seg_desc, nseg, max_rows, k, _stream())
+        # segment column ranges of the batched BPP are the out_off column of seg_desc (stride 4)
+        seg_off = seg_desc[:, 0].contiguous()
+        _lib.call("inmf_bpp", self.sfx, self.G, out, k, out, k, None, 0, mask, 1 if warm else 0, seg_off,
+                  nseg, max_rows, k, self.bpp_stats[0], _stream())
+
+    def stats(self, seg_desc=None, max_rows=None, H=None, St=None, HtH=None, reduce=True, nseg=None):
+        seg_desc = self.seg_full if seg_desc is None else seg_desc
+        max_rows = self.max_rows_full if max_rows is None else max_rows
+        H = self.H if H is None else H
+        St = self.St if St is None else St
+        HtH = self.HtH if HtH is None else HtH
+        nseg = self.N if nseg is None else nseg
+        St.zero_()
+        HtH.zero_()
+        X, k = self.X, self.k
+        if max_rows > 0:
+            _lib.call("inmf_stats", self.sfx, X.rowptr, X.colidx, X.vals, H, k, St, HtH, self.g, seg_desc,
+                      nseg, max_rows, k, _stream())
+        if reduce:
+            self._allreduce(St, HtH)
+
+    def solve_V(self, warm=False):
+        k, g, N = self.k, self.g, self.N
+        _lib.call("inmf_rhs_v", self.sfx, self.St, self.Wt, self.HtH, self.Rv, self.Gv, self.lam, N, g, k,
+                  _stream())
+        _lib.call("inmf_bpp", self.sfx, self.Gv, self.Rv, k, self.Vt, k, None, 0, self.mask_V,
+                  1 if warm else 0, self.seg_genes, N, g, k, self.bpp_stats[1], _stream())
+
+    def solve_W(self, warm=False):
+        k, g, N = self.k, self.g, self.N
+        _lib.call("inmf_rhs_w", self.sfx, self.St, self.Vt, self.HtH, self.Rw, self.Gw, N, g, k, _stream())
+        _lib.call("inmf_bpp", self.sfx, self.Gw, self.Rw, k, self.Wt, k, None, 0, self.mask_W,
+                  1 if warm else 0, self.seg_w, 1, g, k, self.bpp_stats[2], _stream())
+
+    def objective(self):
+        """Objective from the current St/HtH and the Mt/Gwv/Gvv of the last prep(). Device scalar."""
+        _lib.call("inmf_objective", self.sfx, self.St, self.Mt, self.ldm, self.HtH, self.Gwv, self.Gvv,
+                  self.xnorm2, self.lam, self.N, self.g, self.k, self.obj, _stream())
+        return self.obj
+
+    # ------------------------------------------------------------------ ALS
+    def set_als_state(self, W, V, H=None):
+        """W: k x g, V: list of k x g, H: list of n_i x k (GLOBAL rows; the local slice is taken)."""
+        dev, dt = self.device, self.dtype
+        self.Wt.copy_(torch.from_numpy(np.ascontiguousarray(np.asarray(W, dtype=np.float64).T)).to(dev, dt))
+        for i, Vi in enumerate(V):
+            self.Vt[i].copy_(torch.from_numpy(np.ascontiguousarray(np.asarray(Vi, dtype=np.float64).T)).to(dev, dt))
+        if H is not None:
+            for i, Hi in enumerate(H):
+                lo, hi = self.X.own[i]
+                b0, b1 = int(self.X.own_off[i]), int(self.X.own_off[i + 1])
+                if b1 > b0:
+                    self.H[b0:b1].copy_(torch.from_numpy(np.ascontiguousarray(
+                        np.asarray(Hi, dtype=np.float64)[lo:hi])).to(dev, dt))
+
+    def initial_objective(self):
+        """obj0 of _iNMF_ANLS.py:122-129 from the H currently in self.H (one statistics pass)."""
+        self.prep()
+        self.stats()
+        return float(self.objective().item())
+
+    def als_iteration(self, warm=False):
+        """One (H, V, W) block update + objective; returns the device scalar objective.
+
+        Requires prep() of the current W, V (done by initial_objective() / the previous iteration)."""
+        self.solve_H(mask=self.mask_H, warm=warm)
+        self.stats()
+        self.solve_V(warm=warm)
+        self.solve_W(warm=warm)
+        self.prep()
+        return self.objective()
+
+    def gather_H(self):
+        """Full H per dataset as host float64 arrays (all-gather of the row slices)."""
+        out = []
+        for i in range(self.N):
+            b0, b1 = int(self.X.own_off[i]), int(self.X.own_off[i + 1])
+            local = self.H[b0:b1].to(torch.float64)
+            if self.world == 1:
+                out.append(local.cpu().numpy())
+                continue
+            sizes = [shard_bounds(self.X.n_global[i], r, self.world) for r in range(self.world)]
+            out.append(all_gather_rows(local, [hi - lo for lo, hi in sizes], self.group).cpu().numpy())
+        return out
+
+    def host_W(self):
+        return self.Wt.to(torch.float64).cpu().numpy()
+
+    def host_V(self):
+        return [self.Vt[i].to(torch.float64).cpu().numpy() for i in range(self.N)]
+
+    def bpp_report(self):
+        s = self.bpp_stats.cpu().numpy()
+        names = ("not_converged", "factorizations", "backup_flips", "pivot_failures", "rounds_sum",
+                 "rounds_max", "columns")
+        return {which: dict(zip(names, map(int, s[r]))) for r, which in enumerate(("H", "V", "W"))}
+
+    # ------------------------------------------------------------------ online iNMF
+    def alloc_online(self, miniBatch_sizes):
+        """Buffers for the mini-batch loop (_online_iNMF.py:367-378): A/B statistics (+ the copies of
+        information older than two epochs) stacked as [previous | current] datasets."""
+        N, g, k, dev, dt = self.N, self.g, self.k, self.device, self.dtype
+        nall = self.n_prev + N
+        f64 = torch.float64
+        self.A_all = torch.zeros(nall, k, k, dtype=f64, device=dev)
+        self.B_all = torch.zeros(nall, g, k, dtype=dt, device=dev)
+        self.A = self.A_all[self.n_prev:]
+        self.B = self.B_all[self.n_prev:]
+        self.A_old = torch.zeros(N, k, k, dtype=f64, device=dev)
+        self.B_old = torch.zeros(N, g, k, dtype=dt, device=dev)
+        self.HHt = torch.zeros(N, k, k, dtype=f64, device=dev)
+        self.XHt = torch.zeros(N, g, k, dtype=dt, device=dev)
+        self.mbs = [int(m) for m in miniBatch_sizes]
+        self.sub = [shard_bounds(m, self.rank, self.world) for m in self.mbs]  # this rank's part of a batch
+        self.max_sub = max(hi - lo for lo, hi in self.sub)
+        self.H_mb = torch.zeros(max(sum(hi - lo for lo, hi in self.sub), 1), k, dtype=dt, device=dev)
+        self.inv_mb = torch.tensor([1.0 / m for m in self.mbs], dtype=f64, device=dev)
+
+    def online_plan(self, total_iters):
+        """Device seg_desc of every step (see ``online_windows``). Needs replicate=True."""
+        plan = online_windows(total_iters, self.mbs, self.sub, self.X.n_global, self.X.row_base)
+        return torch.from_numpy(plan).to(self.device)
+
+    def online_step(self, seg_desc_t, scales, rollover, n_inner):
+        """One mini-batch: H_mb by BPP, A/B update, HALS on W and V (_online_iNMF.py:416-460).
+        ``scales`` = per-dataset scale_param of _update_A_B (they only differ at iteration 1)."""
+        self.prep()
+        self.solve_H(seg_desc=seg_desc_t, max_rows=self.max_sub, out=self.H_mb)
+        self.stats(seg_desc=seg_desc_t, max_rows=self.max_sub, H=self.H_mb, St=self.XHt, HtH=self.HHt)
+        if len(set(scales)) == 1:
+            _lib.call("inmf_update_ab", self.sfx, self.A, self.A_old, self.B, self.B_old, self.HHt, self.XHt,
+                      self.inv_mb, float(scales[0]), int(rollover), self.N, self.g, self.k, _stream())
+        else:
+            for i, sc in enumerate(scales):
+                _lib.call("inmf_update_ab", self.sfx, self.A[i], self.A_old[i], self.B[i], self.B_old[i],
+                          self.HHt[i], self.XHt[i], self.inv_mb[i:i + 1], float(sc), int(rollover), 1, self.g,
+                          self.k, _stream())
+        _lib.call("inmf_hals", self.sfx, self.A_all, self.B_all, self.Wt, self.Vt_all, self.lam, self.n_prev,
+                  self.n_prev + self.N, self.g, self.k, int(n_inner), _stream())
+
+    def final_H(self, with_V=True):
+        """H for every owned cell from the final W, V (_online_iNMF.py:465-508)."""
+        self.prep(with_V=with_V)
+        self.solve_H()

@@ -1,0 +1,5 @@
+from ._iNMF_ANLS import optimize_ALS
+from ._online_iNMF import online_iNMF
+from ._utilities import nnlsm_blockpivot
+
+__all__ = ["optimize_ALS", "online_iNMF", "nnlsm_blockpivot"]

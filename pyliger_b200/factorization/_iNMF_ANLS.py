@@ -1,0 +1,101 @@
+"""optimize_ALS on B200: same signature, write-back and errors as pyliger
+(/root/reference/src/pyliger/factorization/_iNMF_ANLS.py:8-196), CUDA kernels underneath.
+
+Keyword-only extensions (defaults preserve reference behaviour):
+  dtype       "float64" (default, parity mode) or "float32" (throughput mode)
+  device      torch device (default: current CUDA device)
+  warm_start  start each BPP solve from the previous iteration's passive sets (same unique NNLS
+              solution, fewer pivoting rounds); default False = the reference's cold start
+  return_info if True, return a dict with the per-iteration objectives and solver counters
+              (the reference returns None; the default stays None)
+"""
+import numpy as np
+from tqdm import tqdm
+
+from ..engine import InmfEngine, resolve_dtype
+
+
+def _als_init_host(ns, num_genes, k, seed):
+    """Seeded init in the reference's draw order and RNG (_iNMF_ANLS.py:103-108)."""
+    np.random.seed(seed=seed)
+    W = np.abs(np.random.uniform(0, 2, (k, num_genes)))
+    V = [np.abs(np.random.uniform(0, 2, (k, num_genes))) for _ in ns]
+    H = [np.abs(np.random.uniform(0, 2, (n, k))) for n in ns]
+    return W, V, H
+
+
+def optimize_ALS(
+    liger_object,
+    k,
+    value_lambda=5.0,
+    thresh=1e-6,
+    max_iters=30,
+    nrep=1,
+    H_init=None,
+    W_init=None,
+    V_init=None,
+    rand_seed=1,
+    print_obj=False,
+    *,
+    dtype="float64",
+    device=None,
+    warm_start=False,
+    return_info=False,
+    progress=True,
+):
+    N = liger_object.num_samples
+    ns = [adata.shape[0] for adata in liger_object.adata_list]
+    num_genes = len(liger_object.var_genes)
+    X = [adata.layers["scale_data"] for adata in liger_object.adata_list]
+
+    if k >= np.min(ns):
+        raise ValueError(
+            "Select k lower than the number of cells in smallest dataset: {}".format(np.min(ns)))
+    if k >= num_genes:
+        raise ValueError(
+            "Select k lower than the number of variable genes: {}".format(len(liger_object.var_genes)))
+
+    engine = InmfEngine(X, k, value_lambda, dtype=resolve_dtype(dtype), device=device)
+    best_obj = np.inf
+    best = None
+    info = {"objectives": [], "bpp": None, "iters_run": []}
+    for j in range(nrep):
+        W, V, H = _als_init_host(ns, num_genes, k, rand_seed + j - 1)
+        if W_init is not None:
+            W = W_init
+        if V_init is not None:
+            V = V_init
+        if H_init is not None:
+            H = H_init
+        engine.set_als_state(W, V, H)
+        delta = 1
+        obj0 = engine.initial_objective()
+        objs = [obj0]
+        iters_run = 0
+        it_range = tqdm(range(max_iters)) if progress else range(max_iters)
+        for it in it_range:
+            if delta > thresh:
+                obj_prev = obj0
+                obj0 = float(engine.als_iteration(warm=warm_start and iters_run > 0).item())
+                objs.append(obj0)
+                delta = np.absolute(obj_prev - obj0) / ((obj_prev + obj0) / 2)
+                iters_run += 1
+            else:
+                continue
+        info["objectives"].append(objs)
+        info["iters_run"].append(iters_run)
+        if obj0 < best_obj:
+            best = (engine.gather_H(), engine.host_W(), engine.host_V())
+            best_obj = obj0
+        if print_obj:
+            print("Objective: {}".format(best_obj))
+    info["bpp"] = engine.bpp_report()
+    info["best_objective"] = best_obj
+
+    final_H, final_Wt, final_Vt = best
+    for i in range(N):
+        liger_object.adata_list[i].obsm["H"] = final_H[i]
+        # the reference stores transposed views of its k x g matrices (:184-185); same values here
+        liger_object.adata_list[i].varm["W"] = final_Wt
+        liger_object.adata_list[i].varm["V"] = final_Vt[i]
+    return info if return_info else None

@@ -1,0 +1,179 @@
+"""GPU: every C-ABI kernel against numpy / the oracle on seeded inputs (run with -m gpu on a B200)."""
+import numpy as np
+import pytest
+import scipy.sparse as sps
+import torch
+
+from conftest import relerr
+from oracle import inmf_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+DTYPES = [("float64", 1e-11), ("float32", 2e-5)]
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
+
+
+def _engine(mats, k, lam, dtype):
+    from pyliger_b200.engine import InmfEngine
+    return InmfEngine(mats, k, lam, dtype=dtype)
+
+
+def _rand_problem(seed, ns=(230, 170), g=90, k=7, density=0.15):
+    rng = np.random.default_rng(seed)
+    mats = [sps.random(n, g, density=density, random_state=seed + i, format="csr",
+                       data_rvs=lambda s: rng.gamma(2.0, 1.0, s)) for i, n in enumerate(ns)]
+    W = rng.uniform(0, 2, (k, g))
+    V = [rng.uniform(0, 2, (k, g)) * (rng.random((k, g)) < 0.7) for _ in ns]
+    H = [rng.uniform(0, 2, (n, k)) * (rng.random((n, k)) < 0.6) for n in ns]
+    return mats, W, V, H
+
+
+@pytest.mark.parametrize("dtype,tol", DTYPES)
+@pytest.mark.parametrize("k", [7, 33, 64])
+def test_prep_spmm_stats_objective(dev, dtype, tol, k):
+    lam = 3.5
+    mats, W, V, H = _rand_problem(k, k=k)
+    eng = _engine(mats, k, lam, dtype)
+    eng.set_als_state(W, V, H)
+    eng.prep()
+    N, g = len(mats), mats[0].shape[1]
+    for i in range(N):
+        M = W + V[i]
+        assert relerr(eng.Mt[i, :, :k].cpu().numpy(), M.T) < tol
+        assert float(eng.Mt[i, :, k:].abs().max().item() if eng.ldm > k else 0.0) == 0.0
+        assert relerr(eng.Gwv[i].cpu().numpy(), M @ M.T) < tol
+        assert relerr(eng.Gvv[i].cpu().numpy(), V[i] @ V[i].T) < tol
+        assert relerr(eng.G[i].cpu().numpy(), M @ M.T + lam * V[i] @ V[i].T) < tol
+    # statistics with the H we set
+    eng.stats()
+    for i in range(N):
+        assert relerr(eng.St[i].cpu().numpy(), np.asarray(mats[i].T.dot(H[i]))) < tol
+        assert relerr(eng.HtH[i].cpu().numpy(), H[i].T @ H[i]) < tol
+    obj = float(eng.objective().item())
+    want = orc.objective_dense(mats, H, W, V, lam)
+    assert abs(obj - want) / want < max(tol, 1e-12) * 10
+    xn = eng.xnorm2.cpu().numpy()
+    np.testing.assert_allclose(xn, [m.multiply(m).sum() for m in mats], rtol=max(tol, 1e-12))
+    # SpMM alone: R = X (W+V)'
+    from pyliger_b200 import _lib
+    from pyliger_b200.engine import _stream
+    R = torch.zeros_like(eng.H)
+    _lib.call("inmf_spmm", eng.sfx, eng.X.rowptr, eng.X.colidx, eng.X.vals, eng.Mt, eng.ldm, eng.g, R, k,
+              eng.seg_full, N, eng.max_rows_full, k, _stream())
+    want_R = np.vstack([np.asarray(mats[i].dot((W + V[i]).T)) for i in range(N)])
+    assert relerr(R.cpu().numpy(), want_R) < tol
+
+
+@pytest.mark.parametrize("dtype,tol", DTYPES)
+def test_rhs_v_w(dev, dtype, tol):
+    k, lam = 9, 5.0
+    mats, W, V, H = _rand_problem(3, k=k)
+    eng = _engine(mats, k, lam, dtype)
+    eng.set_als_state(W, V, H)
+    eng.stats()
+    from pyliger_b200 import _lib
+    from pyliger_b200.engine import _stream
+    N, g = eng.N, eng.g
+    _lib.call("inmf_rhs_v", eng.sfx, eng.St, eng.Wt, eng.HtH, eng.Rv, eng.Gv, lam, N, g, k, _stream())
+    _lib.call("inmf_rhs_w", eng.sfx, eng.St, eng.Vt, eng.HtH, eng.Rw, eng.Gw, N, g, k, _stream())
+    S = [np.asarray(mats[i].T.dot(H[i])).T for i in range(N)]
+    C = [H[i].T @ H[i] for i in range(N)]
+    for i in range(N):
+        assert relerr(eng.Rv[i].cpu().numpy(), (S[i] - C[i] @ W).T) < tol * 10
+        assert relerr(eng.Gv[i].cpu().numpy(), (1 + lam) * C[i]) < tol
+    assert relerr(eng.Rw.cpu().numpy(), sum(S[i] - C[i] @ V[i] for i in range(N)).T) < tol * 10
+    assert relerr(eng.Gw[0].cpu().numpy(), sum(C)) < tol
+
+
+@pytest.mark.parametrize("dtype,tol", DTYPES)
+def test_window_segments_wrap(dev, dtype, tol):
+    """Mini-batch windows incl. wrap-around at the end of a dataset (seg_desc semantics)."""
+    k, lam = 6, 2.0
+    mats, W, V, H = _rand_problem(5, ns=(50, 37), g=40, k=k)
+    eng = _engine(mats, k, lam, dtype)
+    eng.set_als_state(W, V, None)
+    eng.prep()
+    # dataset 0: rows 44..49,0..5 (12 rows); dataset 1: rows 30..36,0..1 (9 rows)
+    seg = torch.tensor([[0, 0, 44, 50], [12, 50, 30, 37], [21, 0, 0, 0]], dtype=torch.int64, device=dev)
+    out = torch.zeros(21, k, dtype=eng.dtype, device=dev)
+    eng.solve_H(seg_desc=seg, max_rows=12, out=out)
+    rows0 = [(44 + j) % 50 for j in range(12)]
+    rows1 = [(30 + j) % 37 for j in range(9)]
+    for i, rows, sl in ((0, rows0, slice(0, 12)), (1, rows1, slice(12, 21))):
+        M = W + V[i]
+        G = M @ M.T + lam * V[i] @ V[i].T
+        R = np.asarray(mats[i][rows].dot(M.T)).T
+        want = orc.bpp(G, R)[0].T
+        assert relerr(out[sl].cpu().numpy(), want) < max(tol * 50, 1e-9)
+    St = torch.zeros_like(eng.St)
+    HtH = torch.zeros_like(eng.HtH)
+    eng.stats(seg_desc=seg, max_rows=12, H=out, St=St, HtH=HtH)
+    Hh = out.cpu().numpy().astype(np.float64)
+    assert relerr(St[0].cpu().numpy(), np.asarray(mats[0][rows0].T.dot(Hh[:12]))) < tol * 10
+    assert relerr(St[1].cpu().numpy(), np.asarray(mats[1][rows1].T.dot(Hh[12:]))) < tol * 10
+    assert relerr(HtH[1].cpu().numpy(), Hh[12:].T @ Hh[12:]) < tol * 10
+
+
+def test_update_ab_kat6(dev, golden_online):
+    """KAT-6 of SURVEY.md App. C through the CUDA epilogue (fp64)."""
+    from pyliger_b200 import _lib
+    from pyliger_b200.engine import _stream
+    d = golden_online
+    f64 = torch.float64
+    A = torch.eye(2, dtype=f64, device=dev).reshape(1, 2, 2).clone()
+    B = torch.ones(1, 3, 2, dtype=f64, device=dev)
+    Ao = torch.zeros_like(A)
+    Bo = torch.zeros_like(B)
+    Hm = np.array([[1.0, 2], [0, 1]])
+    Xm = np.arange(6, dtype=np.float64).reshape(3, 2)
+    HHt = torch.from_numpy(Hm @ Hm.T).to(dev).reshape(1, 2, 2)
+    XHt = torch.from_numpy(Xm @ Hm.T).to(dev).reshape(1, 3, 2)
+    inv_mb = torch.tensor([0.5], dtype=f64, device=dev)
+    for s, (it, ep, epp) in enumerate(((0, 0, 0), (1, 0, 0), (2, 1, 0), (3, 1, 1))):
+        scale = 0.0 if it == 0 else (0.5 if it == 1 else (it - 1) / it)
+        roll = int(ep > 0 and ep - epp == 1)
+        _lib.call("inmf_update_ab", "f64", A, Ao, B, Bo, HHt, XHt, inv_mb, scale, roll, 1, 3, 2, _stream())
+        np.testing.assert_allclose(A[0].cpu().numpy(), d["kat6_A"][s], rtol=1e-14)
+        np.testing.assert_allclose(B[0].cpu().numpy(), d["kat6_B"][s], rtol=1e-14)
+        np.testing.assert_allclose(Ao[0].cpu().numpy(), d["kat6_Aold"][s], rtol=1e-14)
+        np.testing.assert_allclose(Bo[0].cpu().numpy(), d["kat6_Bold"][s], rtol=1e-14)
+    # exact-zero diagonal -> 1e-15
+    A.zero_(); Ao.zero_()
+    _lib.call("inmf_update_ab", "f64", A, Ao, B, Bo, torch.zeros_like(HHt), XHt, inv_mb, 0.0, 0, 1, 3, 2, _stream())
+    np.testing.assert_array_equal(A[0].cpu().numpy(), [[1e-15, 0], [0, 1e-15]])
+
+
+@pytest.mark.parametrize("dtype,tol", [("float64", 1e-11), ("float32", 5e-5)])
+def test_hals_sweep_golden(dev, golden_online, dtype, tol):
+    from pyliger_b200 import _lib
+    from pyliger_b200.engine import _stream, resolve_dtype
+    d = golden_online
+    dt = resolve_dtype(dtype)
+    A = torch.from_numpy(d["hals_A"]).to(dev)
+    B = torch.from_numpy(d["hals_B"]).to(dev, dt)
+    W = torch.from_numpy(d["hals_W0"]).to(dev, dt)
+    V = torch.from_numpy(d["hals_V0"]).to(dev, dt)
+    N, g, k = d["hals_V0"].shape
+    sfx = "f64" if dt == torch.float64 else "f32"
+    _lib.call("inmf_hals", sfx, A, B, W, V, 5.0, 0, N, g, k, 1, _stream())
+    assert relerr(W.cpu().numpy(), d["hals_W1"]) < tol
+    assert relerr(V.cpu().numpy(), d["hals_V1"]) < tol
+    # scenario-2 form: first dataset is "previous" -> its V must stay untouched, W sums still use it
+    W2 = torch.from_numpy(d["hals_W0"]).to(dev, dt)
+    V2 = torch.from_numpy(d["hals_V0"]).to(dev, dt)
+    _lib.call("inmf_hals", sfx, A, B, W2, V2, 5.0, 1, N, g, k, 1, _stream())
+    assert relerr(W2.cpu().numpy(), d["hals_W1"]) < tol
+    np.testing.assert_array_equal(V2[0].cpu().numpy(), torch.from_numpy(d["hals_V0"][0]).to(dt).numpy())
+    assert relerr(V2[1:].cpu().numpy(), d["hals_V1"][1:]) < tol
+
+
+def test_error_reporting(dev):
+    from pyliger_b200 import _lib
+    with pytest.raises(_lib.InmfError, match="k must be"):
+        _lib.call("inmf_bpp", "f32", 0, 0, 1, 0, 1, 0, 1, 0, 0, 0, 1, 1, 65, 0, 0)

@@ -1,0 +1,326 @@
+"""GPU parity tests proper: the pyliger-shaped API of pyliger_b200 (CUDA, through the C ABI) against
+(a) golden vectors produced by the unmodified reference and (b) the numpy oracle on seeded inputs.
+
+Tolerances (north star): per-iteration objective within 1e-5 relative in fp64 mode and 1e-3 in fp32
+mode; final H/W/V relative Frobenius error <= 1e-6 (fp64) / 1e-2 (fp32).  The fp64 asserts below are
+tighter than required (observed ~1e-12).
+"""
+import numpy as np
+import pytest
+import scipy.optimize
+import scipy.sparse as sps
+import torch
+
+from conftest import csr_unpack, relerr
+from oracle import inmf_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+OBJ_TOL = {"float64": 1e-9, "float32": 1e-3}
+FAC_TOL = {"float64": 1e-6, "float32": 1e-2}
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_cuda():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+
+
+def _liger(mats):
+    from pyliger_b200 import liger_from_matrices
+    return liger_from_matrices(mats)
+
+
+# ----------------------------------------------------------------------------------- nnlsm_blockpivot
+@pytest.mark.parametrize("tag", ["kat1", "kat2", "iid", "hard"])
+def test_bpp_raw_inputs_fp64(golden_bpp, tag):
+    from pyliger_b200 import nnlsm_blockpivot
+    d = golden_bpp
+    X, info = nnlsm_blockpivot(d[tag + "_A"], d[tag + "_B"])
+    ok, Y, n_chol, n_eq, n_backup = info
+    assert X.shape == d[tag + "_X"].shape and Y.shape == X.shape
+    tol = 1e-6 if tag == "hard" else 1e-9  # "hard" is ill-conditioned (cond ~ 1e7) on purpose
+    np.testing.assert_allclose(X, d[tag + "_X"], rtol=tol, atol=tol * 1e-2 * max(1.0, np.abs(d[tag + "_X"]).max()))
+    assert ok == bool(d[tag + "_info"][0])
+    if tag != "hard":
+        assert n_backup == int(d[tag + "_info"][3])
+        np.testing.assert_allclose(Y, d[tag + "_Y"], rtol=1e-7, atol=1e-9)
+        assert (X > 0).tolist() == (d[tag + "_X"] > 0).tolist()
+    G = d[tag + "_A"].T @ d[tag + "_A"]
+    R = d[tag + "_A"].T @ d[tag + "_B"]
+    assert orc.kkt_violation(G, R, X) < 1e-8
+
+
+def test_bpp_hard_case_uses_backup_rule(golden_bpp):
+    from pyliger_b200 import nnlsm_blockpivot
+    d = golden_bpp
+    X, info = nnlsm_blockpivot(d["hard_A"], d["hard_B"])
+    assert info[4] > 0 and int(d["hard_info"][3]) > 0  # both walked through the backup rule
+    agree = np.mean(np.all((X > 0) == (d["hard_X"] > 0), axis=0))
+    print("hard case: backup flips %d (reference %d), active-set agreement %.4f" % (info[4], d["hard_info"][3], agree))
+    assert agree > 0.97
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_bpp_product_inputs(golden_bpp, dtype):
+    from pyliger_b200 import nnlsm_blockpivot
+    d = golden_bpp
+    for tag in d["cases"]:
+        tag = str(tag)
+        X, info = nnlsm_blockpivot(d[tag + "_G"], d[tag + "_R"], is_input_prod=True, dtype=dtype)
+        want = d[tag + "_X"]
+        err = relerr(X, want)
+        agree = np.mean(np.all((X > 0) == (want > 0), axis=0))
+        print("%s %s: rel err %.2e, active-set agreement %.4f, backups %d" % (tag, dtype, err, agree, info[4]))
+        assert info[0] is True
+        if dtype == "float64":
+            assert err < 1e-10 and agree == 1.0
+            assert info[4] == int(d[tag + "_info"][3])
+        else:
+            assert err < 1e-4 and agree > 0.98
+
+
+def test_bpp_sparse_B_and_warm_start(golden_bpp):
+    from pyliger_b200 import nnlsm_blockpivot
+    d = golden_bpp
+    A, B = d["iid_A"], d["iid_B"]
+    Xs, _ = nnlsm_blockpivot(A, sps.csr_matrix(B))
+    np.testing.assert_allclose(Xs, d["iid_X"], rtol=1e-9, atol=1e-11)
+    Xw, infow = nnlsm_blockpivot(A, B, init=d["iid_init"])
+    np.testing.assert_allclose(Xw, d["iid_init_X"], rtol=1e-8, atol=1e-10)
+    Xc, infoc = nnlsm_blockpivot(A, B)
+    Xw2, infow2 = nnlsm_blockpivot(A, B, init=Xc)
+    np.testing.assert_allclose(Xw2, Xc, rtol=1e-10, atol=1e-12)
+    assert infow2[2] <= B.shape[1]  # a correct warm start needs exactly one factorisation per column
+    assert infoc[2] > infow2[2]
+
+
+@pytest.mark.parametrize("k", [1, 2, 20, 32, 33, 47, 64])
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_bpp_random_vs_oracle_and_kkt(k, dtype):
+    from pyliger_b200 import nnlsm_blockpivot
+    rng = np.random.default_rng(100 + k)
+    m, cols = 3 * k + 5, 777
+    A = rng.uniform(0, 1, (m, k))
+    B = rng.uniform(-0.3, 1.0, (m, cols))
+    G, R = A.T @ A, A.T @ B
+    X, info = nnlsm_blockpivot(G, R, is_input_prod=True, dtype=dtype)
+    Xo, infoo = orc.nnlsm_blockpivot(G, R, is_input_prod=True)
+    assert info[0] is True and X.shape == (k, cols)
+    assert (X >= 0).all()
+    if dtype == "float64":
+        assert relerr(X, Xo) < 1e-9
+        assert orc.kkt_violation(G, R, X) < 1e-9
+        assert info[4] == infoo[4]
+    else:
+        assert relerr(X, Xo) < 5e-3
+    for c in range(0, cols, 97):
+        ref, _ = scipy.optimize.nnls(A, B[:, c])
+        assert np.linalg.norm(X[:, c] - ref) <= (1e-8 if dtype == "float64" else 5e-3) * max(1.0, np.linalg.norm(ref))
+
+
+def test_bpp_edge_cases():
+    from pyliger_b200 import nnlsm_blockpivot
+    G = np.array([[2.0, 0.5], [0.5, 1.0]])
+    X, info = nnlsm_blockpivot(G, np.zeros((2, 0)), is_input_prod=True)
+    assert X.shape == (2, 0) and info[0] is True
+    R = -np.abs(np.random.default_rng(0).uniform(0.1, 1, (2, 5)))  # all-negative rhs -> x = 0, y = -r
+    X, info = nnlsm_blockpivot(G, R, is_input_prod=True)
+    assert np.all(X == 0) and np.allclose(info[1], -R) and info[2] == 0
+    R = np.abs(R)  # all-positive with diagonally dominant G -> unconstrained solution
+    X, info = nnlsm_blockpivot(G, R, is_input_prod=True)
+    np.testing.assert_allclose(X, np.linalg.solve(G, R), rtol=1e-12)
+    with pytest.raises(ValueError):
+        nnlsm_blockpivot(np.eye(65), np.ones((65, 2)), is_input_prod=True)
+
+
+# ----------------------------------------------------------------------------------- optimize_ALS
+def _check_als(lig, d, N, dtype):
+    assert relerr(lig.adata_list[0].varm["W"], d["W"]) < FAC_TOL[dtype]
+    for i in range(N):
+        a = lig.adata_list[i]
+        assert a.obsm["H"].dtype == np.float64 and a.obsm["H"].shape == d["H%d" % i].shape
+        assert relerr(a.obsm["H"], d["H%d" % i]) < FAC_TOL[dtype]
+        assert relerr(a.varm["V"], d["V%d" % i]) < FAC_TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+@pytest.mark.parametrize("warm", [False, True])
+def test_als_trajectory_vs_reference(golden_als, dtype, warm):
+    from pyliger_b200 import optimize_ALS
+    d = golden_als
+    k, lam, thresh, T, seed = d["params"]
+    lig = _liger([csr_unpack(d, "X0"), csr_unpack(d, "X1")])
+    info = optimize_ALS(lig, int(k), lam, thresh, int(T), rand_seed=int(seed), dtype=dtype, warm_start=warm,
+                        return_info=True, progress=False)
+    objs = np.array(info["objectives"][0])
+    rel = np.abs(objs - d["objectives"]) / d["objectives"]
+    print("ALS %s warm=%s: max rel objective error %.3e; bpp %s" % (dtype, warm, rel.max(), info["bpp"]["H"]))
+    assert rel.max() < OBJ_TOL[dtype]
+    _check_als(lig, d, 2, dtype)
+    assert info["bpp"]["H"]["not_converged"] == 0 and info["bpp"]["H"]["pivot_failures"] == 0
+    assert lig.W.shape == (csr_unpack(d, "X0").shape[1], int(k))
+
+
+def test_als_returns_none_and_prints(golden_als3, capsys):
+    from pyliger_b200 import optimize_ALS
+    d = golden_als3
+    k, lam, thresh, T, seed, nrep = d["params"]
+    lig = _liger([csr_unpack(d, "X%d" % i) for i in range(3)])
+    ret = optimize_ALS(lig, int(k), value_lambda=lam, thresh=thresh, max_iters=int(T), nrep=int(nrep),
+                       rand_seed=int(seed), print_obj=True, progress=False)
+    assert ret is None
+    out = capsys.readouterr().out
+    obj = float(out.strip().split("Objective:")[-1])
+    assert abs(obj - float(d["objective"])) / float(d["objective"]) < 1e-9
+    _check_als(lig, d, 3, "float64")
+
+
+def test_als_value_errors(golden_als):
+    from pyliger_b200 import optimize_ALS
+    lig = _liger([csr_unpack(golden_als, "X0"), csr_unpack(golden_als, "X1")])
+    with pytest.raises(ValueError, match="number of cells in smallest dataset"):
+        optimize_ALS(lig, 260)
+    with pytest.raises(ValueError, match="number of variable genes"):
+        optimize_ALS(lig, 150)
+
+
+def test_als_user_inits_and_no_early_work(golden_als):
+    """W_init/V_init/H_init take the reference layouts (k x g, n x k); a huge thresh stops work after
+    one iteration exactly like the reference's `continue` branch (_iNMF_ANLS.py:166-167)."""
+    from pyliger_b200 import optimize_ALS
+    d = golden_als
+    mats = [csr_unpack(d, "X0"), csr_unpack(d, "X1")]
+    k = 5
+    rng = np.random.default_rng(4)
+    W0 = rng.uniform(0, 2, (k, mats[0].shape[1]))
+    V0 = [rng.uniform(0, 2, (k, mats[0].shape[1])) for _ in mats]
+    H0 = [rng.uniform(0, 2, (m.shape[0], k)) for m in mats]
+    want = orc.als(mats, k, 4.0, 1e-6, 3, W_init=W0, V_init=V0, H_init=H0)
+    lig = _liger(mats)
+    info = optimize_ALS(lig, k, 4.0, 1e-6, 3, W_init=W0, V_init=V0, H_init=H0, return_info=True, progress=False)
+    np.testing.assert_allclose(info["objectives"][0], want["objectives"], rtol=1e-9)
+    assert relerr(lig.H[0], want["H"][0]) < 1e-7
+    stop = orc.als(mats, k, 4.0, 0.5, 6)
+    info = optimize_ALS(_liger(mats), k, 4.0, 0.5, 6, return_info=True, progress=False)
+    assert info["iters_run"] == [stop["iters_run"]] and 0 < stop["iters_run"] < 6
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_als_vs_oracle_medium(dtype):
+    """Seeded medium problem (k=20, C1-like proportions) against the oracle incl. active sets."""
+    from pyliger_b200 import optimize_ALS
+    from pyliger_b200.synth import make_datasets
+    mats = make_datasets([900, 700], 400, 20, density=0.10, seed0=3000)
+    k = 20
+    want = orc.als(mats, k, 5.0, 1e-6, 6, rand_seed=1)
+    lig = _liger(mats)
+    info = optimize_ALS(lig, k, 5.0, 1e-6, 6, rand_seed=1, dtype=dtype, return_info=True, progress=False)
+    rel = np.abs(np.array(info["objectives"][0]) - want["objectives"]) / np.array(want["objectives"])
+    assert rel.max() < OBJ_TOL[dtype]
+    for i in range(2):
+        assert relerr(lig.H[i], want["H"][i]) < FAC_TOL[dtype]
+        agree = np.mean(np.all((lig.H[i] > 0) == (want["H"][i] > 0), axis=1))
+        print("ALS medium %s dataset %d: H active-set agreement per cell %.4f" % (dtype, i, agree))
+        assert agree > (0.999 if dtype == "float64" else 0.9)
+    assert relerr(lig.W.T, want["W"]) < FAC_TOL[dtype]
+
+
+def test_als_large_properties():
+    """Size-independent properties at a larger shape (fp32): monotone objective, KKT of the H solve,
+    statistics-form objective == dense-residual objective of the returned factors."""
+    from pyliger_b200 import optimize_ALS
+    from pyliger_b200.synth import make_datasets
+    mats = make_datasets([6000, 5000, 4000], 1000, 30, density=0.08, structured=False, seed0=3100)
+    k, lam = 30, 5.0
+    lig = _liger(mats)
+    info = optimize_ALS(lig, k, lam, 1e-6, 5, dtype="float32", return_info=True, progress=False)
+    objs = np.array(info["objectives"][0])
+    assert np.all(np.diff(objs) < 0)
+    W = lig.W.T
+    V = [v.T for v in lig.V]
+    dense = orc.objective_dense(mats, lig.H, W, V, lam)
+    assert abs(dense - objs[-1]) / dense < 1e-4
+    assert all((h >= 0).all() for h in lig.H) and (W >= 0).all()
+    assert info["bpp"]["H"]["not_converged"] == 0
+
+
+# ----------------------------------------------------------------------------------- online_iNMF
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_online_scenario1_vs_reference(golden_online, dtype):
+    from pyliger_b200 import online_iNMF
+    d = golden_online
+    k, lam, ep, mbi, mb, chunk, seed = d["s1_params"]
+    lig = _liger([csr_unpack(d, "X0"), csr_unpack(d, "X1")])
+    ret = online_iNMF(lig, k=int(k), value_lambda=lam, max_epochs=int(ep), miniBatch_max_iters=int(mbi),
+                      miniBatch_size=int(mb), h5_chunk_size=int(chunk), rand_seed=int(seed), verbose=False,
+                      dtype=dtype)
+    assert ret is None
+    tol = 1e-7 if dtype == "float64" else 2e-2
+    assert relerr(lig.W, d["s1_W"]) < tol
+    for i, a in enumerate(lig.adata_list):
+        assert a.obsm["H"].shape == d["s1_H%d" % i].shape
+        assert relerr(a.obsm["H"], d["s1_H%d" % i]) < tol
+        assert relerr(a.varm["V"], d["s1_V%d" % i]) < tol
+        assert relerr(a.varm["B"], d["s1_B%d" % i]) < tol
+        assert relerr(a.uns["A"], d["s1_A%d" % i]) < tol
+
+
+def test_online_two_inner_iters(golden_online):
+    from pyliger_b200 import online_iNMF
+    d = golden_online
+    lig = _liger([csr_unpack(d, "X0")])
+    online_iNMF(lig, k=4, value_lambda=3.0, max_epochs=2, miniBatch_max_iters=2, miniBatch_size=100,
+                h5_chunk_size=64, rand_seed=3, verbose=False)
+    assert relerr(lig.W, d["s1b_W"]) < 1e-7
+    assert relerr(lig.H[0], d["s1b_H"]) < 1e-7
+    assert relerr(lig.adata_list[0].uns["A"], d["s1b_A"]) < 1e-7
+    assert relerr(lig.adata_list[0].varm["B"], d["s1b_B"]) < 1e-7
+
+
+def _scenario1_state(lig, d):
+    for i, a in enumerate(lig.adata_list):
+        a.obsm["H"] = d["s1_H%d" % i].copy(); a.varm["W"] = d["s1_W"].copy()
+        a.varm["V"] = d["s1_V%d" % i].copy(); a.varm["B"] = d["s1_B%d" % i].copy(); a.uns["A"] = d["s1_A%d" % i].copy()
+
+
+def test_online_scenario2_refine(golden_online):
+    from pyliger_b200 import AnnDataLike, online_iNMF
+    d = golden_online
+    lig = _liger([csr_unpack(d, "X0"), csr_unpack(d, "X1")])
+    _scenario1_state(lig, d)
+    new = AnnDataLike(csr_unpack(d, "Xnew"), "new")
+    online_iNMF(lig, X_new=[new], k=5, value_lambda=5.0, max_epochs=2, miniBatch_size=80, h5_chunk_size=100,
+                rand_seed=1, verbose=False)
+    assert len(lig.adata_list) == int(d["s2_n_datasets"]) == 3
+    assert relerr(new.varm["W"], d["s2_W"]) < 1e-7
+    assert relerr(new.obsm["H"], d["s2_Hnew"]) < 1e-7
+    assert relerr(new.varm["V"], d["s2_Vnew"]) < 1e-7
+    assert relerr(new.uns["A"], d["s2_Anew"]) < 1e-7
+    assert relerr(new.varm["B"], d["s2_Bnew"]) < 1e-7
+    for i in range(2):
+        assert relerr(lig.adata_list[i].obsm["H"], d["s2_Hold%d" % i]) < 1e-7
+        assert relerr(lig.adata_list[i].varm["W"], d["s2_W"]) < 1e-7
+
+
+def test_online_scenario3_projection(golden_online):
+    from pyliger_b200 import AnnDataLike, online_iNMF
+    d = golden_online
+    lig = _liger([csr_unpack(d, "X0"), csr_unpack(d, "X1")])
+    _scenario1_state(lig, d)
+    new = AnnDataLike(csr_unpack(d, "Xnew"), "proj")
+    online_iNMF(lig, X_new=[new], projection=True, k=5, miniBatch_size=100, verbose=False)
+    assert relerr(new.obsm["H"], d["s3_H"]) < 1e-8
+    assert np.all(new.varm["V"] == 0) and new.varm["V"].shape == d["s3_V"].shape
+    assert len(lig.adata_list) == 3
+
+
+def test_online_vs_oracle_medium_fp32():
+    from pyliger_b200 import online_iNMF
+    from pyliger_b200.synth import make_datasets
+    mats = make_datasets([3000, 2500], 500, 20, density=0.1, seed0=3200)
+    want = orc.online(mats, 20, 5.0, 2, 1, 500, 1000, 1)
+    lig = _liger(mats)
+    online_iNMF(lig, k=20, value_lambda=5.0, max_epochs=2, miniBatch_size=500, verbose=False, dtype="float32")
+    assert relerr(lig.W, want["W"]) < 2e-2
+    assert relerr(lig.H[0], want["H"][0]) < 5e-2

@@ -1,0 +1,188 @@
+"""CPU: host-side logic, the C-ABI surface (load + exported symbols, no compute), 2-rank gloo plumbing."""
+import ctypes
+import os
+import re
+import socket
+import sys
+
+import numpy as np
+import pytest
+import scipy.sparse as sps
+import torch
+
+from conftest import ROOT, csr_unpack
+from oracle import inmf_oracle as orc
+
+
+def test_library_exports_every_declared_symbol():
+    from pyliger_b200 import _lib
+    from pyliger_b200.build import build_library
+    build_library()  # no-op when up to date; nvcc cross-compiles without a GPU
+    header = open(os.path.join(ROOT, "include", "inmf_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(inmf_[a-z0-9_]+)\s*\(", header)))
+    assert len(declared) >= 24
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), "missing export %s" % name
+    assert sorted(_lib.EXPORTED_SYMBOLS) == declared
+    assert _lib.load().inmf_version() >= 100
+
+
+def test_no_cpu_fallback_without_cuda():
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    import pyliger_b200
+    from pyliger_b200._lib import InmfError
+    with pytest.raises(InmfError, match="no CPU fallback"):
+        pyliger_b200.nnlsm_blockpivot(np.eye(2), np.ones((2, 1)), is_input_prod=True)
+    lig = pyliger_b200.liger_from_matrices([sps.random(30, 10, 0.3, format="csr") for _ in range(2)])
+    with pytest.raises(InmfError):
+        pyliger_b200.optimize_ALS(lig, 3)
+    with pytest.raises(ValueError):  # argument checks come first, as in the reference
+        pyliger_b200.optimize_ALS(lig, 10)
+
+
+def test_product_path_never_imports_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "pyliger_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src, "%s mentions the oracle" % f
+
+
+def test_shard_bounds_cover():
+    from pyliger_b200.engine import shard_bounds
+    for n in (0, 1, 7, 100, 250001):
+        for world in (1, 2, 3, 8):
+            b = [shard_bounds(n, r, world) for r in range(world)]
+            assert b[0][0] == 0 and b[-1][1] == n
+            assert all(b[r][1] == b[r + 1][0] for r in range(world - 1))
+            assert max(hi - lo for lo, hi in b) - min(hi - lo for lo, hi in b) <= 1
+
+
+def test_device_csr_slicing_cpu(golden_als):
+    from pyliger_b200.engine import DeviceCSR
+    mats = [csr_unpack(golden_als, "X0"), csr_unpack(golden_als, "X1")]
+    world = 3
+    parts = [DeviceCSR(mats, torch.float64, torch.device("cpu"), r, world) for r in range(world)]
+    for i, m in enumerate(mats):
+        rows = []
+        for p in parts:
+            b0, b1 = p.row_base[i], p.row_base[i + 1]
+            ip = p.rowptr.numpy()
+            sub = sps.csr_matrix((p.vals.numpy()[ip[b0]:ip[b1]], p.colidx.numpy()[ip[b0]:ip[b1]],
+                                  ip[b0:b1 + 1] - ip[b0]), shape=(b1 - b0, m.shape[1]))
+            rows.append(sub)
+        assert abs(sps.vstack(rows) - m).max() == 0
+    rep = DeviceCSR(mats, torch.float32, torch.device("cpu"), 1, world, replicate=True)
+    assert rep.n_total == sum(m.shape[0] for m in mats) and rep.own == parts[1].own
+    assert rep.vals.dtype == torch.float32
+
+
+def test_online_windows_match_reference_row_order():
+    from pyliger_b200.engine import online_windows, shard_bounds
+    n, mb, epochs, chunk = [333, 200], [130, 78], 2, 100
+    iters = 5
+    for world in (1, 2):
+        covered = [[[] for _ in range(iters)] for _ in n]
+        for rank in range(world):
+            sub = [shard_bounds(m, rank, world) for m in mb]
+            plan = online_windows(iters, mb, sub, n, [0, n[0]])
+            for t in range(iters):
+                for i in range(2):
+                    cnt = plan[t, i + 1, 0] - plan[t, i, 0]
+                    assert cnt == sub[i][1] - sub[i][0]
+                    covered[i][t] += [int((plan[t, i, 2] + j) % plan[t, i, 3]) for j in range(cnt)]
+        for i in range(2):
+            want = orc.minibatch_rows(iters, mb[i], epochs, chunk, n[i])
+            for t in range(iters):
+                rows = [r for lo, hi in want[t] for r in range(lo, hi)]
+                assert covered[i][t] == rows
+
+
+def test_als_init_stream_matches_kat3():
+    from pyliger_b200.factorization._iNMF_ANLS import _als_init_host
+    W, V, H = _als_init_host([4, 5], 3, 2, 1 + 0 - 1)  # rand_seed=1 seeds 0 (App. B-1)
+    np.testing.assert_allclose(W, [[1.097627007855, 1.430378732745, 1.205526752143],
+                                   [1.089766365994, 0.847309598678, 1.291788226133]], rtol=1e-12)
+    Wo, Vo, Ho = orc.als_init([4, 5], 3, 2, 1)
+    np.testing.assert_array_equal(H[1], Ho[1])
+    np.testing.assert_array_equal(V[0], Vo[0])
+
+
+def test_online_init_matches_oracle(golden_online):
+    from pyliger_b200.factorization._online_iNMF import _init_V_online, _init_W
+    np.testing.assert_array_equal(_init_W(3, 2, 1), golden_online["kat4_initW"])
+    X0 = csr_unpack(golden_online, "X0")
+    np.testing.assert_allclose(_init_V_online(420, 5, X0, 100, 1), golden_online["s1_initV0"], rtol=1e-13)
+
+
+def test_pack_passive_mask():
+    from pyliger_b200.factorization._utilities import pack_passive_mask
+    init = np.zeros((64, 3))
+    init[0, 0] = 1; init[63, 0] = 2; init[5, 1] = 0.1; init[6, 1] = -1
+    m = pack_passive_mask(init).view(np.uint64)
+    assert m[0] == (1 | (1 << 63)) and m[1] == (1 << 5) and m[2] == 0
+
+
+# ------------------------------------------------------------------------------------------ gloo
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from pyliger_b200.engine import DeviceCSR, all_gather_rows, shard_bounds
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(0)
+        mats = [sps.random(n, 23, density=0.3, random_state=7 + i, format="csr") for i, n in enumerate((41, 30, 5))]
+        k = 4
+        H = [rng.uniform(0, 1, (m.shape[0], k)) for m in mats]
+        part = DeviceCSR(mats, torch.float64, torch.device("cpu"), rank, world)
+        ip = part.rowptr.numpy()
+        St = torch.zeros(len(mats), 23, k, dtype=torch.float64)
+        HtH = torch.zeros(len(mats), k, k, dtype=torch.float64)
+        gathered = []
+        for i, m in enumerate(mats):
+            b0, b1 = part.row_base[i], part.row_base[i + 1]
+            lo, hi = part.own[i]
+            sub = sps.csr_matrix((part.vals.numpy()[ip[b0]:ip[b1]], part.colidx.numpy()[ip[b0]:ip[b1]],
+                                  ip[b0:b1 + 1] - ip[b0]), shape=(b1 - b0, 23))
+            Hl = H[i][lo:hi]
+            St[i] = torch.from_numpy(np.asarray(sub.T.dot(Hl)))
+            HtH[i] = torch.from_numpy(Hl.T @ Hl)
+            counts = [shard_bounds(m.shape[0], r, world)[1] - shard_bounds(m.shape[0], r, world)[0] for r in range(world)]
+            gathered.append(all_gather_rows(torch.from_numpy(Hl.copy()), counts).numpy())
+        dist.all_reduce(St)
+        dist.all_reduce(HtH)
+        ok = True
+        for i, m in enumerate(mats):
+            ok &= np.allclose(St[i].numpy(), np.asarray(m.T.dot(H[i])), rtol=1e-12)
+            ok &= np.allclose(HtH[i].numpy(), H[i].T @ H[i], rtol=1e-12)
+            ok &= np.array_equal(gathered[i], H[i])
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_statistics_and_gather():
+    """world_size 2 over gloo: row-sharded statistics all-reduce to the full ones; ragged H gather."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(res) == [(0, True), (1, True)]
