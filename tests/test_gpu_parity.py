@@ -127,7 +127,7 @@ def test_bpp_edge_cases():
     R = -np.abs(np.random.default_rng(0).uniform(0.1, 1, (2, 5)))  # all-negative rhs -> x = 0, y = -r
     X, info = nnlsm_blockpivot(G, R, is_input_prod=True)
     assert np.all(X == 0) and np.allclose(info[1], -R) and info[2] == 0
-    R = np.abs(R)  # all-positive with diagonally dominant G -> unconstrained solution
+    R = G @ np.abs(R)  # interior solution -> equals the unconstrained one
     X, info = nnlsm_blockpivot(G, R, is_input_prod=True)
     np.testing.assert_allclose(X, np.linalg.solve(G, R), rtol=1e-12)
     with pytest.raises(ValueError):
