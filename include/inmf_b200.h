@@ -42,6 +42,8 @@ extern "C" {
 
 int32_t inmf_version(void);
 const char* inmf_last_error(void);
+/* Number of kernels this library has launched since it was loaded (host-side counter). */
+int64_t inmf_launch_count(void);
 
 /* Batched block-principal-pivoting NNLS; one problem per column, G shared per segment.
  * Replaces nnlsm_blockpivot + normal_eq_comb (_utilities.py:181-358) for all six call sites

@@ -27,7 +27,7 @@ _TYPED = {
     "inmf_normal_eq": [_PTR, _PTR, _I64, _I32, _I64, _PTR, _PTR, _PTR],
 }
 
-EXPORTED_SYMBOLS = ["inmf_version", "inmf_last_error"] + [
+EXPORTED_SYMBOLS = ["inmf_version", "inmf_last_error", "inmf_launch_count"] + [
     "%s_%s" % (n, t) for n in _TYPED for t in ("f32", "f64")
 ]
 
@@ -52,6 +52,8 @@ def load():
     lib.inmf_version.argtypes = []
     lib.inmf_last_error.restype = _c.c_char_p
     lib.inmf_last_error.argtypes = []
+    lib.inmf_launch_count.restype = _I64
+    lib.inmf_launch_count.argtypes = []
     for name, argtypes in _TYPED.items():
         for suffix in ("f32", "f64"):
             fn = getattr(lib, "%s_%s" % (name, suffix))
@@ -79,3 +81,8 @@ def call(name, suffix, *args):
     if rc != 0:
         raise InmfError("%s_%s failed (%d): %s" % (name, suffix, rc, lib.inmf_last_error().decode()))
     return rc
+
+
+def launch_count():
+    """Kernels launched by libinmf_b200.so so far in this process."""
+    return int(load().inmf_launch_count())

@@ -29,7 +29,12 @@ extern thread_local char g_inmf_err[512];
         }                                                                                       \
     } while (0)
 
-#define INMF_LAUNCH_CHECK() INMF_CUDA_CHECK(cudaGetLastError())
+extern long long g_inmf_launches;  // kernels launched by this library (host-side count)
+#define INMF_LAUNCH_CHECK()                      \
+    do {                                         \
+        __atomic_add_fetch(&g_inmf_launches, 1, __ATOMIC_RELAXED); \
+        INMF_CUDA_CHECK(cudaGetLastError());     \
+    } while (0)
 
 static inline int inmf_num_sms() {
     static int sms = 0;

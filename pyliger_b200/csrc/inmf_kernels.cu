@@ -5,7 +5,10 @@
 
 thread_local char g_inmf_err[512] = "";
 
+long long g_inmf_launches = 0;
+
 extern "C" int32_t inmf_version(void) { return 100; }
+extern "C" int64_t inmf_launch_count(void) { return (int64_t)__atomic_load_n(&g_inmf_launches, __ATOMIC_RELAXED); }
 extern "C" const char* inmf_last_error(void) { return g_inmf_err; }
 
 // =================================================================================================

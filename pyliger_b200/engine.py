@@ -78,13 +78,17 @@ def online_windows(total_iters, mbs, sub, n_global, row_base):
 class DeviceCSR(object):
     """All datasets' (local row slices of) scale_data concatenated by rows on the device."""
 
-    def __init__(self, mats, dtype, device, rank=0, world=1, pin=False, replicate=False):
+    def __init__(self, mats, dtype, device, rank=0, world=1, pin=False, replicate=False, presharded=False):
         self.N = len(mats)
         self.g = int(mats[0].shape[1])
         self.n_global = [int(m.shape[0]) for m in mats]
-        # own[i]    = global rows whose H this rank computes (always a 1/world slice)
-        # bounds[i] = global rows resident on this rank (== own, or everything when replicated)
-        self.own = [shard_bounds(n, rank, world) for n in self.n_global]
+        self.presharded = bool(presharded)
+        # own[i]    = rows (of the matrices passed in) whose H this rank computes
+        # bounds[i] = rows resident on this rank (== own, or everything when replicated)
+        if presharded:  # every rank was handed only its own cells: take them all
+            self.own = [(0, n) for n in self.n_global]
+        else:
+            self.own = [shard_bounds(n, rank, world) for n in self.n_global]
         self.bounds = [(0, n) for n in self.n_global] if replicate else list(self.own)
         self.n_local = [hi - lo for lo, hi in self.bounds]
         self.n_own = [hi - lo for lo, hi in self.own]
@@ -122,7 +126,7 @@ class InmfEngine(object):
     """Buffers + step functions shared by optimize_ALS and online_iNMF."""
 
     def __init__(self, mats, k, value_lambda, dtype=torch.float64, device=None, group=None, pin=False,
-                 replicate=False, n_prev=0):
+                 replicate=False, n_prev=0, presharded=False):
         self.device = require_cuda(device)
         self.dtype = resolve_dtype(dtype)
         self.sfx = _SUFFIX[self.dtype]
@@ -139,7 +143,7 @@ class InmfEngine(object):
         self.n_prev = int(n_prev)
         with torch.cuda.device(self.device):
             self.X = DeviceCSR(mats, self.dtype, self.device, self.rank, self.world, pin=pin,
-                               replicate=replicate)
+                               replicate=replicate, presharded=presharded)
             self._alloc()
 
     # ------------------------------------------------------------------ buffers
@@ -185,7 +189,7 @@ class InmfEngine(object):
         self.seg_w = torch.tensor([0, g], dtype=torch.int64, device=dev)
         _lib.call("inmf_sqnorm", self.sfx, X.rowptr, X.vals, torch.from_numpy(whole).to(dev), N, self.xnorm2,
                   _stream())
-        if X.bounds == X.own:
+        if X.bounds == X.own and (self.world > 1):
             self._allreduce(self.xnorm2)
 
     def _allreduce(self, *tensors):
@@ -287,7 +291,7 @@ class InmfEngine(object):
         for i in range(self.N):
             b0, b1 = int(self.X.own_off[i]), int(self.X.own_off[i + 1])
             local = self.H[b0:b1].to(torch.float64)
-            if self.world == 1:
+            if self.world == 1 or self.X.presharded:
                 out.append(local.cpu().numpy())
                 continue
             sizes = [shard_bounds(self.X.n_global[i], r, self.world) for r in range(self.world)]

@@ -8,6 +8,12 @@ Keyword-only extensions (defaults preserve reference behaviour):
               solution, fewer pivoting rounds); default False = the reference's cold start
   return_info if True, return a dict with the per-iteration objectives and solver counters
               (the reference returns None; the default stays None)
+  presharded  multi-GPU only (one process per GPU under torchrun): if True every process passes ONLY
+              its own cells of each dataset (H is written back for those cells); if False every process
+              passes the full datasets and works on its 1/world row slice, and the full H is gathered.
+
+Multi-GPU: when torch.distributed is initialised the cells are sharded over the ranks and the k x k
+and genes x k statistics are all-reduced once per iteration.
 """
 import numpy as np
 from tqdm import tqdm
@@ -15,11 +21,15 @@ from tqdm import tqdm
 from ..engine import InmfEngine, resolve_dtype
 
 
-def _als_init_host(ns, num_genes, k, seed):
-    """Seeded init in the reference's draw order and RNG (_iNMF_ANLS.py:103-108)."""
+def _als_init_host(ns, num_genes, k, seed, h_stream=None):
+    """Seeded init in the reference's draw order and RNG (_iNMF_ANLS.py:103-108).
+    ``h_stream``: pre-sharded multi-GPU runs draw their local H from a per-rank stream (W and V must be
+    identical on every rank; H only enters the initial objective, App. B-17)."""
     np.random.seed(seed=seed)
     W = np.abs(np.random.uniform(0, 2, (k, num_genes)))
     V = [np.abs(np.random.uniform(0, 2, (k, num_genes))) for _ in ns]
+    if h_stream is not None:
+        np.random.seed(seed=(seed + 7919 * (h_stream + 1)) % (2 ** 32))
     H = [np.abs(np.random.uniform(0, 2, (n, k))) for n in ns]
     return W, V, H
 
@@ -42,6 +52,7 @@ def optimize_ALS(
     warm_start=False,
     return_info=False,
     progress=True,
+    presharded=False,
 ):
     N = liger_object.num_samples
     ns = [adata.shape[0] for adata in liger_object.adata_list]
@@ -55,12 +66,13 @@ def optimize_ALS(
         raise ValueError(
             "Select k lower than the number of variable genes: {}".format(len(liger_object.var_genes)))
 
-    engine = InmfEngine(X, k, value_lambda, dtype=resolve_dtype(dtype), device=device)
+    engine = InmfEngine(X, k, value_lambda, dtype=resolve_dtype(dtype), device=device, presharded=presharded)
     best_obj = np.inf
     best = None
     info = {"objectives": [], "bpp": None, "iters_run": []}
     for j in range(nrep):
-        W, V, H = _als_init_host(ns, num_genes, k, rand_seed + j - 1)
+        W, V, H = _als_init_host(ns, num_genes, k, rand_seed + j - 1,
+                                 h_stream=engine.rank if (presharded and engine.world > 1) else None)
         if W_init is not None:
             W = W_init
         if V_init is not None:

@@ -93,3 +93,38 @@ def make_datasets(ns, g, k_true, density=0.08, structured=True, seed0=1000):
         else:
             counts.append(_iid_counts_fast(int(n), g, density, rng))
     return scale_like_pyliger(counts)
+
+
+def make_datasets_device(ns, g, k_true, density=0.08, seed0=1000, device="cuda", chunk=16384):
+    """Same structured generator as ``make_datasets`` but the Gamma/Poisson draws run on the GPU with
+    torch's RNG (seconds instead of a minute at 4 x 50k x 3k); scaling is the same host code.
+    Different random stream than the numpy generator, same distribution."""
+    import torch
+
+    dev = torch.device(device)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(int(seed0) - 1)
+
+    def gamma_half(shape):
+        # Gamma(1/2, 1) = N(0,1)^2 / 2
+        return torch.randn(shape, device=dev, dtype=torch.float32, generator=gen).square_().mul_(0.5)
+
+    W_star = gamma_half((k_true, g))
+    counts = []
+    for i, n in enumerate(ns):
+        gen.manual_seed(int(seed0) + i)
+        M = W_star + 0.3 * gamma_half((k_true, g))
+        Hs = gamma_half((2048, k_true))
+        s = _depth_for_density((Hs @ M).double().cpu().numpy(), density)
+        rows, cols, vals = [], [], []
+        for lo in range(0, int(n), chunk):
+            m = min(chunk, int(n) - lo)
+            rate = (gamma_half((m, k_true)) @ M).mul_(float(s))
+            C = torch.poisson(rate, generator=gen)
+            nz = C.nonzero(as_tuple=True)
+            rows.append((nz[0] + lo).cpu().numpy())
+            cols.append(nz[1].to(torch.int32).cpu().numpy())
+            vals.append(C[nz].double().cpu().numpy())
+        counts.append(sps.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))),
+                                     shape=(int(n), g)))
+    return scale_like_pyliger(counts)
