@@ -249,16 +249,12 @@ def main():
     phases = ["spmm", "bpp_H", "stats", "solve_V", "solve_W", "prep", "objective"]
     acc = {p: 0.0 for p in phases}
     reps = 5
-    from pyliger_b200.engine import _stream
     for _ in range(reps):
         evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(phases) + 1)]
-        X = eng.X
         evs[0].record()
-        _lib.call("inmf_spmm", eng.sfx, X.rowptr, X.colidx, X.vals, eng.Mt, eng.ldm, eng.g, eng.H, k, eng.seg_full,
-                  eng.N, eng.max_rows_full, k, _stream())
+        eng.rhs_H()
         evs[1].record()
-        _lib.call("inmf_bpp", eng.sfx, eng.G, eng.H, k, eng.H, k, None, 0, eng.mask_H, int(bool(args.warm_start)),
-                  eng.seg_full[:, 0].contiguous(), eng.N, eng.max_rows_full, k, eng.bpp_stats[0], _stream())
+        eng.bpp_H(mask=eng.mask_H, warm=bool(args.warm_start))
         evs[2].record()
         eng.stats()
         evs[3].record()

@@ -82,6 +82,26 @@ int32_t inmf_spmm_f64(const int64_t* rowptr, const int32_t* colidx, const double
                       int64_t ldm, int64_t g, double* R, int64_t ldr, const int64_t* seg_desc,
                       int32_t nseg, int64_t max_seg_rows, int32_t k, void* stream);
 
+/* Blocked form of the two X-streaming passes (the optimised hot kernels; same maths as inmf_spmm /
+ * inmf_stats for whole datasets).  X is stored a second and third time as packed (index, value) pairs
+ * -- f32: {int32 idx, float val} (8 B), f64: {int64 idx, double val} (16 B) -- grouped so that the
+ * gathered dense operand of a CTA is one shared-memory tile:
+ *   pass 1  pairs sorted by (dataset, gene block, cell, gene), idx = gene - block start,
+ *           dense = Mt (rows = genes), out = R/H rows (ACCUMULATED: caller zeroes)
+ *   pass 2  pairs sorted by (dataset, cell block, gene, cell), idx = cell - block start,
+ *           dense = H (rows = cells, leading dimension kp), out = St rows (accumulated), and
+ *           gram_out[seg] (k x k double) += tile'tile for work items with gram_seg >= 0
+ * work: device int64[nwork][8] = {ptr_base, dense_row0, tile_rows, row_begin, row_end, out_row_base,
+ * gram_seg, 0}: the CTA loads dense rows [dense_row0, +tile_rows) (leading dimension kp, TMA bulk copy)
+ * and, for r in [row_begin, row_end), adds sum_{q in [ptr[ptr_base+r], ptr[ptr_base+r+1])}
+ * val_q * tile[idx_q, :] to out[(out_row_base + r) * ldo + 0..k). */
+int32_t inmf_blocked_spmm_f32(const int64_t* work, int32_t nwork, const int64_t* ptr, const void* pairs,
+                              const float* dense, int32_t kp, float* out, int64_t ldo, int32_t k,
+                              int32_t max_tile_rows, double* gram_out, void* stream);
+int32_t inmf_blocked_spmm_f64(const int64_t* work, int32_t nwork, const int64_t* ptr, const void* pairs,
+                              const double* dense, int32_t kp, double* out, int64_t ldo, int32_t k,
+                              int32_t max_tile_rows, double* gram_out, void* stream);
+
 /* Sufficient statistics of one pass over the cells (accumulating; caller zeroes):
  *   St[s] (g x k) += sum_q X[row(q), :]' H[q, :],   HtH[s] (k x k, double) += sum_q H[q,:]' H[q,:]
  * Replaces the dense X - H@W / vstack products of _iNMF_ANLS.py:144-152 and the H H', X H' of

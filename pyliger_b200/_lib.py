@@ -25,6 +25,7 @@ _TYPED = {
     "inmf_update_ab": [_PTR, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR, _F64, _I32, _I32, _I64, _I32, _PTR],
     "inmf_hals": [_PTR, _PTR, _PTR, _PTR, _F64, _I32, _I32, _I64, _I32, _I32, _PTR],
     "inmf_normal_eq": [_PTR, _PTR, _I64, _I32, _I64, _PTR, _PTR, _PTR],
+    "inmf_blocked_spmm": [_PTR, _I32, _PTR, _PTR, _PTR, _I32, _PTR, _I64, _I32, _I32, _PTR, _PTR],
 }
 
 EXPORTED_SYMBOLS = ["inmf_version", "inmf_last_error", "inmf_launch_count"] + [

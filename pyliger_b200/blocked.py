@@ -1,0 +1,141 @@
+"""Blocked device copies of X for the two streaming passes (see csrc/blocked.cuh).
+
+Built once per factorisation from the device CSR with torch sort / bincount / cumsum (plumbing only; the
+arithmetic passes over these structures are libinmf_b200.so kernels).
+
+pass 1  "gene-blocked CSR":  pairs ordered by (dataset, gene block, cell, gene);  tile = rows of Mt
+pass 2  "cell-blocked CSC":  pairs ordered by (dataset, cell block, gene, cell);  tile = rows of H
+"""
+import numpy as np
+import torch
+
+WORK_FIELDS = 8
+SMEM_BUDGET = 227 * 1024 - 128 - 2048
+
+
+def tile_cap_rows(kp, esize):
+    return SMEM_BUDGET // (kp * esize)
+
+
+def _pack_pairs(idx_local, vals):
+    """(int idx, T val) -> packed pairs: f32 {int32, float32} = int32[nnz, 2]; f64 {int64, float64}."""
+    if vals.dtype == torch.float32:
+        out = torch.empty(idx_local.numel(), 2, dtype=torch.int32, device=vals.device)
+        out[:, 0] = idx_local.to(torch.int32)
+        out[:, 1] = vals.view(torch.int32)
+    else:
+        out = torch.empty(idx_local.numel(), 2, dtype=torch.int64, device=vals.device)
+        out[:, 0] = idx_local.to(torch.int64)
+        out[:, 1] = vals.view(torch.int64)
+    return out
+
+
+class BlockedPass(object):
+    __slots__ = ("work", "nwork", "ptr", "pairs", "max_tile_rows")
+
+
+def _own_nnz(X):
+    """Per-nnz (own_row, col, val) of the rows this rank owns, in CSR order. own_row indexes the
+    concatenated owned rows (the H buffer)."""
+    dev = X.rowptr.device
+    rows, cols, vals = [], [], []
+    for s in range(X.N):
+        r0 = int(X.row_base[s]) + (X.own[s][0] - X.bounds[s][0])
+        n = X.n_own[s]
+        if n == 0:
+            continue
+        rp = X.rowptr[r0:r0 + n + 1]
+        p0, p1 = int(rp[0].item()), int(rp[-1].item())
+        counts = rp[1:] - rp[:-1]
+        rows.append(torch.repeat_interleave(torch.arange(n, device=dev, dtype=torch.int64) + int(X.own_off[s]), counts))
+        cols.append(X.colidx[p0:p1])
+        vals.append(X.vals[p0:p1])
+    if not rows:
+        z = torch.zeros(0, dtype=torch.int64, device=dev)
+        return z, torch.zeros(0, dtype=torch.int32, device=dev), X.vals[:0]
+    return torch.cat(rows), torch.cat(cols), torch.cat(vals)
+
+
+def build_pass1(X, kp, esize, n_sms):
+    """Gene-blocked CSR over the owned cells."""
+    dev = X.rowptr.device
+    g, N = X.g, X.N
+    cap = tile_cap_rows(kp, esize)
+    NB = max(1, -(-g // cap))
+    gbs = -(-g // NB)
+    own_row, col, val = _own_nnz(X)
+    own_off = torch.from_numpy(np.asarray(X.own_off, dtype=np.int64)).to(dev)
+    n_own = torch.from_numpy(np.asarray(X.n_own, dtype=np.int64)).to(dev)
+    seg = torch.bucketize(own_row, own_off[1:], right=True)
+    gb = (col.to(torch.int64) // gbs)
+    local_row = own_row - own_off[seg]
+    cidx = NB * own_off[seg] + gb * n_own[seg] + local_row
+    order = torch.sort(cidx, stable=True)[1]
+    n_tot = X.n_own_total
+    ptr = torch.zeros(NB * n_tot + 1, dtype=torch.int64, device=dev)
+    if cidx.numel():
+        ptr[1:] = torch.cumsum(torch.bincount(cidx, minlength=NB * n_tot), 0)
+    idx_local = (col.to(torch.int64) - gb * gbs)[order]
+    bp = BlockedPass()
+    bp.pairs = _pack_pairs(idx_local, val[order])
+    bp.ptr = ptr
+    chunks = max(1, n_sms // max(1, N * NB))
+    work = []
+    for s in range(N):
+        n = X.n_own[s]
+        if n == 0:
+            continue
+        per = -(-n // chunks)
+        for b in range(NB):
+            rows_b = min(gbs, g - b * gbs)
+            if rows_b <= 0:
+                continue
+            for lo in range(0, n, per):
+                work.append([NB * int(X.own_off[s]) + b * n, s * g + b * gbs, rows_b, lo, min(n, lo + per),
+                             int(X.own_off[s]), -1, 0])
+    bp.nwork = len(work)
+    bp.work = torch.tensor(work if work else [[0] * WORK_FIELDS], dtype=torch.int64, device=dev)
+    bp.max_tile_rows = min(gbs, g)
+    return bp
+
+
+def build_pass2(X, kp, esize, n_sms):
+    """Cell-blocked CSC over the owned cells."""
+    dev = X.rowptr.device
+    g, N = X.g, X.N
+    cap = tile_cap_rows(kp, esize)
+    n_tot = max(1, X.n_own_total)
+    nb = [0 if n == 0 else max(-(-n // cap), int(round(n / n_tot * n_sms))) for n in X.n_own]
+    cbs = [1 if b == 0 else -(-n // b) for n, b in zip(X.n_own, nb)]
+    nb = [0 if n == 0 else -(-n // c) for n, c in zip(X.n_own, cbs)]
+    blk_off = np.concatenate([[0], np.cumsum(nb)]).astype(np.int64)
+    total_blocks = int(blk_off[-1])
+    own_row, col, val = _own_nnz(X)
+    own_off = torch.from_numpy(np.asarray(X.own_off, dtype=np.int64)).to(dev)
+    seg = torch.bucketize(own_row, own_off[1:], right=True)
+    local_row = own_row - own_off[seg]
+    cbs_t = torch.tensor(cbs, dtype=torch.int64, device=dev)
+    blk_off_t = torch.from_numpy(blk_off).to(dev)
+    cb = local_row // cbs_t[seg]
+    cidx = (blk_off_t[seg] + cb) * g + col.to(torch.int64)
+    order = torch.sort(cidx, stable=True)[1]
+    ptr = torch.zeros(g * total_blocks + 1, dtype=torch.int64, device=dev)
+    if cidx.numel():
+        ptr[1:] = torch.cumsum(torch.bincount(cidx, minlength=g * total_blocks), 0)
+    idx_local = (local_row - cb * cbs_t[seg])[order]
+    bp = BlockedPass()
+    bp.pairs = _pack_pairs(idx_local, val[order])
+    bp.ptr = ptr
+    chunks = max(1, n_sms // max(1, total_blocks))
+    per = -(-g // chunks)
+    work = []
+    for s in range(N):
+        for b in range(nb[s]):
+            rows_b = min(cbs[s], X.n_own[s] - b * cbs[s])
+            for ci, lo in enumerate(range(0, g, per)):
+                work.append([g * (int(blk_off[s]) + b), int(X.own_off[s]) + b * cbs[s], rows_b, lo, min(g, lo + per),
+                             s * g, s if ci == 0 else -1, 0])
+    bp.nwork = len(work)
+    bp.work = torch.tensor(work if work else [[0] * WORK_FIELDS], dtype=torch.int64, device=dev)
+    bp.max_tile_rows = max(cbs) if cbs else 1
+    return bp

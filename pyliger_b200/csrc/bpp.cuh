@@ -5,40 +5,77 @@
 // _utilities.py:341-357, is only a CPU cost optimisation), so one warp owns one column:
 //   * the passive set is a 64-bit mask held uniformly by the warp (k <= 64),
 //   * infeasible indices are found with __ballot_sync,
-//   * the passive-set system G_PP z = r_P is solved by a left-looking Cholesky on the compacted
-//     (p+1) x p augmented matrix [G_PP ; r_P'] kept in a per-warp shared-memory scratch, the extra
-//     row giving the forward substitution for free; back substitution is right-looking,
+//   * the passive-set system G_PP z = r_P is solved by a left-looking Cholesky of the compacted
+//     augmented matrix [G_PP ; r_P'] (the extra row is the forward substitution, for free):
+//       - fast path (|P| <= 31): lane i keeps row i of L in REGISTERS (fully unrolled), the pivot
+//         row is broadcast from a per-warp shared copy with 128-bit loads, back substitution is
+//         right-looking with one shuffle per step;
+//       - general path (|P| up to 64): L lives in the per-warp shared scratch.
 //   * y = G x - r is formed for the non-passive rows from the shared copy of G.
 // The reference solves with LAPACK LU (numpy.linalg.solve); for symmetric positive definite G_PP the
 // Cholesky solution is the same up to round-off.
+//
+// Zero thresholds: the reference zeroes |x|, |y| < 1e-16 (_utilities.py:290,292).  That is kept
+// verbatim for T = double.  For T = float the same absolute constant is meaningless, so values
+// within a few ulps of the terms they were summed from are treated as zero (see zero_x / zero_y);
+// without it near-degenerate columns cycle until the 5k round limit.
 #pragma once
 #include "inmf_common.cuh"
 
+#define BPP_FAST_MAX_P 31
+
+template <typename T>
+struct BppTraits;
+template <>
+struct BppTraits<float> {
+    static constexpr int VEC = 4;
+    static constexpr int LDL_FAST = 36;  // 32 + 4: 16-byte aligned rows, 4-way (not 32-way) column stores
+    typedef float4 Vec;
+    __device__ static __forceinline__ float rel_tol() { return 9.5367431640625e-7f; }  // 16 ulp
+};
+template <>
+struct BppTraits<double> {
+    static constexpr int VEC = 2;
+    static constexpr int LDL_FAST = 34;
+    typedef double2 Vec;
+    __device__ static __forceinline__ double rel_tol() { return 0.0; }  // reference behaviour: absolute 1e-16 only
+};
+
 template <typename T>
 struct BppWarpScratch {
-    T* L;          // (k+1) x ldl
+    T* L;          // max((k+1) x ldl, 32 x LDL_FAST)
     T* r;          // k   right-hand side of this column
-    T* z;          // k   compacted solution (thresholded)
-    T* dinv;       // k   1 / L[c][c]
+    T* z;          // k   compacted solution (general path)
+    T* dinv;       // k   1 / L[c][c]         (general path)
     uint8_t* idx;  // 64  compacted position -> factor index
-    int ldl;
+    int ldl;       // general-path leading dimension
 };
 
 template <typename T>
 __host__ __device__ inline size_t bpp_warp_scratch_elems(int k) {
-    int ldl = k | 1;
-    return (size_t)(k + 1) * ldl + 3 * (size_t)k + 64 / sizeof(T) + 2;
+    const int ldl = k | 1;
+    size_t l_elems = (size_t)(k + 1) * ldl;
+    const size_t fast = (size_t)32 * BppTraits<T>::LDL_FAST;
+    if (l_elems < fast) l_elems = fast;
+    l_elems = (l_elems + 3) & ~(size_t)3;
+    size_t total = l_elems + 3 * (size_t)((k + 3) & ~3) + 64 / sizeof(T);
+    return (total + 3) & ~(size_t)3;
 }
 
 template <typename T>
 __device__ __forceinline__ BppWarpScratch<T> bpp_carve(T* base, int k) {
     BppWarpScratch<T> s;
     s.ldl = k | 1;
+    size_t l_elems = (size_t)(k + 1) * s.ldl;
+    const size_t fast = (size_t)32 * BppTraits<T>::LDL_FAST;
+    if (l_elems < fast) l_elems = fast;
+    l_elems = (l_elems + 3) & ~(size_t)3;
+    const int kp = (k + 3) & ~3;
     s.L = base;
-    s.r = s.L + (size_t)(k + 1) * s.ldl;
-    s.z = s.r + k;
-    s.dinv = s.z + k;
-    s.idx = reinterpret_cast<uint8_t*>(s.dinv + k);
+    s.r = s.L + l_elems;
+    s.z = s.r + kp;
+    s.dinv = s.z + kp;
+    s.idx = reinterpret_cast<uint8_t*>(s.dinv + kp);
     return s;
 }
 
@@ -52,27 +89,150 @@ struct BppCounters {
 
 __device__ __forceinline__ bool mask_bit(uint64_t m, int j) { return (m >> j) & 1ull; }
 
-// Solve G_PP z = r_P for the warp's column and update x (lane j, j+32), y.  P != 0 required.
+// x: solution component, scale: largest |z| of the column's solve
 template <typename T>
-__device__ __forceinline__ void bpp_solve_passive(const T* __restrict__ Gs, int ldg, BppWarpScratch<T>& sc,
-                                                  int k, uint64_t P, T r0, T r1, T& x0, T& x1, T& y0,
-                                                  T& y1, BppCounters& cnt) {
+__device__ __forceinline__ T zero_x(T x, T scale) {
+    return (inmf_abs(x) < T(1e-16) || inmf_abs(x) <= BppTraits<T>::rel_tol() * scale) ? T(0) : x;
+}
+// y = a - r with a = (G x)_j
+template <typename T>
+__device__ __forceinline__ T zero_y(T a, T r) {
+    const T y = a - r;
+    return (inmf_abs(y) < T(1e-16) || inmf_abs(y) <= BppTraits<T>::rel_tol() * (inmf_abs(a) + inmf_abs(r))) ? T(0) : y;
+}
+
+template <typename T>
+__device__ __forceinline__ T warp_max(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const T t = __shfl_xor_sync(INMF_FULL_MASK, v, o);
+        v = t > v ? t : v;
+    }
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fast path: |P| = p <= 31.  Lane i owns compacted row i (i < p: G_PP row, i == p: the r_P row).
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ void bpp_solve_passive_fast(const T* __restrict__ Gs, int ldg, BppWarpScratch<T>& sc,
+                                                       int k, uint64_t P, int p, T r0, T r1, T& x0, T& x1, T& y0,
+                                                       T& y1, BppCounters& cnt) {
+    typedef BppTraits<T> TR;
+    typedef typename TR::Vec Vec;
+    constexpr int VEC = TR::VEC;
+    constexpr int LDL = TR::LDL_FAST;
     const int lane = threadIdx.x & 31;
     const int j0 = lane, j1 = lane + 32;
     const bool has0 = j0 < k, has1 = j1 < k;
-    const int p = __popcll(P);
-    const int ldl = sc.ldl;
-    const uint64_t below0 = (1ull << j0) - 1ull;
-    const uint64_t below1 = (1ull << j1) - 1ull;
     const bool pas0 = has0 && mask_bit(P, j0);
     const bool pas1 = has1 && mask_bit(P, j1);
-    const int pos0 = __popcll(P & below0);
-    const int pos1 = __popcll(P & below1);
+    const int pos0 = __popcll(P & ((1ull << j0) - 1ull));
+    const int pos1 = __popcll(P & ((1ull << j1) - 1ull));
+    if (pas0) sc.idx[pos0] = (uint8_t)j0;
+    if (pas1) sc.idx[pos1] = (uint8_t)j1;
+    __syncwarp();
+    const int myidx = (lane < p) ? (int)sc.idx[lane] : 0;
+    const T* __restrict__ Grow = Gs + myidx * ldg;
+    const T* __restrict__ rsh = sc.r;
+    T* __restrict__ Ls = sc.L;
+    T* __restrict__ Lmine = Ls + lane * LDL;
+    const bool is_g = lane < p, is_r = lane == p;
+    T L[32];
+    T w = T(0), mydinv = T(0);
+    int nfail = 0;
+    // Branch-free body: every lane executes every instruction; roles are applied with selects.
+#pragma unroll
+    for (int c = 0; c < BPP_FAST_MAX_P; ++c) {
+        if (c >= p) break;
+        const int ic = __shfl_sync(INMF_FULL_MASK, myidx, c);
+        const T gv = Grow[ic];
+        const T rv = rsh[ic];
+        T s = is_g ? gv : (is_r ? rv : T(0));
+        T s2 = T(0);
+        const T* __restrict__ Lc = Ls + c * LDL;
+#pragma unroll
+        for (int jb = 0; jb < c; jb += VEC) {
+            const Vec v = *reinterpret_cast<const Vec*>(Lc + jb);
+            const T* pv = reinterpret_cast<const T*>(&v);
+#pragma unroll
+            for (int u = 0; u < VEC; ++u) {
+                if (jb + u < c) {
+                    if (u & 1) s2 = fma(-L[jb + u], pv[u], s2);
+                    else s = fma(-L[jb + u], pv[u], s);
+                }
+            }
+        }
+        s += s2;
+        const T d = __shfl_sync(INMF_FULL_MASK, s, c);
+        const bool pd = d > T(0);
+        const T di = pd ? inmf_rsqrt<T>(pd ? d : T(1)) : T(0);
+        nfail += pd ? 0 : 1;
+        const T l = (lane >= c) ? s * di : T(0);
+        L[c] = l;
+        Lmine[c] = l;
+        mydinv = (lane == c) ? di : mydinv;
+        const T t = __shfl_sync(INMF_FULL_MASK, l, p);  // w_c = L[p][c]
+        w = (lane == c) ? t : w;
+        __syncwarp();
+    }
+    // right-looking back substitution z = L^-T w; afterwards lane c holds z_c
+    for (int c = p - 1; c >= 0; --c) {
+        const T zc = __shfl_sync(INMF_FULL_MASK, w * mydinv, c);
+        const T lv = Ls[c * LDL + lane];
+        w = (lane < c) ? fma(-lv, zc, w) : ((lane == c) ? zc : w);
+    }
+    T z = is_g ? w : T(0);
+    const T zscale = warp_max(inmf_abs(z));
+    z = zero_x<T>(z, zscale);
+    const T t0 = __shfl_sync(INMF_FULL_MASK, z, pos0 & 31);
+    const T t1 = __shfl_sync(INMF_FULL_MASK, z, pos1 & 31);
+    x0 = pas0 ? t0 : T(0);
+    x1 = pas1 ? t1 : T(0);
+    // y = G x - r on the non-passive rows
+    T a0 = T(0), a1 = T(0);
+    const T* __restrict__ G0 = Gs + (has0 ? j0 : 0) * ldg;
+    const T* __restrict__ G1 = Gs + (has1 ? j1 : 0) * ldg;
+    if (k > 32) {
+        for (int c = 0; c < p; ++c) {
+            const int ic = __shfl_sync(INMF_FULL_MASK, myidx, c);
+            const T zc = __shfl_sync(INMF_FULL_MASK, z, c);
+            a0 = fma(G0[ic], zc, a0);
+            a1 = fma(G1[ic], zc, a1);
+        }
+    } else {
+        for (int c = 0; c < p; ++c) {
+            const int ic = __shfl_sync(INMF_FULL_MASK, myidx, c);
+            const T zc = __shfl_sync(INMF_FULL_MASK, z, c);
+            a0 = fma(G0[ic], zc, a0);
+        }
+    }
+    y0 = (!has0 || pas0) ? T(0) : zero_y<T>(a0, r0);
+    y1 = (!has1 || pas1) ? T(0) : zero_y<T>(a1, r1);
+    __syncwarp();
+    cnt.nfail += nfail;
+    cnt.nfact++;
+}
+
+// ------------------------------------------------------------------------------------------------
+// General path: any |P| <= 64, L in the shared scratch.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __noinline__ void bpp_solve_passive_general(const T* __restrict__ Gs, int ldg, BppWarpScratch<T>& sc,
+                                                       int k, uint64_t P, int p, T r0, T r1, T& x0, T& x1, T& y0,
+                                                       T& y1, BppCounters& cnt) {
+    const int lane = threadIdx.x & 31;
+    const int j0 = lane, j1 = lane + 32;
+    const bool has0 = j0 < k, has1 = j1 < k;
+    const int ldl = sc.ldl;
+    const bool pas0 = has0 && mask_bit(P, j0);
+    const bool pas1 = has1 && mask_bit(P, j1);
+    const int pos0 = __popcll(P & ((1ull << j0) - 1ull));
+    const int pos1 = __popcll(P & ((1ull << j1) - 1ull));
     if (pas0) sc.idx[pos0] = (uint8_t)j0;
     if (pas1) sc.idx[pos1] = (uint8_t)j1;
     __syncwarp();
 
-    // ---- left-looking Cholesky of the augmented system, column by column ----
     for (int c = 0; c < p; ++c) {
         const int ic = sc.idx[c];
         const T* Lc = sc.L + (size_t)c * ldl;
@@ -87,7 +247,7 @@ __device__ __forceinline__ void bpp_solve_passive(const T* __restrict__ Gs, int 
         T di = T(0);
         if (d > T(0)) {
             di = inmf_rsqrt<T>(d);
-        } else if (lane == 0) {
+        } else {
             cnt.nfail++;
         }
         if (i <= p) sc.L[(size_t)i * ldl + c] = s * di;
@@ -101,7 +261,6 @@ __device__ __forceinline__ void bpp_solve_passive(const T* __restrict__ Gs, int 
         __syncwarp();
     }
 
-    // ---- right-looking back substitution: z = L^-T w, w = augmented row ----
     const T* Lw = sc.L + (size_t)p * ldl;
     T w0 = (lane < p) ? Lw[lane] : T(0);
     T w1 = (lane + 32 < p) ? Lw[lane + 32] : T(0);
@@ -115,14 +274,15 @@ __device__ __forceinline__ void bpp_solve_passive(const T* __restrict__ Gs, int 
             if (c < 32) w0 = zc; else w1 = zc;
         }
     }
-    // threshold as _utilities.py:290 and publish the compacted solution
-    if (lane < p) sc.z[lane] = (inmf_abs(w0) < T(1e-16)) ? T(0) : w0;
-    if (lane + 32 < p) sc.z[lane + 32] = (inmf_abs(w1) < T(1e-16)) ? T(0) : w1;
+    if (lane >= p) w0 = T(0);
+    if (lane + 32 >= p) w1 = T(0);
+    const T zscale = warp_max(inmf_abs(w0) > inmf_abs(w1) ? inmf_abs(w0) : inmf_abs(w1));
+    if (lane < p) sc.z[lane] = zero_x<T>(w0, zscale);
+    if (lane + 32 < p) sc.z[lane + 32] = zero_x<T>(w1, zscale);
     __syncwarp();
 
     x0 = pas0 ? sc.z[pos0] : T(0);
     x1 = pas1 ? sc.z[pos1] : T(0);
-    // y = G x - r on the non-passive rows (zero on the passive set), thresholded as :292
     T a0 = T(0), a1 = T(0);
     const T* G0 = Gs + (size_t)(has0 ? j0 : 0) * ldg;
     const T* G1 = Gs + (size_t)(has1 ? j1 : 0) * ldg;
@@ -132,12 +292,21 @@ __device__ __forceinline__ void bpp_solve_passive(const T* __restrict__ Gs, int 
         a0 += G0[ic] * zc;
         a1 += G1[ic] * zc;
     }
-    a0 -= r0;
-    a1 -= r1;
-    y0 = (!has0 || pas0 || inmf_abs(a0) < T(1e-16)) ? T(0) : a0;
-    y1 = (!has1 || pas1 || inmf_abs(a1) < T(1e-16)) ? T(0) : a1;
+    y0 = (!has0 || pas0) ? T(0) : zero_y<T>(a0, r0);
+    y1 = (!has1 || pas1) ? T(0) : zero_y<T>(a1, r1);
     __syncwarp();
-    if (lane == 0) cnt.nfact++;
+    cnt.nfact++;
+}
+
+template <typename T>
+__device__ __forceinline__ void bpp_solve_passive(const T* __restrict__ Gs, int ldg, BppWarpScratch<T>& sc, int k,
+                                                  uint64_t P, T r0, T r1, T& x0, T& x1, T& y0, T& y1,
+                                                  BppCounters& cnt) {
+    const int p = __popcll(P);
+    if (p <= BPP_FAST_MAX_P)
+        bpp_solve_passive_fast<T>(Gs, ldg, sc, k, P, p, r0, r1, x0, x1, y0, y1, cnt);
+    else
+        bpp_solve_passive_general<T>(Gs, ldg, sc, k, P, p, r0, r1, x0, x1, y0, y1, cnt);
 }
 
 // Full BPP for one column.  r0/r1: this lane's entries of r (factor lane, lane+32; 0 beyond k).
@@ -152,17 +321,21 @@ __device__ __forceinline__ void bpp_column(const T* __restrict__ Gs, int ldg, Bp
     if (has0) sc.r[lane] = r0;
     if (has1) sc.r[lane + 32] = r1;
     __syncwarp();
-    x0 = T(0);
-    x1 = T(0);
-    y0 = has0 ? -r0 : T(0);
-    y1 = has1 ? -r1 : T(0);
     P = warm ? (P & kmask) : 0ull;
-    if (P != 0ull) bpp_solve_passive<T>(Gs, ldg, sc, k, P, r0, r1, x0, x1, y0, y1, cnt);
     int ninf = k + 1;
     int pbar = 3;
     const int max_rounds = 5 * k;  // _utilities.py:220
     int rounds = 0;
     while (true) {
+        // evaluate the current partition (single call site keeps the unrolled solver in one copy)
+        if (P != 0ull) {
+            bpp_solve_passive<T>(Gs, ldg, sc, k, P, r0, r1, x0, x1, y0, y1, cnt);
+        } else {
+            x0 = T(0);
+            x1 = T(0);
+            y0 = has0 ? -r0 : T(0);
+            y1 = has1 ? -r1 : T(0);
+        }
         const bool bad0 = has0 && (mask_bit(P, lane) ? (x0 < T(0)) : (y0 < T(0)));
         const bool bad1 = has1 && (mask_bit(P, lane + 32) ? (x1 < T(0)) : (y1 < T(0)));
         const uint64_t I = (uint64_t)__ballot_sync(INMF_FULL_MASK, bad0) |
@@ -184,15 +357,7 @@ __device__ __forceinline__ void bpp_column(const T* __restrict__ Gs, int ldg, Bp
             P ^= I;
         } else {  // backup rule: flip only the largest infeasible index (:278-283)
             P ^= 1ull << (63 - __clzll(I));
-            if (lane == 0) cnt.nbackup++;
-        }
-        if (P != 0ull) {
-            bpp_solve_passive<T>(Gs, ldg, sc, k, P, r0, r1, x0, x1, y0, y1, cnt);
-        } else {
-            x0 = T(0);
-            x1 = T(0);
-            y0 = has0 ? -r0 : T(0);
-            y1 = has1 ? -r1 : T(0);
+            cnt.nbackup++;
         }
     }
     cnt.rounds = rounds;

@@ -51,7 +51,9 @@ template <typename T>
 __device__ __forceinline__ T inmf_rsqrt(T x);
 template <>
 __device__ __forceinline__ float inmf_rsqrt<float>(float x) {
-    return rsqrtf(x);
+    float y;  // MUFU.RSQ without the denormal pre-scaling sequence (Gram pivots are never denormal)
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
 template <>
 __device__ __forceinline__ double inmf_rsqrt<double>(double x) {
@@ -92,3 +94,44 @@ __device__ __forceinline__ int64_t seg_row(const SegWin& w, int64_t j) {
     if (r >= w.win_mod) r %= w.win_mod;
     return w.row_base + r;
 }
+
+// =================================================================================================
+// Tall-skinny Gram helper: out(k x k, double) += tile' * tile for a row tile staged in shared memory.
+// Each thread owns a 4x4 block of the output.
+// =================================================================================================
+#define GRAM_TILE_ROWS 64
+
+template <typename T>
+__device__ __forceinline__ void tile_gram_accumulate(const T* __restrict__ tile, int ldt, int rows, int k,
+                                                     double* __restrict__ out, double scale) {
+    const int nb = (k + 3) >> 2;
+    for (int blk = threadIdx.x; blk < nb * nb; blk += blockDim.x) {
+        const int bi = blk / nb, bj = blk % nb;
+        T acc[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) acc[a][b] = T(0);
+        for (int r = 0; r < rows; ++r) {
+            const T* row = tile + (size_t)r * ldt;
+            T va[4], vb[4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                va[a] = row[4 * bi + a];
+                vb[a] = row[4 * bj + a];
+            }
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) acc[a][b] += va[a] * vb[b];
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int i = 4 * bi + a, j = 4 * bj + b;
+                if (i < k && j < k) atomicAdd(&out[(size_t)i * k + j], scale * (double)acc[a][b]);
+            }
+    }
+}
+

@@ -1,7 +1,8 @@
 // libinmf_b200.so -- kernels + C ABI for pyliger's iNMF hot path on B200 (sm_100a).
 // ABI and reference citations: include/inmf_b200.h.  Design notes: DESIGN.md.
-#include "bpp.cuh"
 #include "inmf_common.cuh"
+#include "bpp.cuh"
+#include "blocked.cuh"
 
 thread_local char g_inmf_err[512] = "";
 
@@ -15,7 +16,7 @@ extern "C" const char* inmf_last_error(void) { return g_inmf_err; }
 // K3: batched BPP
 // =================================================================================================
 template <typename T>
-__global__ void bpp_kernel(const double* __restrict__ G, const T* R, int64_t ldr, T* X, int64_t ldx,
+__global__ void __launch_bounds__(256, 2) bpp_kernel(const double* __restrict__ G, const T* R, int64_t ldr, T* X, int64_t ldx,
                            T* __restrict__ Y, int64_t ldy, uint64_t* __restrict__ mask, int warm, const int64_t* __restrict__ seg_off, int k,
                            long long* __restrict__ stats) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -119,46 +120,6 @@ extern "C" int32_t inmf_bpp_f64(const double* G, const double* R, int64_t ldr, d
                                 int32_t nseg, int64_t max_seg_cols, int32_t k, int64_t* stats, void* stream) {
     return bpp_launch<double>(G, R, ldr, X, ldx, Y, ldy, mask, warm, seg_off, nseg, max_seg_cols, k, stats,
                               stream);
-}
-
-// =================================================================================================
-// Tall-skinny Gram helper: out(k x k, double) += tile' * tile for a row tile staged in shared memory.
-// Each thread owns a 4x4 block of the output.
-// =================================================================================================
-#define GRAM_TILE_ROWS 64
-
-template <typename T>
-__device__ __forceinline__ void tile_gram_accumulate(const T* __restrict__ tile, int ldt, int rows, int k,
-                                                     double* __restrict__ out, double scale) {
-    const int nb = (k + 3) >> 2;
-    for (int blk = threadIdx.x; blk < nb * nb; blk += blockDim.x) {
-        const int bi = blk / nb, bj = blk % nb;
-        T acc[4][4];
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int b = 0; b < 4; ++b) acc[a][b] = T(0);
-        for (int r = 0; r < rows; ++r) {
-            const T* row = tile + (size_t)r * ldt;
-            T va[4], vb[4];
-#pragma unroll
-            for (int a = 0; a < 4; ++a) {
-                va[a] = row[4 * bi + a];
-                vb[a] = row[4 * bj + a];
-            }
-#pragma unroll
-            for (int a = 0; a < 4; ++a)
-#pragma unroll
-                for (int b = 0; b < 4; ++b) acc[a][b] += va[a] * vb[b];
-        }
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                const int i = 4 * bi + a, j = 4 * bj + b;
-                if (i < k && j < k) atomicAdd(&out[(size_t)i * k + j], scale * (double)acc[a][b]);
-            }
-    }
 }
 
 // =================================================================================================
@@ -829,4 +790,40 @@ extern "C" int32_t inmf_normal_eq_f32(const float* A, const float* B, int64_t m,
 extern "C" int32_t inmf_normal_eq_f64(const double* A, const double* B, int64_t m, int32_t n, int64_t cols,
                                       double* G, double* Rt, void* stream) {
     return normal_eq_launch<double>(A, B, m, n, cols, G, Rt, stream);
+}
+
+// =================================================================================================
+// v2 hot kernels: blocked sparse x shared dense tile (blocked.cuh)
+// =================================================================================================
+template <typename T>
+static int32_t blocked_launch(const int64_t* work, int32_t nwork, const int64_t* ptr, const void* pairs, const T* dense,
+                              int32_t kp, T* out, int64_t ldo, int32_t k, int32_t max_tile_rows, double* gram_out,
+                              void* stream) {
+    INMF_REQUIRE(k >= 1 && k <= INMF_MAX_K, "k must be in [1, 64]");
+    INMF_REQUIRE(kp >= k && kp % 4 == 0 && kp <= 64, "kp must be a multiple of 4 in [k, 64]");
+    INMF_REQUIRE(ldo >= k, "ldo must be >= k");
+    if (nwork <= 0) return 0;
+    const size_t smem = 128 + (size_t)max_tile_rows * kp * sizeof(T);
+    INMF_REQUIRE(smem <= 227 * 1024, "dense tile does not fit in shared memory");
+    static bool attr_done[2] = {false, false};
+    const int ti = sizeof(T) == 8;
+    if (!attr_done[ti]) {
+        INMF_CUDA_CHECK(cudaFuncSetAttribute(blocked_spmm_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             227 * 1024));
+        attr_done[ti] = true;
+    }
+    blocked_spmm_kernel<T><<<(unsigned)nwork, 1024, smem, (cudaStream_t)stream>>>(
+        work, ptr, reinterpret_cast<const typename PairTraits<T>::Pair*>(pairs), dense, kp, out, ldo, k, gram_out);
+    INMF_LAUNCH_CHECK();
+    return 0;
+}
+extern "C" int32_t inmf_blocked_spmm_f32(const int64_t* work, int32_t nwork, const int64_t* ptr, const void* pairs,
+                                         const float* dense, int32_t kp, float* out, int64_t ldo, int32_t k,
+                                         int32_t max_tile_rows, double* gram_out, void* stream) {
+    return blocked_launch<float>(work, nwork, ptr, pairs, dense, kp, out, ldo, k, max_tile_rows, gram_out, stream);
+}
+extern "C" int32_t inmf_blocked_spmm_f64(const int64_t* work, int32_t nwork, const int64_t* ptr, const void* pairs,
+                                         const double* dense, int32_t kp, double* out, int64_t ldo, int32_t k,
+                                         int32_t max_tile_rows, double* gram_out, void* stream) {
+    return blocked_launch<double>(work, nwork, ptr, pairs, dense, kp, out, ldo, k, max_tile_rows, gram_out, stream);
 }

@@ -12,7 +12,7 @@ import numpy as np
 import scipy.sparse as sps
 import torch
 
-from . import _lib
+from . import _lib, blocked
 
 _SUFFIX = {torch.float32: "f32", torch.float64: "f64"}
 
@@ -126,7 +126,9 @@ class InmfEngine(object):
     """Buffers + step functions shared by optimize_ALS and online_iNMF."""
 
     def __init__(self, mats, k, value_lambda, dtype=torch.float64, device=None, group=None, pin=False,
-                 replicate=False, n_prev=0, presharded=False):
+                 replicate=False, n_prev=0, presharded=False, use_blocked=True, need_stats=True):
+        self.use_blocked = bool(use_blocked)
+        self.need_stats = bool(need_stats)
         self.device = require_cuda(device)
         self.dtype = resolve_dtype(dtype)
         self.sfx = _SUFFIX[self.dtype]
@@ -158,7 +160,7 @@ class InmfEngine(object):
         # stacked [previous datasets (online scenario 2) | current datasets]
         self.Vt_all = z(self.n_prev + N, g, k)
         self.Vt = self.Vt_all[self.n_prev:]
-        self.H = z(max(X.n_own_total, 1), k)
+        self.H = z(max(X.n_own_total, 1), self.ldm)  # leading dimension ldm: pad columns stay zero
         self.Mt = z(N, g, self.ldm)
         self.G = z(N, k, k, dtype=f64)
         self.Gwv = z(N, k, k, dtype=f64)
@@ -181,6 +183,7 @@ class InmfEngine(object):
         full[:N, 2] = [o[0] - b[0] for o, b in zip(X.own, X.bounds)]
         full[:N, 3] = np.maximum(X.n_local, 1)
         self.seg_full = torch.from_numpy(full).to(dev)
+        self.seg_full_off = self.seg_full[:, 0].contiguous()
         self.max_rows_full = int(max(X.n_own)) if N else 0
         whole = full.copy()  # every resident row exactly once (sqnorm)
         whole[:N, 2] = 0
@@ -191,6 +194,14 @@ class InmfEngine(object):
                   _stream())
         if X.bounds == X.own and (self.world > 1):
             self._allreduce(self.xnorm2)
+        # blocked copies of X for the two streaming passes over whole datasets (csrc/blocked.cuh)
+        self.pass1 = self.pass2 = None
+        if self.use_blocked and X.n_own_total > 0:
+            esize = 4 if dt == torch.float32 else 8
+            sms = torch.cuda.get_device_properties(dev).multi_processor_count
+            self.pass1 = blocked.build_pass1(X, self.ldm, esize, sms)
+            if self.need_stats:
+                self.pass2 = blocked.build_pass2(X, self.ldm, esize, sms)
 
     def _allreduce(self, *tensors):
         if self.world > 1:
@@ -202,23 +213,47 @@ class InmfEngine(object):
         _lib.call("inmf_prep", self.sfx, self.Wt, self.Vt if with_V else None, self.Mt, self.ldm, self.G,
                   self.Gwv, self.Gvv, self.lam, self.N, self.g, self.k, _stream())
 
-    def solve_H(self, seg_desc=None, max_rows=None, out=None, mask=None, warm=False, nseg=None):
-        """out[q,:] = argmin_{h>=0} for every row of the windows in seg_desc (default: all local cells)."""
-        seg_desc = self.seg_full if seg_desc is None else seg_desc
+    def rhs_H(self, seg_desc=None, max_rows=None, out=None, nseg=None):
+        """out[q, :k] = X[row(q), :] (W+V)  for the windows in seg_desc (default: all owned cells)."""
+        full = seg_desc is None
+        seg_desc = self.seg_full if full else seg_desc
         max_rows = self.max_rows_full if max_rows is None else max_rows
         out = self.H if out is None else out
         nseg = self.N if nseg is None else nseg
         if max_rows <= 0:
             return
         X, k = self.X, self.k
-        _lib.call("inmf_spmm", self.sfx, X.rowptr, X.colidx, X.vals, self.Mt, self.ldm, self.g, out, k,
-                  seg_desc, nseg, max_rows, k, _stream())
-        # segment column ranges of the batched BPP are the out_off column of seg_desc (stride 4)
-        seg_off = seg_desc[:, 0].contiguous()
-        _lib.call("inmf_bpp", self.sfx, self.G, out, k, out, k, None, 0, mask, 1 if warm else 0, seg_off,
-                  nseg, max_rows, k, self.bpp_stats[0], _stream())
+        if full and out is self.H and self.pass1 is not None:
+            out.zero_()
+            p = self.pass1
+            _lib.call("inmf_blocked_spmm", self.sfx, p.work, p.nwork, p.ptr, p.pairs, self.Mt, self.ldm, out,
+                      self.ldm, k, p.max_tile_rows, None, _stream())
+        else:
+            _lib.call("inmf_spmm", self.sfx, X.rowptr, X.colidx, X.vals, self.Mt, self.ldm, self.g, out, self.ldm,
+                      seg_desc, nseg, max_rows, k, _stream())
+
+    def bpp_H(self, seg_desc=None, max_rows=None, out=None, mask=None, warm=False, nseg=None):
+        """In-place batched BPP on the right-hand sides produced by rhs_H."""
+        if seg_desc is None:
+            seg_off = self.seg_full_off
+        else:
+            seg_off = seg_desc[:, 0].contiguous()  # column ranges = the out_off column of seg_desc
+        max_rows = self.max_rows_full if max_rows is None else max_rows
+        out = self.H if out is None else out
+        nseg = self.N if nseg is None else nseg
+        if max_rows <= 0:
+            return
+        k = self.k
+        _lib.call("inmf_bpp", self.sfx, self.G, out, self.ldm, out, self.ldm, None, 0, mask, 1 if warm else 0,
+                  seg_off, nseg, max_rows, k, self.bpp_stats[0], _stream())
+
+    def solve_H(self, seg_desc=None, max_rows=None, out=None, mask=None, warm=False, nseg=None):
+        """out[q,:] = argmin_{h>=0} for every row of the windows in seg_desc (default: all owned cells)."""
+        self.rhs_H(seg_desc, max_rows, out, nseg)
+        self.bpp_H(seg_desc, max_rows, out, mask, warm, nseg)
 
     def stats(self, seg_desc=None, max_rows=None, H=None, St=None, HtH=None, reduce=True, nseg=None):
+        full = seg_desc is None and H is None
         seg_desc = self.seg_full if seg_desc is None else seg_desc
         max_rows = self.max_rows_full if max_rows is None else max_rows
         H = self.H if H is None else H
@@ -229,8 +264,13 @@ class InmfEngine(object):
         HtH.zero_()
         X, k = self.X, self.k
         if max_rows > 0:
-            _lib.call("inmf_stats", self.sfx, X.rowptr, X.colidx, X.vals, H, k, St, HtH, self.g, seg_desc,
-                      nseg, max_rows, k, _stream())
+            if full and self.pass2 is not None:
+                p = self.pass2
+                _lib.call("inmf_blocked_spmm", self.sfx, p.work, p.nwork, p.ptr, p.pairs, H, self.ldm, St, k, k,
+                          p.max_tile_rows, HtH, _stream())
+            else:
+                _lib.call("inmf_stats", self.sfx, X.rowptr, X.colidx, X.vals, H, self.ldm, St, HtH, self.g, seg_desc,
+                          nseg, max_rows, k, _stream())
         if reduce:
             self._allreduce(St, HtH)
 
@@ -265,7 +305,7 @@ class InmfEngine(object):
                 lo, hi = self.X.own[i]
                 b0, b1 = int(self.X.own_off[i]), int(self.X.own_off[i + 1])
                 if b1 > b0:
-                    self.H[b0:b1].copy_(torch.from_numpy(np.ascontiguousarray(
+                    self.H[b0:b1, :self.k].copy_(torch.from_numpy(np.ascontiguousarray(
                         np.asarray(Hi, dtype=np.float64)[lo:hi])).to(dev, dt))
 
     def initial_objective(self):
@@ -290,7 +330,7 @@ class InmfEngine(object):
         out = []
         for i in range(self.N):
             b0, b1 = int(self.X.own_off[i]), int(self.X.own_off[i + 1])
-            local = self.H[b0:b1].to(torch.float64)
+            local = self.H[b0:b1, :self.k].to(torch.float64).contiguous()
             if self.world == 1 or self.X.presharded:
                 out.append(local.cpu().numpy())
                 continue
@@ -328,7 +368,7 @@ class InmfEngine(object):
         self.mbs = [int(m) for m in miniBatch_sizes]
         self.sub = [shard_bounds(m, self.rank, self.world) for m in self.mbs]  # this rank's part of a batch
         self.max_sub = max(hi - lo for lo, hi in self.sub)
-        self.H_mb = torch.zeros(max(sum(hi - lo for lo, hi in self.sub), 1), k, dtype=dt, device=dev)
+        self.H_mb = torch.zeros(max(sum(hi - lo for lo, hi in self.sub), 1), self.ldm, dtype=dt, device=dev)
         self.inv_mb = torch.tensor([1.0 / m for m in self.mbs], dtype=f64, device=dev)
 
     def online_plan(self, total_iters):

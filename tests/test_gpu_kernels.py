@@ -64,10 +64,21 @@ def test_prep_spmm_stats_objective(dev, dtype, tol, k):
     from pyliger_b200 import _lib
     from pyliger_b200.engine import _stream
     R = torch.zeros_like(eng.H)
-    _lib.call("inmf_spmm", eng.sfx, eng.X.rowptr, eng.X.colidx, eng.X.vals, eng.Mt, eng.ldm, eng.g, R, k,
+    _lib.call("inmf_spmm", eng.sfx, eng.X.rowptr, eng.X.colidx, eng.X.vals, eng.Mt, eng.ldm, eng.g, R, eng.ldm,
               eng.seg_full, N, eng.max_rows_full, k, _stream())
     want_R = np.vstack([np.asarray(mats[i].dot((W + V[i]).T)) for i in range(N)])
-    assert relerr(R.cpu().numpy(), want_R) < tol
+    assert relerr(R[:, :k].cpu().numpy(), want_R) < tol
+    # blocked pass 1 (TMA tile + packed pairs) computes the same right-hand sides
+    eng.rhs_H()
+    assert eng.pass1 is not None and eng.pass2 is not None
+    assert relerr(eng.H[:, :k].cpu().numpy(), want_R) < tol
+    assert float(eng.H[:, k:].abs().max().item() if eng.ldm > k else 0.0) == 0.0
+    # and the row-kernel statistics agree with the blocked pass 2 used by eng.stats() above
+    eng.set_als_state(W, V, H)
+    St2 = torch.zeros_like(eng.St); HtH2 = torch.zeros_like(eng.HtH)
+    eng.stats(seg_desc=eng.seg_full, H=eng.H, St=St2, HtH=HtH2)
+    assert relerr(St2.cpu().numpy(), eng.St.cpu().numpy()) < tol
+    assert relerr(HtH2.cpu().numpy(), eng.HtH.cpu().numpy()) < tol
 
 
 @pytest.mark.parametrize("dtype,tol", DTYPES)
@@ -101,7 +112,7 @@ def test_window_segments_wrap(dev, dtype, tol):
     eng.prep()
     # dataset 0: rows 44..49,0..5 (12 rows); dataset 1: rows 30..36,0..1 (9 rows)
     seg = torch.tensor([[0, 0, 44, 50], [12, 50, 30, 37], [21, 0, 0, 0]], dtype=torch.int64, device=dev)
-    out = torch.zeros(21, k, dtype=eng.dtype, device=dev)
+    out = torch.zeros(21, eng.ldm, dtype=eng.dtype, device=dev)
     eng.solve_H(seg_desc=seg, max_rows=12, out=out)
     rows0 = [(44 + j) % 50 for j in range(12)]
     rows1 = [(30 + j) % 37 for j in range(9)]
@@ -110,11 +121,11 @@ def test_window_segments_wrap(dev, dtype, tol):
         G = M @ M.T + lam * V[i] @ V[i].T
         R = np.asarray(mats[i][rows].dot(M.T)).T
         want = orc.bpp(G, R)[0].T
-        assert relerr(out[sl].cpu().numpy(), want) < max(tol * 50, 1e-9)
+        assert relerr(out[sl, :k].cpu().numpy(), want) < max(tol * 50, 1e-9)
     St = torch.zeros_like(eng.St)
     HtH = torch.zeros_like(eng.HtH)
     eng.stats(seg_desc=seg, max_rows=12, H=out, St=St, HtH=HtH)
-    Hh = out.cpu().numpy().astype(np.float64)
+    Hh = out[:, :k].cpu().numpy().astype(np.float64)
     assert relerr(St[0].cpu().numpy(), np.asarray(mats[0][rows0].T.dot(Hh[:12]))) < tol * 10
     assert relerr(St[1].cpu().numpy(), np.asarray(mats[1][rows1].T.dot(Hh[12:]))) < tol * 10
     assert relerr(HtH[1].cpu().numpy(), Hh[12:].T @ Hh[12:]) < tol * 10

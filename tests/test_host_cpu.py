@@ -186,3 +186,61 @@ def test_two_rank_gloo_statistics_and_gather():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert sorted(res) == [(0, True), (1, True)]
+
+
+# ------------------------------------------------------------------------------------------ blocked formats
+def _emulate_blocked(bp, dense, kp, out, k, gram=None):
+    """numpy statement of what inmf_blocked_spmm computes from (work, ptr, pairs)."""
+    work = bp.work.numpy()[:bp.nwork]
+    ptr = bp.ptr.numpy()
+    pairs = bp.pairs.numpy()
+    idx = pairs[:, 0].astype(np.int64)
+    vals = pairs[:, 1].copy().view(np.float32 if pairs.dtype == np.int32 else np.float64).astype(np.float64)
+    for ptr_base, dense_row0, tile_rows, r0, r1, out_base, gram_seg, _ in work:
+        tile = dense[dense_row0:dense_row0 + tile_rows]
+        assert tile.shape[0] == tile_rows
+        for r in range(r0, r1):
+            b, e = ptr[ptr_base + r], ptr[ptr_base + r + 1]
+            if e > b:
+                assert idx[b:e].max() < tile_rows and idx[b:e].min() >= 0
+                out[out_base + r, :k] += vals[b:e] @ tile[idx[b:e], :k]
+        if gram is not None and gram_seg >= 0:
+            gram[gram_seg] += tile[:, :k].T @ tile[:, :k]
+
+
+@pytest.mark.parametrize("world,rank", [(1, 0), (3, 1)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_blocked_formats_reproduce_products(world, rank, dtype):
+    from pyliger_b200 import blocked
+    from pyliger_b200.engine import DeviceCSR
+    rng = np.random.default_rng(5)
+    g, k, kp = 157, 6, 8
+    mats = [sps.random(n, g, density=0.2, random_state=3 + i, format="csr") for i, n in enumerate((301, 77, 5))]
+    X = DeviceCSR(mats, dtype, torch.device("cpu"), rank, world)
+    esize = 4 if dtype == torch.float32 else 8
+    old = blocked.SMEM_BUDGET
+    blocked.SMEM_BUDGET = 50 * kp * esize  # force several gene / cell blocks at this toy size
+    try:
+        p1 = blocked.build_pass1(X, kp, esize, n_sms=7)
+        p2 = blocked.build_pass2(X, kp, esize, n_sms=7)
+    finally:
+        blocked.SMEM_BUDGET = old
+    assert p1.max_tile_rows <= 50 and p2.max_tile_rows <= 50
+    N = len(mats)
+    Mt = rng.uniform(0, 1, (N * g, kp)); Mt[:, k:] = 0
+    H = rng.uniform(0, 1, (X.n_own_total, kp)); H[:, k:] = 0
+    R = np.zeros((X.n_own_total, kp))
+    _emulate_blocked(p1, Mt, kp, R, k)
+    St = np.zeros((N * g, k)); gram = np.zeros((N, k, k))
+    _emulate_blocked(p2, H, kp, St, k, gram)
+    tol = 1e-5 if dtype == torch.float32 else 1e-12
+    for s, m in enumerate(mats):
+        lo, hi = X.own[s]
+        o0, o1 = X.own_off[s], X.own_off[s + 1]
+        sub = m[lo:hi]
+        np.testing.assert_allclose(R[o0:o1, :k], sub @ Mt[s * g:(s + 1) * g, :k], rtol=tol, atol=tol)
+        np.testing.assert_allclose(St[s * g:(s + 1) * g], sub.T @ H[o0:o1, :k], rtol=tol, atol=tol)
+        np.testing.assert_allclose(gram[s], H[o0:o1, :k].T @ H[o0:o1, :k], rtol=1e-12, atol=1e-12)
+    # every owned non-zero appears exactly once in each pass
+    own_nnz = sum(m[lo:hi].nnz for m, (lo, hi) in zip(mats, X.own))
+    assert p1.pairs.shape[0] == own_nnz == p2.pairs.shape[0]
