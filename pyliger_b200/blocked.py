@@ -18,7 +18,7 @@ def tile_cap_rows(kp, esize):
 
 
 def _pack_pairs(idx_local, vals):
-    """(int idx, T val) -> packed pairs: f32 {int32, float32} = int32[nnz, 2]; f64 {int64, float64}."""
+    """(int byte offset, T val) -> packed pairs: f32 {int32, float32} = int32[nnz, 2]; f64 {int64, float64}."""
     if vals.dtype == torch.float32:
         out = torch.empty(idx_local.numel(), 2, dtype=torch.int32, device=vals.device)
         out[:, 0] = idx_local.to(torch.int32)
@@ -77,7 +77,7 @@ def build_pass1(X, kp, esize, n_sms):
         ptr[1:] = torch.cumsum(torch.bincount(cidx, minlength=NB * n_tot), 0)
     idx_local = (col.to(torch.int64) - gb * gbs)[order]
     bp = BlockedPass()
-    bp.pairs = _pack_pairs(idx_local, val[order])
+    bp.pairs = _pack_pairs(idx_local * (kp * esize), val[order])  # byte offset of the gathered tile row
     bp.ptr = ptr
     chunks = max(1, n_sms // max(1, N * NB))
     work = []
@@ -124,7 +124,7 @@ def build_pass2(X, kp, esize, n_sms):
         ptr[1:] = torch.cumsum(torch.bincount(cidx, minlength=g * total_blocks), 0)
     idx_local = (local_row - cb * cbs_t[seg])[order]
     bp = BlockedPass()
-    bp.pairs = _pack_pairs(idx_local, val[order])
+    bp.pairs = _pack_pairs(idx_local * (kp * esize), val[order])  # byte offset of the gathered tile row
     bp.ptr = ptr
     chunks = max(1, n_sms // max(1, total_blocks))
     per = -(-g // chunks)

@@ -7,10 +7,14 @@
 // Both are "sparse row times a dense (rows x KP) tile" with k <= 64 columns, so they are bound by the
 // shared-memory operand bandwidth (4*KP bytes per non-zero at 128 B/clk/SM), not by tensor math: the
 // dense tile is brought in ONCE per CTA with a TMA bulk copy (cp.async.bulk, mbarrier completion), the
-// packed (index, value) pairs of X are streamed from HBM exactly once per pass with 64/128-bit loads,
+// packed (offset, value) pairs of X are streamed from HBM exactly once per pass with 64/128-bit loads,
 // each lane owns 4 (fp32) / 2 (fp64) consecutive factors and reads them with one 128-bit LDS, and
 // accumulation is in registers.  X is stored twice in blocked form (gene-blocked CSR for pass 1,
 // cell-blocked CSC for pass 2) so that in both passes the gathered operand is the shared tile.
+//
+// Pair layout: f32 {int32 off, float val}, f64 {int64 off, double val}; off = (row of the tile) * KP *
+// sizeof(T) is the BYTE offset of the gathered tile row, premultiplied when the format is built so the
+// inner loop is LDG.64 -> IADD -> LDS.128 -> 4 FFMA per lane group.
 #pragma once
 #include "inmf_common.cuh"
 
@@ -21,25 +25,44 @@ template <typename T>
 struct PairTraits;
 template <>
 struct PairTraits<float> {
-    typedef int2 Pair;  // {idx, float bits}
-    typedef float4 Vec;
+    typedef int2 Pair;
     static constexpr int VEC = 4;
-    __device__ static __forceinline__ void unpack(const Pair& p, int& idx, float& v) {
-        idx = p.x;
-        v = __int_as_float(p.y);
-    }
     __device__ static __forceinline__ Pair zero() { return make_int2(0, 0); }
+    __device__ static __forceinline__ Pair ld(const Pair* p) {
+        int2 r;
+        asm volatile("ld.global.nc.L1::no_allocate.v2.s32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+        return r;
+    }
+    // acc[0..3] += val * tile_row[sub*4 .. sub*4+3]
+    __device__ static __forceinline__ void fma_row(const Pair& p, uint32_t tsub, float (&acc)[4]) {
+        float m0, m1, m2, m3;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(m0), "=f"(m1), "=f"(m2), "=f"(m3)
+                     : "r"(tsub + (uint32_t)p.x));
+        const float v = __int_as_float(p.y);
+        acc[0] = fmaf(v, m0, acc[0]);
+        acc[1] = fmaf(v, m1, acc[1]);
+        acc[2] = fmaf(v, m2, acc[2]);
+        acc[3] = fmaf(v, m3, acc[3]);
+    }
 };
 template <>
 struct PairTraits<double> {
-    typedef longlong2 Pair;  // {idx (low 32 bits), double bits}
-    typedef double2 Vec;
+    typedef longlong2 Pair;
     static constexpr int VEC = 2;
-    __device__ static __forceinline__ void unpack(const Pair& p, int& idx, double& v) {
-        idx = (int)p.x;
-        v = __longlong_as_double(p.y);
-    }
     __device__ static __forceinline__ Pair zero() { return make_longlong2(0, 0); }
+    __device__ static __forceinline__ Pair ld(const Pair* p) {
+        longlong2 r;
+        asm volatile("ld.global.nc.L1::no_allocate.v2.s64 {%0, %1}, [%2];" : "=l"(r.x), "=l"(r.y) : "l"(p));
+        return r;
+    }
+    __device__ static __forceinline__ void fma_row(const Pair& p, uint32_t tsub, double (&acc)[2]) {
+        double m0, m1;
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(m0), "=d"(m1) : "r"(tsub + (uint32_t)p.x));
+        const double v = __longlong_as_double(p.y);
+        acc[0] = fma(v, m0, acc[0]);
+        acc[1] = fma(v, m1, acc[1]);
+    }
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -72,75 +95,85 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  : "memory");
 }
 
-template <typename T>
-__device__ __forceinline__ typename PairTraits<T>::Pair ld_pair(const typename PairTraits<T>::Pair* p);
-template <>
-__device__ __forceinline__ int2 ld_pair<float>(const int2* p) {
-    int2 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v2.s32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
-    return r;
-}
-template <>
-__device__ __forceinline__ longlong2 ld_pair<double>(const longlong2* p) {
-    longlong2 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v2.s64 {%0, %1}, [%2];" : "=l"(r.x), "=l"(r.y) : "l"(p));
-    return r;
-}
+#define BLK_U 4  // quads (groups of npi non-zeros) per pipeline stage
 
-#define BLK_UNROLL 4
-
-// One warp: out[0..KP) = sum over pairs [beg, end) of val * tile[idx][:].  Lane (grp, sub): grp = which of
-// the NPI pairs in flight, sub = which VEC-wide factor chunk.  Result (all groups summed) is returned in
-// acc[] of the lanes with grp == 0.
-template <typename T>
-__device__ __forceinline__ void warp_sparse_dot(const typename PairTraits<T>::Pair* __restrict__ pairs, int64_t beg,
-                                                int64_t end, const T* __restrict__ tile, int KP, int lpn, int npi,
-                                                int grp, int sub, bool active, T (&acc)[PairTraits<T>::VEC]) {
+// One warp, one sparse row of m pairs starting at pl0 (= pairs + beg).  Lane (grp, sub): grp = which of
+// the npi pairs handled per warp instruction, sub = which VEC-wide factor chunk.  The sum over all groups
+// ends up in acc[] of the lanes with grp == 0.  LPN_T > 0 fixes lanes-per-non-zero at compile time.
+template <typename T, int LPN_T>
+__device__ __forceinline__ void warp_row_dot(const typename PairTraits<T>::Pair* __restrict__ pl0, int m, int lpn_rt,
+                                             int grp, bool active, uint32_t tsub,
+                                             T (&acc)[PairTraits<T>::VEC]) {
     typedef PairTraits<T> PT;
     typedef typename PT::Pair Pair;
-    typedef typename PT::Vec Vec;
     constexpr int VEC = PT::VEC;
+    const int lpn = LPN_T > 0 ? LPN_T : lpn_rt;
+    const int npi = 32 / lpn;
 #pragma unroll
     for (int u = 0; u < VEC; ++u) acc[u] = T(0);
-    const T* __restrict__ tsub = tile + sub * VEC;
-    const int64_t step = (int64_t)npi * BLK_UNROLL;
-    // software pipeline: the loads of batch i+1 are in flight while batch i is consumed
-    Pair cur[BLK_UNROLL], nxt[BLK_UNROLL];
+    // lanes beyond npi*lpn shadow group 0 (their sums are never folded in)
+    const Pair* __restrict__ pl = pl0 + (active ? grp : 0);
+    const int nfull = m / npi;              // quads in which every group has a pair
+    const int nq = (m + npi - 1) / npi;     // all quads
+    int j = 0;
+    if (nfull >= BLK_U) {
+        Pair A[BLK_U], B[BLK_U];
 #pragma unroll
-    for (int t = 0; t < BLK_UNROLL; ++t) {
-        const int64_t q = beg + (int64_t)t * npi + grp;
-        cur[t] = (active && q < end) ? ld_pair<T>(pairs + q) : PT::zero();
+        for (int t = 0; t < BLK_U; ++t) A[t] = PT::ld(pl + t * npi);
+        // ping-pong: the loads of the next stage are in flight while the current one is consumed
+        while (true) {
+            const Pair* __restrict__ pn = pl + (size_t)(j + BLK_U) * npi;
+            if (j + 2 * BLK_U <= nfull) {
+#pragma unroll
+                for (int t = 0; t < BLK_U; ++t) B[t] = PT::ld(pn + t * npi);
+#pragma unroll
+                for (int t = 0; t < BLK_U; ++t) PT::fma_row(A[t], tsub, acc);
+                j += BLK_U;
+            } else {
+#pragma unroll
+                for (int t = 0; t < BLK_U; ++t) PT::fma_row(A[t], tsub, acc);
+                j += BLK_U;
+                break;
+            }
+            const Pair* __restrict__ pm = pl + (size_t)(j + BLK_U) * npi;
+            if (j + 2 * BLK_U <= nfull) {
+#pragma unroll
+                for (int t = 0; t < BLK_U; ++t) A[t] = PT::ld(pm + t * npi);
+#pragma unroll
+                for (int t = 0; t < BLK_U; ++t) PT::fma_row(B[t], tsub, acc);
+                j += BLK_U;
+            } else {
+#pragma unroll
+                for (int t = 0; t < BLK_U; ++t) PT::fma_row(B[t], tsub, acc);
+                j += BLK_U;
+                break;
+            }
+        }
     }
-    for (int64_t base = beg; base < end; base += step) {  // warp-uniform trip count
+    // tail quads (predicated)
+    {
+        Pair C[BLK_U];  // at most (nfull mod BLK_U) + 1 <= BLK_U quads are left
 #pragma unroll
-        for (int t = 0; t < BLK_UNROLL; ++t) {
-            const int64_t q = base + step + (int64_t)t * npi + grp;
-            nxt[t] = (active && q < end) ? ld_pair<T>(pairs + q) : PT::zero();
+        for (int t = 0; t < BLK_U; ++t) {
+            const int q = (j + t) * npi + grp;
+            C[t] = (active && (j + t) < nq && q < m) ? PT::ld(pl0 + q) : PT::zero();
         }
 #pragma unroll
-        for (int t = 0; t < BLK_UNROLL; ++t) {
-            int idx;
-            T v;
-            PT::unpack(cur[t], idx, v);
-            const Vec m = *reinterpret_cast<const Vec*>(tsub + (size_t)idx * KP);
-            const T* pm = reinterpret_cast<const T*>(&m);
-#pragma unroll
-            for (int u = 0; u < VEC; ++u) acc[u] = fma(v, pm[u], acc[u]);
-        }
-#pragma unroll
-        for (int t = 0; t < BLK_UNROLL; ++t) cur[t] = nxt[t];
+        for (int t = 0; t < BLK_U; ++t)
+            if (j + t < nq) PT::fma_row(C[t], tsub, acc);
     }
     // fold the npi groups onto group 0
+#pragma unroll 4
     for (int gq = 1; gq < npi; ++gq) {
 #pragma unroll
         for (int u = 0; u < VEC; ++u) {
             const T o = __shfl_down_sync(INMF_FULL_MASK, acc[u], gq * lpn);
-            if (grp == 0) acc[u] += o;
+            acc[u] += (grp == 0) ? o : T(0);
         }
     }
 }
 
-template <typename T>
+template <typename T, int LPN_T>
 __global__ void __launch_bounds__(1024, 1)
 blocked_spmm_kernel(const int64_t* __restrict__ work, const int64_t* __restrict__ ptr,
                     const typename PairTraits<T>::Pair* __restrict__ pairs, const T* __restrict__ dense, int KP,
@@ -167,19 +200,20 @@ blocked_spmm_kernel(const int64_t* __restrict__ work, const int64_t* __restrict_
             bulk_g2s(dst + off, src + off, (uint32_t)n, bar);
         }
     }
-    mbar_wait(bar, 0);
-
     const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int lpn = KP / VEC;         // lanes per non-zero
-    const int npi = 32 / lpn;         // non-zeros in flight per warp instruction
+    const int lpn = LPN_T > 0 ? LPN_T : KP / VEC;  // lanes per non-zero
+    const int npi = 32 / lpn;                      // non-zeros per warp instruction
     const int grp = lane / lpn, sub = lane - grp * lpn;
     const bool active = grp < npi;
+    const uint32_t tsub = smem_u32(tile) + (uint32_t)((active ? sub : 0) * VEC * sizeof(T));
     int64_t r = row_begin + warp;
     int64_t beg = 0, end = 0;
-    if (r < row_end) {
+    if (r < row_end) {  // overlaps the tile copy
         beg = ptr[ptr_base + r];
         end = ptr[ptr_base + r + 1];
     }
+    mbar_wait(bar, 0);
+
     while (r < row_end) {
         // prefetch the next row's extent while this one is processed
         const int64_t rn = r + nwarps;
@@ -190,7 +224,7 @@ blocked_spmm_kernel(const int64_t* __restrict__ work, const int64_t* __restrict_
         }
         if (beg != end) {
             T acc[VEC];
-            warp_sparse_dot<T>(pairs, beg, end, tile, KP, lpn, npi, active ? grp : 0, active ? sub : 0, active, acc);
+            warp_row_dot<T, LPN_T>(pairs + beg, (int)(end - beg), lpn, grp, active, tsub, acc);
             if (grp == 0) {
                 T* o = out + (out_row_base + r) * ldo + sub * VEC;
 #pragma unroll

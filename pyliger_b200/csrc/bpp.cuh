@@ -58,7 +58,9 @@ __host__ __device__ inline size_t bpp_warp_scratch_elems(int k) {
     const size_t fast = (size_t)32 * BppTraits<T>::LDL_FAST;
     if (l_elems < fast) l_elems = fast;
     l_elems = (l_elems + 3) & ~(size_t)3;
-    size_t total = l_elems + 3 * (size_t)((k + 3) & ~3) + 64 / sizeof(T);
+    const size_t kp = (k + 3) & ~3;
+    const size_t zk = kp < 36 ? 36 : kp;  // the fast path writes z for all 32 lanes (+ padded reads)
+    size_t total = l_elems + 2 * kp + zk + 64 / sizeof(T);
     return (total + 3) & ~(size_t)3;
 }
 
@@ -74,7 +76,7 @@ __device__ __forceinline__ BppWarpScratch<T> bpp_carve(T* base, int k) {
     s.L = base;
     s.r = s.L + l_elems;
     s.z = s.r + kp;
-    s.dinv = s.z + kp;
+    s.dinv = s.z + (kp < 36 ? 36 : kp);
     s.idx = reinterpret_cast<uint8_t*>(s.dinv + kp);
     return s;
 }
@@ -111,108 +113,7 @@ __device__ __forceinline__ T warp_max(T v) {
     return v;
 }
 
-// ------------------------------------------------------------------------------------------------
-// Fast path: |P| = p <= 31.  Lane i owns compacted row i (i < p: G_PP row, i == p: the r_P row).
-// ------------------------------------------------------------------------------------------------
-template <typename T>
-__device__ __forceinline__ void bpp_solve_passive_fast(const T* __restrict__ Gs, int ldg, BppWarpScratch<T>& sc,
-                                                       int k, uint64_t P, int p, T r0, T r1, T& x0, T& x1, T& y0,
-                                                       T& y1, BppCounters& cnt) {
-    typedef BppTraits<T> TR;
-    typedef typename TR::Vec Vec;
-    constexpr int VEC = TR::VEC;
-    constexpr int LDL = TR::LDL_FAST;
-    const int lane = threadIdx.x & 31;
-    const int j0 = lane, j1 = lane + 32;
-    const bool has0 = j0 < k, has1 = j1 < k;
-    const bool pas0 = has0 && mask_bit(P, j0);
-    const bool pas1 = has1 && mask_bit(P, j1);
-    const int pos0 = __popcll(P & ((1ull << j0) - 1ull));
-    const int pos1 = __popcll(P & ((1ull << j1) - 1ull));
-    if (pas0) sc.idx[pos0] = (uint8_t)j0;
-    if (pas1) sc.idx[pos1] = (uint8_t)j1;
-    __syncwarp();
-    const int myidx = (lane < p) ? (int)sc.idx[lane] : 0;
-    const T* __restrict__ Grow = Gs + myidx * ldg;
-    const T* __restrict__ rsh = sc.r;
-    T* __restrict__ Ls = sc.L;
-    T* __restrict__ Lmine = Ls + lane * LDL;
-    const bool is_g = lane < p, is_r = lane == p;
-    T L[32];
-    T w = T(0), mydinv = T(0);
-    int nfail = 0;
-    // Branch-free body: every lane executes every instruction; roles are applied with selects.
-#pragma unroll
-    for (int c = 0; c < BPP_FAST_MAX_P; ++c) {
-        if (c >= p) break;
-        const int ic = __shfl_sync(INMF_FULL_MASK, myidx, c);
-        const T gv = Grow[ic];
-        const T rv = rsh[ic];
-        T s = is_g ? gv : (is_r ? rv : T(0));
-        T s2 = T(0);
-        const T* __restrict__ Lc = Ls + c * LDL;
-#pragma unroll
-        for (int jb = 0; jb < c; jb += VEC) {
-            const Vec v = *reinterpret_cast<const Vec*>(Lc + jb);
-            const T* pv = reinterpret_cast<const T*>(&v);
-#pragma unroll
-            for (int u = 0; u < VEC; ++u) {
-                if (jb + u < c) {
-                    if (u & 1) s2 = fma(-L[jb + u], pv[u], s2);
-                    else s = fma(-L[jb + u], pv[u], s);
-                }
-            }
-        }
-        s += s2;
-        const T d = __shfl_sync(INMF_FULL_MASK, s, c);
-        const bool pd = d > T(0);
-        const T di = pd ? inmf_rsqrt<T>(pd ? d : T(1)) : T(0);
-        nfail += pd ? 0 : 1;
-        const T l = (lane >= c) ? s * di : T(0);
-        L[c] = l;
-        Lmine[c] = l;
-        mydinv = (lane == c) ? di : mydinv;
-        const T t = __shfl_sync(INMF_FULL_MASK, l, p);  // w_c = L[p][c]
-        w = (lane == c) ? t : w;
-        __syncwarp();
-    }
-    // right-looking back substitution z = L^-T w; afterwards lane c holds z_c
-    for (int c = p - 1; c >= 0; --c) {
-        const T zc = __shfl_sync(INMF_FULL_MASK, w * mydinv, c);
-        const T lv = Ls[c * LDL + lane];
-        w = (lane < c) ? fma(-lv, zc, w) : ((lane == c) ? zc : w);
-    }
-    T z = is_g ? w : T(0);
-    const T zscale = warp_max(inmf_abs(z));
-    z = zero_x<T>(z, zscale);
-    const T t0 = __shfl_sync(INMF_FULL_MASK, z, pos0 & 31);
-    const T t1 = __shfl_sync(INMF_FULL_MASK, z, pos1 & 31);
-    x0 = pas0 ? t0 : T(0);
-    x1 = pas1 ? t1 : T(0);
-    // y = G x - r on the non-passive rows
-    T a0 = T(0), a1 = T(0);
-    const T* __restrict__ G0 = Gs + (has0 ? j0 : 0) * ldg;
-    const T* __restrict__ G1 = Gs + (has1 ? j1 : 0) * ldg;
-    if (k > 32) {
-        for (int c = 0; c < p; ++c) {
-            const int ic = __shfl_sync(INMF_FULL_MASK, myidx, c);
-            const T zc = __shfl_sync(INMF_FULL_MASK, z, c);
-            a0 = fma(G0[ic], zc, a0);
-            a1 = fma(G1[ic], zc, a1);
-        }
-    } else {
-        for (int c = 0; c < p; ++c) {
-            const int ic = __shfl_sync(INMF_FULL_MASK, myidx, c);
-            const T zc = __shfl_sync(INMF_FULL_MASK, z, c);
-            a0 = fma(G0[ic], zc, a0);
-        }
-    }
-    y0 = (!has0 || pas0) ? T(0) : zero_y<T>(a0, r0);
-    y1 = (!has1 || pas1) ? T(0) : zero_y<T>(a1, r1);
-    __syncwarp();
-    cnt.nfail += nfail;
-    cnt.nfact++;
-}
+#include "bpp_fast.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // General path: any |P| <= 64, L in the shared scratch.

@@ -14,9 +14,13 @@ extern "C" const char* inmf_last_error(void) { return g_inmf_err; }
 
 // =================================================================================================
 // K3: batched BPP
+#ifndef BPP_THREADS
+#define BPP_THREADS 128
+#define BPP_MIN_BLOCKS 6
+#endif
 // =================================================================================================
 template <typename T>
-__global__ void __launch_bounds__(256, 2) bpp_kernel(const double* __restrict__ G, const T* R, int64_t ldr, T* X, int64_t ldx,
+__global__ void __launch_bounds__(BPP_THREADS, BPP_MIN_BLOCKS) bpp_kernel(const double* __restrict__ G, const T* R, int64_t ldr, T* X, int64_t ldx,
                            T* __restrict__ Y, int64_t ldy, uint64_t* __restrict__ mask, int warm, const int64_t* __restrict__ seg_off, int k,
                            long long* __restrict__ stats) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -36,6 +40,8 @@ __global__ void __launch_bounds__(256, 2) bpp_kernel(const double* __restrict__ 
     __syncthreads();
     size_t goff = ((size_t)k * ldg + 3) & ~(size_t)3;
     BppWarpScratch<T> sc = bpp_carve<T>(smem + goff + (size_t)warp * bpp_warp_scratch_elems<T>(k), k);
+    if (lane < 16) reinterpret_cast<uint32_t*>(sc.idx)[lane] = 0u;  // padded index reads stay in range
+    __syncwarp();
 
     long long n_notconv = 0, n_fact = 0, n_backup = 0, n_fail = 0, n_rounds = 0, max_rounds = 0, n_cols = 0;
     for (int64_t c = (int64_t)blockIdx.x * nwarps + warp; c < ncols; c += (int64_t)gridDim.x * nwarps) {
@@ -88,7 +94,7 @@ static int32_t bpp_launch(const double* G, const T* R, int64_t ldr, T* X, int64_
     const int ldg = k | 1;
     const size_t goff = ((size_t)k * ldg + 3) & ~(size_t)3;
     const size_t per_warp = bpp_warp_scratch_elems<T>(k) * sizeof(T);
-    int nwarps = 8;
+    int nwarps = BPP_THREADS / 32;
     while (nwarps > 1 && goff * sizeof(T) + nwarps * per_warp > 64 * 1024) nwarps >>= 1;
     const size_t smem = goff * sizeof(T) + nwarps * per_warp;
     INMF_REQUIRE(smem <= 227 * 1024, "shared memory budget exceeded");
@@ -795,6 +801,22 @@ extern "C" int32_t inmf_normal_eq_f64(const double* A, const double* B, int64_t 
 // =================================================================================================
 // v2 hot kernels: blocked sparse x shared dense tile (blocked.cuh)
 // =================================================================================================
+template <typename T, int LPN_T>
+static int32_t blocked_launch_one(const int64_t* work, int32_t nwork, const int64_t* ptr, const void* pairs,
+                                  const T* dense, int32_t kp, T* out, int64_t ldo, int32_t k, size_t smem,
+                                  double* gram_out, void* stream) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        INMF_CUDA_CHECK(cudaFuncSetAttribute(blocked_spmm_kernel<T, LPN_T>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_done = true;
+    }
+    blocked_spmm_kernel<T, LPN_T><<<(unsigned)nwork, 1024, smem, (cudaStream_t)stream>>>(
+        work, ptr, reinterpret_cast<const typename PairTraits<T>::Pair*>(pairs), dense, kp, out, ldo, k, gram_out);
+    INMF_LAUNCH_CHECK();
+    return 0;
+}
+
 template <typename T>
 static int32_t blocked_launch(const int64_t* work, int32_t nwork, const int64_t* ptr, const void* pairs, const T* dense,
                               int32_t kp, T* out, int64_t ldo, int32_t k, int32_t max_tile_rows, double* gram_out,
@@ -805,17 +827,23 @@ static int32_t blocked_launch(const int64_t* work, int32_t nwork, const int64_t*
     if (nwork <= 0) return 0;
     const size_t smem = 128 + (size_t)max_tile_rows * kp * sizeof(T);
     INMF_REQUIRE(smem <= 227 * 1024, "dense tile does not fit in shared memory");
-    static bool attr_done[2] = {false, false};
-    const int ti = sizeof(T) == 8;
-    if (!attr_done[ti]) {
-        INMF_CUDA_CHECK(cudaFuncSetAttribute(blocked_spmm_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             227 * 1024));
-        attr_done[ti] = true;
+    const int lpn = kp / PairTraits<T>::VEC;
+#define INMF_BLK_CASE(L)                                                                                          \
+    case L:                                                                                                       \
+        return blocked_launch_one<T, L>(work, nwork, ptr, pairs, dense, kp, out, ldo, k, smem, gram_out, stream)
+    switch (lpn) {  // lanes per non-zero fixed at compile time for the common factor counts
+        INMF_BLK_CASE(5);   // f32 k <= 20
+        INMF_BLK_CASE(8);   // f32 k <= 32
+        INMF_BLK_CASE(10);  // f32 k <= 40, f64 k <= 20
+        INMF_BLK_CASE(15);  // f32 k <= 60
+        INMF_BLK_CASE(16);  // f32 k <= 64, f64 k <= 32
+        INMF_BLK_CASE(20);  // f64 k <= 40
+        INMF_BLK_CASE(30);  // f64 k <= 60
+        INMF_BLK_CASE(32);  // f64 k <= 64
+        default:
+            return blocked_launch_one<T, 0>(work, nwork, ptr, pairs, dense, kp, out, ldo, k, smem, gram_out, stream);
     }
-    blocked_spmm_kernel<T><<<(unsigned)nwork, 1024, smem, (cudaStream_t)stream>>>(
-        work, ptr, reinterpret_cast<const typename PairTraits<T>::Pair*>(pairs), dense, kp, out, ldo, k, gram_out);
-    INMF_LAUNCH_CHECK();
-    return 0;
+#undef INMF_BLK_CASE
 }
 extern "C" int32_t inmf_blocked_spmm_f32(const int64_t* work, int32_t nwork, const int64_t* ptr, const void* pairs,
                                          const float* dense, int32_t kp, float* out, int64_t ldo, int32_t k,

@@ -194,7 +194,9 @@ def _emulate_blocked(bp, dense, kp, out, k, gram=None):
     work = bp.work.numpy()[:bp.nwork]
     ptr = bp.ptr.numpy()
     pairs = bp.pairs.numpy()
-    idx = pairs[:, 0].astype(np.int64)
+    esize = 4 if pairs.dtype == np.int32 else 8
+    assert np.all(pairs[:, 0] % (kp * esize) == 0)  # premultiplied byte offsets of tile rows
+    idx = pairs[:, 0].astype(np.int64) // (kp * esize)
     vals = pairs[:, 1].copy().view(np.float32 if pairs.dtype == np.int32 else np.float64).astype(np.float64)
     for ptr_base, dense_row0, tile_rows, r0, r1, out_base, gram_seg, _ in work:
         tile = dense[dense_row0:dense_row0 + tile_rows]
