@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--cpu-cols", type=int, default=20000)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-ginv", action="store_true", help="cold start without the G^-1 full-set shortcut")
     args = ap.parse_args()
     import torch
     from pyliger_b200 import _lib
@@ -61,6 +62,7 @@ def main():
         Xo = torch.empty_like(Rt)
         mask = torch.zeros(args.cols, dtype=torch.int64, device=dev)
         seg = torch.tensor([0, args.cols], dtype=torch.int64, device=dev)
+        ginv = torch.empty(k, k, dtype=torch.float64, device=dev)
         res = {"k": k, "cols": args.cols, "dtype": args.dtype}
         for mode, warm in (("cold", 0), ("warm", 1)):
             times = []
@@ -68,7 +70,8 @@ def main():
                 stats = torch.zeros(8, dtype=torch.int64, device=dev)
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-                _lib.call("inmf_bpp", args.dtype, Gd, Rt, k, Xo, k, None, 0, mask, warm, seg, 1, args.cols, k, stats, _stream())
+                _lib.call("inmf_bpp", args.dtype, Gd, Rt, k, Xo, k, None, 0, mask, warm, seg, 1, args.cols, k, stats,
+                          None if (warm or args.no_ginv) else ginv, _stream())
                 e1.record()
                 torch.cuda.synchronize()
                 if rep > 0:

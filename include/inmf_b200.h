@@ -56,13 +56,16 @@ int64_t inmf_launch_count(void);
  *            (the reference's `init` argument, _utilities.py:222-225)
  *   seg_off  device int64[nseg+1] column ranges;  max_seg_cols = max segment length (host value)
  *   stats    device int64[INMF_BPP_NSTATS], accumulated (caller zeroes)
+ *   ginv_ws  device double[nseg][k][k] workspace or NULL.  If given, G^-1 is formed per segment first
+ *            and the "all indices passive" solves (the first round of every cold start on non-negative
+ *            right-hand sides) become one k x k mat-vec; the result is the same NNLS solution.
  */
 int32_t inmf_bpp_f32(const double* G, const float* R, int64_t ldr, float* X, int64_t ldx, float* Y,
                      int64_t ldy, uint64_t* mask, int32_t warm, const int64_t* seg_off, int32_t nseg,
-                     int64_t max_seg_cols, int32_t k, int64_t* stats, void* stream);
+                     int64_t max_seg_cols, int32_t k, int64_t* stats, double* ginv_ws, void* stream);
 int32_t inmf_bpp_f64(const double* G, const double* R, int64_t ldr, double* X, int64_t ldx, double* Y,
                      int64_t ldy, uint64_t* mask, int32_t warm, const int64_t* seg_off, int32_t nseg,
-                     int64_t max_seg_cols, int32_t k, int64_t* stats, void* stream);
+                     int64_t max_seg_cols, int32_t k, int64_t* stats, double* ginv_ws, void* stream);
 
 /* H-update preparation per segment s (replaces the hstack/AtA of _iNMF_ANLS.py:137 +
  * _utilities.py:212 and _online_iNMF.py:421): Mt[s] = Wt + Vt[s] (zero padded to ldm),

@@ -14,7 +14,7 @@ _I32, _I64, _F64, _PTR = _c.c_int32, _c.c_int64, _c.c_double, _c.c_void_p
 
 # name -> argtypes (without the _f32/_f64 suffix; P = device pointer or stream)
 _TYPED = {
-    "inmf_bpp": [_PTR, _PTR, _I64, _PTR, _I64, _PTR, _I64, _PTR, _I32, _PTR, _I32, _I64, _I32, _PTR, _PTR],
+    "inmf_bpp": [_PTR, _PTR, _I64, _PTR, _I64, _PTR, _I64, _PTR, _I32, _PTR, _I32, _I64, _I32, _PTR, _PTR, _PTR],
     "inmf_prep": [_PTR, _PTR, _PTR, _I64, _PTR, _PTR, _PTR, _F64, _I32, _I64, _I32, _PTR],
     "inmf_spmm": [_PTR, _PTR, _PTR, _PTR, _I64, _I64, _PTR, _I64, _PTR, _I32, _I64, _I32, _PTR],
     "inmf_stats": [_PTR, _PTR, _PTR, _PTR, _I64, _PTR, _PTR, _I64, _PTR, _I32, _I64, _I32, _PTR],

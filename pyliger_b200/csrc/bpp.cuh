@@ -199,6 +199,41 @@ __device__ __noinline__ void bpp_solve_passive_general(const T* __restrict__ Gs,
     cnt.nfact++;
 }
 
+// All k indices passive: x = G^-1 r from the shared copy of the inverse, y = 0.
+template <typename T>
+__device__ __forceinline__ void bpp_solve_full(const T* __restrict__ Gis, int ldg, BppWarpScratch<T>& sc, int k, T& x0,
+                                               T& x1, T& y0, T& y1, BppCounters& cnt) {
+    const int lane = threadIdx.x & 31;
+    const bool has0 = lane < k, has1 = lane + 32 < k;
+    const T* __restrict__ I0 = Gis + (has0 ? lane : 0) * ldg;
+    const T* __restrict__ I1 = Gis + (has1 ? lane + 32 : 0) * ldg;
+    const T* __restrict__ r = sc.r;
+    T a0 = T(0), b0 = T(0), a1 = T(0), b1 = T(0);
+    int c = 0;
+    for (; c + 1 < k; c += 2) {
+        const T rc = r[c], rd = r[c + 1];
+        a0 = fma(I0[c], rc, a0);
+        b0 = fma(I0[c + 1], rd, b0);
+        if (k > 32) {
+            a1 = fma(I1[c], rc, a1);
+            b1 = fma(I1[c + 1], rd, b1);
+        }
+    }
+    if (c < k) {
+        a0 = fma(I0[c], r[c], a0);
+        if (k > 32) a1 = fma(I1[c], r[c], a1);
+    }
+    a0 = has0 ? a0 + b0 : T(0);
+    a1 = has1 ? a1 + b1 : T(0);
+    const T m = inmf_abs(a0) > inmf_abs(a1) ? inmf_abs(a0) : inmf_abs(a1);
+    const T zscale = warp_max(m);
+    x0 = zero_x<T>(a0, zscale);
+    x1 = zero_x<T>(a1, zscale);
+    y0 = T(0);
+    y1 = T(0);
+    cnt.nfact++;
+}
+
 template <typename T>
 __device__ __forceinline__ void bpp_solve_passive(const T* __restrict__ Gs, int ldg, BppWarpScratch<T>& sc, int k,
                                                   uint64_t P, T r0, T r1, T& x0, T& x1, T& y0, T& y1,
@@ -213,7 +248,8 @@ __device__ __forceinline__ void bpp_solve_passive(const T* __restrict__ Gs, int 
 // Full BPP for one column.  r0/r1: this lane's entries of r (factor lane, lane+32; 0 beyond k).
 // P: in = warm-start passive set (ignored unless warm), out = final passive set.
 template <typename T>
-__device__ __forceinline__ void bpp_column(const T* __restrict__ Gs, int ldg, BppWarpScratch<T>& sc, int k,
+__device__ __forceinline__ void bpp_column(const T* __restrict__ Gs, const T* __restrict__ Gis, int ldg,
+                                           BppWarpScratch<T>& sc, int k,
                                            T r0, T r1, uint64_t& P, bool warm, T& x0, T& x1, T& y0, T& y1,
                                            BppCounters& cnt) {
     const int lane = threadIdx.x & 31;
@@ -229,7 +265,9 @@ __device__ __forceinline__ void bpp_column(const T* __restrict__ Gs, int ldg, Bp
     int rounds = 0;
     while (true) {
         // evaluate the current partition (single call site keeps the unrolled solver in one copy)
-        if (P != 0ull) {
+        if (P == kmask && Gis != nullptr) {
+            bpp_solve_full<T>(Gis, ldg, sc, k, x0, x1, y0, y1, cnt);
+        } else if (P != 0ull) {
             bpp_solve_passive<T>(Gs, ldg, sc, k, P, r0, r1, x0, x1, y0, y1, cnt);
         } else {
             x0 = T(0);

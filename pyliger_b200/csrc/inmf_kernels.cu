@@ -19,8 +19,44 @@ extern "C" const char* inmf_last_error(void) { return g_inmf_err; }
 #define BPP_MIN_BLOCKS 6
 #endif
 // =================================================================================================
+// In-place Gauss-Jordan inverse of every segment's SPD normal matrix (double, one CTA per segment).
+// Used for the "all indices passive" solve x = G^-1 r, which is what the first round of a cold start
+// always asks for when the right-hand sides are non-negative.  A non-positive pivot marks the inverse
+// invalid (NaN in element 0) and the solver falls back to the Cholesky paths.
+__global__ void ginv_kernel(const double* __restrict__ G, double* __restrict__ Ginv, int k) {
+    extern __shared__ double ginv_a[];
+    __shared__ double f[INMF_MAX_K];
+    const int seg = blockIdx.x;
+    const int t = threadIdx.x, nt = blockDim.x;
+    for (int e = t; e < k * k; e += nt) ginv_a[e] = G[(size_t)seg * k * k + e];
+    bool ok = true;
+    for (int p = 0; p < k; ++p) {
+        __syncthreads();
+        const double piv = ginv_a[p * k + p];
+        if (!(piv > 0.0)) {
+            ok = false;
+            break;
+        }
+        __syncthreads();
+        if (t < k) {
+            ginv_a[p * k + t] = ((t == p) ? 1.0 : ginv_a[p * k + t]) / piv;
+        } else if (t - k < k && t - k != p) {  // a second group of threads saves / clears column p
+            f[t - k] = ginv_a[(t - k) * k + p];
+            ginv_a[(t - k) * k + p] = 0.0;
+        }
+        __syncthreads();
+        for (int e = t; e < k * k; e += nt) {
+            const int i = e / k, j = e - i * k;
+            if (i != p) ginv_a[e] -= f[i] * ginv_a[p * k + j];
+        }
+    }
+    __syncthreads();
+    for (int e = t; e < k * k; e += nt)
+        Ginv[(size_t)seg * k * k + e] = ok ? ginv_a[e] : __longlong_as_double(0x7ff8000000000000ll);
+}
+
 template <typename T>
-__global__ void __launch_bounds__(BPP_THREADS, BPP_MIN_BLOCKS) bpp_kernel(const double* __restrict__ G, const T* R, int64_t ldr, T* X, int64_t ldx,
+__global__ void __launch_bounds__(BPP_THREADS, BPP_MIN_BLOCKS) bpp_kernel(const double* __restrict__ G, const double* __restrict__ Ginv, const T* R, int64_t ldr, T* X, int64_t ldx,
                            T* __restrict__ Y, int64_t ldy, uint64_t* __restrict__ mask, int warm, const int64_t* __restrict__ seg_off, int k,
                            long long* __restrict__ stats) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -37,8 +73,16 @@ __global__ void __launch_bounds__(BPP_THREADS, BPP_MIN_BLOCKS) bpp_kernel(const 
     T* Gs = smem;
     const double* Gseg = G + (size_t)seg * k * k;
     for (int t = threadIdx.x; t < k * k; t += blockDim.x) Gs[(t / k) * ldg + (t % k)] = (T)Gseg[t];
-    __syncthreads();
     size_t goff = ((size_t)k * ldg + 3) & ~(size_t)3;
+    const T* Gis = nullptr;  // shared copy of G^-1 (full-passive-set solve), if provided and valid
+    if (Ginv != nullptr) {
+        const double* Iseg = Ginv + (size_t)seg * k * k;
+        T* Gi = smem + goff;
+        for (int t = threadIdx.x; t < k * k; t += blockDim.x) Gi[(t / k) * ldg + (t % k)] = (T)Iseg[t];
+        if (Iseg[0] == Iseg[0]) Gis = Gi;
+        goff *= 2;
+    }
+    __syncthreads();
     BppWarpScratch<T> sc = bpp_carve<T>(smem + goff + (size_t)warp * bpp_warp_scratch_elems<T>(k), k);
     if (lane < 16) reinterpret_cast<uint32_t*>(sc.idx)[lane] = 0u;  // padded index reads stay in range
     __syncwarp();
@@ -52,7 +96,7 @@ __global__ void __launch_bounds__(BPP_THREADS, BPP_MIN_BLOCKS) bpp_kernel(const 
         uint64_t P = (warm && mask) ? mask[col] : 0ull;
         T x0, x1, y0, y1;
         BppCounters cnt = {0, 0, 0, 0, true};
-        bpp_column<T>(Gs, ldg, sc, k, r0, r1, P, warm != 0, x0, x1, y0, y1, cnt);
+        bpp_column<T>(Gs, Gis, ldg, sc, k, r0, r1, P, warm != 0, x0, x1, y0, y1, cnt);
         T* x = X + col * ldx;
         if (lane < k) x[lane] = x0;
         if (lane + 32 < k) x[lane + 32] = x1;
@@ -86,13 +130,13 @@ __global__ void __launch_bounds__(BPP_THREADS, BPP_MIN_BLOCKS) bpp_kernel(const 
 template <typename T>
 static int32_t bpp_launch(const double* G, const T* R, int64_t ldr, T* X, int64_t ldx, T* Y, int64_t ldy,
                           uint64_t* mask, int32_t warm, const int64_t* seg_off, int32_t nseg,
-                          int64_t max_seg_cols, int32_t k, int64_t* stats, void* stream) {
+                          int64_t max_seg_cols, int32_t k, int64_t* stats, double* ginv_ws, void* stream) {
     INMF_REQUIRE(k >= 1 && k <= INMF_MAX_K, "k must be in [1, 64]");
     INMF_REQUIRE(nseg >= 1 && nseg <= 65535, "nseg out of range");
     INMF_REQUIRE(ldr >= k && ldx >= k && (Y == nullptr || ldy >= k), "leading dimensions must be >= k");
     if (max_seg_cols <= 0) return 0;
     const int ldg = k | 1;
-    const size_t goff = ((size_t)k * ldg + 3) & ~(size_t)3;
+    const size_t goff = (((size_t)k * ldg + 3) & ~(size_t)3) * (ginv_ws ? 2 : 1);
     const size_t per_warp = bpp_warp_scratch_elems<T>(k) * sizeof(T);
     int nwarps = BPP_THREADS / 32;
     while (nwarps > 1 && goff * sizeof(T) + nwarps * per_warp > 64 * 1024) nwarps >>= 1;
@@ -108,24 +152,30 @@ static int32_t bpp_launch(const double* G, const T* R, int64_t ldr, T* X, int64_
     int64_t blocks = (max_seg_cols + nwarps - 1) / nwarps;
     const int64_t cap = (int64_t)inmf_num_sms() * 16;
     if (blocks > cap) blocks = cap;
+    if (ginv_ws != nullptr) {
+        ginv_kernel<<<(unsigned)nseg, 256, (size_t)k * k * sizeof(double), (cudaStream_t)stream>>>(G, ginv_ws, k);
+        INMF_LAUNCH_CHECK();
+    }
     dim3 grid((unsigned)blocks, (unsigned)nseg);
     bpp_kernel<T><<<grid, nwarps * 32, smem, (cudaStream_t)stream>>>(
-        G, R, ldr, X, ldx, Y, ldy, mask, warm, seg_off, k, (long long*)stats);
+        G, ginv_ws, R, ldr, X, ldx, Y, ldy, mask, warm, seg_off, k, (long long*)stats);
     INMF_LAUNCH_CHECK();
     return 0;
 }
 
 extern "C" int32_t inmf_bpp_f32(const double* G, const float* R, int64_t ldr, float* X, int64_t ldx, float* Y,
                                 int64_t ldy, uint64_t* mask, int32_t warm, const int64_t* seg_off,
-                                int32_t nseg, int64_t max_seg_cols, int32_t k, int64_t* stats, void* stream) {
+                                int32_t nseg, int64_t max_seg_cols, int32_t k, int64_t* stats, double* ginv_ws,
+                                void* stream) {
     return bpp_launch<float>(G, R, ldr, X, ldx, Y, ldy, mask, warm, seg_off, nseg, max_seg_cols, k, stats,
-                             stream);
+                             ginv_ws, stream);
 }
 extern "C" int32_t inmf_bpp_f64(const double* G, const double* R, int64_t ldr, double* X, int64_t ldx,
                                 double* Y, int64_t ldy, uint64_t* mask, int32_t warm, const int64_t* seg_off,
-                                int32_t nseg, int64_t max_seg_cols, int32_t k, int64_t* stats, void* stream) {
+                                int32_t nseg, int64_t max_seg_cols, int32_t k, int64_t* stats, double* ginv_ws,
+                                void* stream) {
     return bpp_launch<double>(G, R, ldr, X, ldx, Y, ldy, mask, warm, seg_off, nseg, max_seg_cols, k, stats,
-                              stream);
+                              ginv_ws, stream);
 }
 
 // =================================================================================================

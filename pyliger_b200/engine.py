@@ -171,6 +171,7 @@ class InmfEngine(object):
         self.Rw = z(g, k)
         self.Gv = z(N, k, k, dtype=f64)
         self.Gw = z(1, k, k, dtype=f64)
+        self.ginv_ws = z(max(N, 1), k, k, dtype=f64)  # G^-1 workspace of the cold-start BPP solves
         self.xnorm2 = z(N, dtype=f64)
         self.obj = z(1, dtype=f64)
         self.bpp_stats = torch.zeros(3, 8, dtype=torch.int64, device=dev)  # rows: H, V, W solves
@@ -245,7 +246,7 @@ class InmfEngine(object):
             return
         k = self.k
         _lib.call("inmf_bpp", self.sfx, self.G, out, self.ldm, out, self.ldm, None, 0, mask, 1 if warm else 0,
-                  seg_off, nseg, max_rows, k, self.bpp_stats[0], _stream())
+                  seg_off, nseg, max_rows, k, self.bpp_stats[0], None if warm else self.ginv_ws, _stream())
 
     def solve_H(self, seg_desc=None, max_rows=None, out=None, mask=None, warm=False, nseg=None):
         """out[q,:] = argmin_{h>=0} for every row of the windows in seg_desc (default: all owned cells)."""
@@ -279,13 +280,14 @@ class InmfEngine(object):
         _lib.call("inmf_rhs_v", self.sfx, self.St, self.Wt, self.HtH, self.Rv, self.Gv, self.lam, N, g, k,
                   _stream())
         _lib.call("inmf_bpp", self.sfx, self.Gv, self.Rv, k, self.Vt, k, None, 0, self.mask_V,
-                  1 if warm else 0, self.seg_genes, N, g, k, self.bpp_stats[1], _stream())
+                  1 if warm else 0, self.seg_genes, N, g, k, self.bpp_stats[1], None if warm else self.ginv_ws,
+                  _stream())
 
     def solve_W(self, warm=False):
         k, g, N = self.k, self.g, self.N
         _lib.call("inmf_rhs_w", self.sfx, self.St, self.Vt, self.HtH, self.Rw, self.Gw, N, g, k, _stream())
         _lib.call("inmf_bpp", self.sfx, self.Gw, self.Rw, k, self.Wt, k, None, 0, self.mask_W,
-                  1 if warm else 0, self.seg_w, 1, g, k, self.bpp_stats[2], _stream())
+                  1 if warm else 0, self.seg_w, 1, g, k, self.bpp_stats[2], None if warm else self.ginv_ws, _stream())
 
     def objective(self):
         """Objective from the current St/HtH and the Mt/Gwv/Gvv of the last prep(). Device scalar."""

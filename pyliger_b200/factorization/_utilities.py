@@ -27,7 +27,8 @@ def _solve_on_device(G, Rt, init_mask, k, dtype, device, want_Y=True):
     if init_mask is not None:
         mask.copy_(init_mask)
         warm = 1
-    _lib.call("inmf_bpp", sfx, G, Rt, k, X, k, Y, k, mask, warm, seg_off, 1, cols, k, stats, _stream())
+    ginv = None if warm else torch.empty(k, k, dtype=torch.float64, device=device)
+    _lib.call("inmf_bpp", sfx, G, Rt, k, X, k, Y, k, mask, warm, seg_off, 1, cols, k, stats, ginv, _stream())
     return X, Y, mask, stats
 
 
