@@ -695,18 +695,35 @@ extern "C" int32_t inmf_update_ab_f64(double* A, double* A_old, double* B, doubl
 // =================================================================================================
 // K12/K13: HALS sweeps, warp per gene row
 // =================================================================================================
-template <typename T>
+#define HALS_MAX_SETS 16  // datasets whose V sweeps are reduced together (register arrays)
+
+// A is staged TRANSPOSED in shared memory (At[i][j][a] = A_i[a][j]) so that the per-factor dot products
+// read consecutive addresses; when it does not fit, the same index is read from global memory.
+template <typename T, bool A_IN_SMEM>
 __global__ void hals_kernel(const double* __restrict__ A, const T* __restrict__ B, T* __restrict__ Wt,
-                            T* __restrict__ Vt, double lambda, int n_prev, int nall, int64_t g, int k,
-                            int n_inner) {
+                            T* __restrict__ Vt, double lambda, int n_prev, int nall, int64_t g, int k, int n_inner) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kk = k * k;
+    T* At = reinterpret_cast<T*>(smem_raw);  // [nall][k][k] transposed (only if A_IN_SMEM)
+    const size_t a_elems = A_IN_SMEM ? (((size_t)nall * kk + 3) & ~(size_t)3) : 0;
+    if (A_IN_SMEM) {
+        for (int e = threadIdx.x; e < nall * kk; e += blockDim.x) {
+            const int i = e / kk, rem = e - i * kk, j = rem / k, a = rem - j * k;
+            At[e] = (T)A[(size_t)i * kk + (size_t)a * k + j];
+        }
+        __syncthreads();
+    }
     const int per_warp = (1 + 2 * nall) * k;
-    T* ws = reinterpret_cast<T*>(smem_raw) + (size_t)warp * per_warp;
-    T* vs = ws + k;                     // [nall][k]
-    T* bs = vs + (size_t)nall * k;      // [nall][k]
-    const T eps = T(1e-16);             // nonneg(), _utilities.py:10-13
+    T* ws = reinterpret_cast<T*>(smem_raw) + a_elems + (size_t)warp * per_warp;
+    T* vs = ws + k;                 // [nall][k]
+    T* bs = vs + (size_t)nall * k;  // [nall][k]
+    const T eps = T(1e-16);         // nonneg(), _utilities.py:10-13
     const T one_lam = (T)(1.0 + lambda);
+    const int ncur = nall - n_prev;
+    auto a_t = [&](int i, int j, int a) -> T {  // A_i[a][j]
+        return A_IN_SMEM ? At[(size_t)i * kk + j * k + a] : (T)A[(size_t)i * kk + (size_t)a * k + j];
+    };
     for (int64_t w = (int64_t)blockIdx.x * nwarps + warp; w < g; w += (int64_t)gridDim.x * nwarps) {
         for (int j = lane; j < k; j += 32) ws[j] = Wt[w * k + j];
         for (int i = 0; i < nall; ++i)
@@ -721,8 +738,7 @@ __global__ void hals_kernel(const double* __restrict__ A, const T* __restrict__ 
                 T part = T(0);
                 for (int a = lane; a < k; a += 32) {
                     const T wa = ws[a];
-                    for (int i = 0; i < nall; ++i)
-                        part += (wa + vs[i * k + a]) * (T)A[((size_t)i * k + a) * k + j];
+                    for (int i = 0; i < nall; ++i) part = fma(wa + vs[i * k + a], a_t(i, j, a), part);
                 }
                 part = warp_sum(part);
                 if (lane == 0) {
@@ -730,24 +746,43 @@ __global__ void hals_kernel(const double* __restrict__ A, const T* __restrict__ 
                     T den = T(0);
                     for (int i = 0; i < nall; ++i) {
                         num += bs[i * k + j];
-                        den += (T)A[((size_t)i * k + j) * k + j];
+                        den += a_t(i, j, j);
                     }
-                    T nw = ws[j] + num / den;
+                    const T nw = ws[j] + num / den;
                     ws[j] = nw < eps ? eps : nw;
                 }
                 __syncwarp();
             }
-            // ---- V sweep (current datasets only), j outer / dataset inner ----
+            // ---- V sweep (current datasets only): j outer, the datasets' reductions run together ----
             for (int j = 0; j < k; ++j) {
-                for (int i = n_prev; i < nall; ++i) {
-                    T part = T(0);
-                    for (int a = lane; a < k; a += 32)
-                        part += (ws[a] + one_lam * vs[i * k + a]) * (T)A[((size_t)i * k + a) * k + j];
-                    part = warp_sum(part);
-                    if (lane == 0) {
-                        const T ajj = (T)A[((size_t)i * k + j) * k + j];
-                        T nv = vs[i * k + j] + (bs[i * k + j] - part) / (one_lam * ajj);
-                        vs[i * k + j] = nv < eps ? eps : nv;
+                for (int i0 = 0; i0 < ncur; i0 += HALS_MAX_SETS) {
+                    const int cnt = (ncur - i0 < HALS_MAX_SETS) ? (ncur - i0) : HALS_MAX_SETS;
+                    T part[HALS_MAX_SETS];
+#pragma unroll
+                    for (int u = 0; u < HALS_MAX_SETS; ++u) part[u] = T(0);
+                    for (int a = lane; a < k; a += 32) {
+                        const T wa = ws[a];
+#pragma unroll
+                        for (int u = 0; u < HALS_MAX_SETS; ++u) {
+                            if (u < cnt) {
+                                const int i = n_prev + i0 + u;
+                                part[u] = fma(wa + one_lam * vs[i * k + a], a_t(i, j, a), part[u]);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                        for (int u = 0; u < HALS_MAX_SETS; ++u)
+                            if (u < cnt) part[u] += __shfl_xor_sync(INMF_FULL_MASK, part[u], o);
+                    }
+#pragma unroll
+                    for (int u = 0; u < HALS_MAX_SETS; ++u) {
+                        if (u < cnt && lane == u) {  // lane u finishes dataset u
+                            const int i = n_prev + i0 + u;
+                            const T nv = vs[i * k + j] + (bs[i * k + j] - part[u]) / (one_lam * a_t(i, j, j));
+                            vs[i * k + j] = nv < eps ? eps : nv;
+                        }
                     }
                     __syncwarp();
                 }
@@ -765,21 +800,32 @@ static int32_t hals_launch(const double* A, const T* B, T* Wt, T* Vt, double lam
     INMF_REQUIRE(k >= 1 && k <= INMF_MAX_K && nall >= 1 && g >= 1, "bad shape");
     INMF_REQUIRE(n_prev >= 0 && n_prev <= nall && n_inner >= 0, "bad n_prev / n_inner");
     const size_t per_warp = (size_t)(1 + 2 * nall) * k * sizeof(T);
+    const size_t a_bytes = ((((size_t)nall * k * k) + 3) & ~(size_t)3) * sizeof(T);
+    const bool a_smem = a_bytes <= 112 * 1024;
+    const size_t budget = 220 * 1024 - (a_smem ? a_bytes : 0);
     int nwarps = 8;
-    while (nwarps > 1 && nwarps * per_warp > 96 * 1024) nwarps >>= 1;
-    const size_t smem = nwarps * per_warp;
+    while (nwarps > 1 && nwarps * per_warp > budget) nwarps >>= 1;
+    const size_t smem = (a_smem ? a_bytes : 0) + nwarps * per_warp;
     INMF_REQUIRE(smem <= 227 * 1024, "too many datasets for the HALS shared-memory staging");
-    static bool attr_done[2] = {false, false};
+    static bool attr_done[2][2] = {{false, false}, {false, false}};
     const int ti = sizeof(T) == 8;
-    if (!attr_done[ti]) {
-        INMF_CUDA_CHECK(cudaFuncSetAttribute(hals_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             227 * 1024));
-        attr_done[ti] = true;
+    if (!attr_done[ti][a_smem]) {
+        if (a_smem)
+            INMF_CUDA_CHECK(cudaFuncSetAttribute(hals_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 227 * 1024));
+        else
+            INMF_CUDA_CHECK(cudaFuncSetAttribute(hals_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 227 * 1024));
+        attr_done[ti][a_smem] = true;
     }
     int64_t blocks = (g + nwarps - 1) / nwarps;
     if (blocks > inmf_num_sms() * 8) blocks = inmf_num_sms() * 8;
-    hals_kernel<T><<<(unsigned)blocks, nwarps * 32, smem, (cudaStream_t)stream>>>(A, B, Wt, Vt, lambda, n_prev, nall,
-                                                                                g, k, n_inner);
+    if (a_smem)
+        hals_kernel<T, true><<<(unsigned)blocks, nwarps * 32, smem, (cudaStream_t)stream>>>(A, B, Wt, Vt, lambda, n_prev,
+                                                                                          nall, g, k, n_inner);
+    else
+        hals_kernel<T, false><<<(unsigned)blocks, nwarps * 32, smem, (cudaStream_t)stream>>>(A, B, Wt, Vt, lambda, n_prev,
+                                                                                           nall, g, k, n_inner);
     INMF_LAUNCH_CHECK();
     return 0;
 }
