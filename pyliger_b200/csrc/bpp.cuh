@@ -87,6 +87,7 @@ struct BppCounters {
     int nbackup;
     int nfail;
     bool ok;
+    int h[6];  // experiment counters (BPP_HIST builds only)
 };
 
 __device__ __forceinline__ bool mask_bit(uint64_t m, int j) { return (m >> j) & 1ull; }
@@ -281,6 +282,17 @@ __device__ __forceinline__ void bpp_column(const T* __restrict__ Gs, const T* __
                            ((uint64_t)__ballot_sync(INMF_FULL_MASK, bad1) << 32);
         const int bad = __popcll(I);
         if (bad == 0) break;
+#ifdef BPP_HIST  // experiment: size of the first exchange set
+        if (rounds == 0) {
+            const int rem = __popcll(I & P);
+            cnt.h[0] = (bad == 1 && rem == 1);   // one removal
+            cnt.h[1] = (bad == 1 && rem == 0);   // one addition
+            cnt.h[2] = (bad == 2);
+            cnt.h[3] = (bad == 3 || bad == 4);
+            cnt.h[4] = (bad >= 5);
+        }
+        if (rounds == 1) cnt.h[5] = 1;           // needed a third solve
+#endif
         ++rounds;
         if (rounds > max_rounds) {
             cnt.ok = false;

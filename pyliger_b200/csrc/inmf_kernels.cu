@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(BPP_THREADS, BPP_MIN_BLOCKS) bpp_kernel(const 
         const T r1 = (lane + 32 < k) ? r[lane + 32] : T(0);
         uint64_t P = (warm && mask) ? mask[col] : 0ull;
         T x0, x1, y0, y1;
-        BppCounters cnt = {0, 0, 0, 0, true};
+        BppCounters cnt = {0, 0, 0, 0, true, {0, 0, 0, 0, 0, 0}};
         bpp_column<T>(Gs, Gis, ldg, sc, k, r0, r1, P, warm != 0, x0, x1, y0, y1, cnt);
         T* x = X + col * ldx;
         if (lane < k) x[lane] = x0;
@@ -108,12 +108,21 @@ __global__ void __launch_bounds__(BPP_THREADS, BPP_MIN_BLOCKS) bpp_kernel(const 
         if (mask && lane == 0) mask[col] = P;
         if (lane == 0) {
             n_cols++;
+#ifndef BPP_HIST
             n_notconv += cnt.ok ? 0 : 1;
             n_fact += cnt.nfact;
             n_backup += cnt.nbackup;
             n_fail += cnt.nfail;
             n_rounds += cnt.rounds;
             max_rounds = max_rounds > cnt.rounds ? max_rounds : cnt.rounds;
+#else
+            n_notconv += cnt.h[0];
+            n_fact += cnt.h[1];
+            n_backup += cnt.h[2];
+            n_fail += cnt.h[3];
+            n_rounds += cnt.h[4];
+            max_rounds += cnt.h[5];
+#endif
         }
     }
     if (stats && lane == 0 && n_cols) {

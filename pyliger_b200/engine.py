@@ -96,9 +96,10 @@ class DeviceCSR(object):
         self.own_off = np.concatenate([[0], np.cumsum(self.n_own)]).astype(np.int64)
         self.n_total = int(self.row_base[-1])
         self.n_own_total = int(self.own_off[-1])
-        ndt = np.float32 if dtype == torch.float32 else np.float64
+        # The index / value arrays go to the device straight from scipy's own buffers (no host-side
+        # concatenation or dtype conversion pass); casts happen on the device.
         indptr = [np.zeros(1, dtype=np.int64)]
-        cols, vals = [], []
+        pieces = []
         off = 0
         for m, (lo, hi) in zip(mats, self.bounds):
             if m.shape[1] != self.g:
@@ -109,17 +110,26 @@ class DeviceCSR(object):
                 m = m.sorted_indices()
             p0, p1 = int(m.indptr[lo]), int(m.indptr[hi])
             indptr.append(m.indptr[lo + 1:hi + 1].astype(np.int64) - p0 + off)
-            cols.append(m.indices[p0:p1].astype(np.int32, copy=False))
-            vals.append(m.data[p0:p1].astype(ndt, copy=False))
+            pieces.append((off, m.indices[p0:p1], m.data[p0:p1]))
             off += p1 - p0
         self.nnz = off
-        self.host = (np.concatenate(indptr), np.concatenate(cols) if cols else np.zeros(0, np.int32),
-                     np.concatenate(vals) if vals else np.zeros(0, ndt))
-        self.h2d_bytes = sum(a.nbytes for a in self.host)
-        ts = [torch.from_numpy(a) for a in self.host]
-        if pin:
-            ts = [t.pin_memory() for t in ts]
-        self.rowptr, self.colidx, self.vals = [t.to(device, non_blocking=pin) for t in ts]
+        self.rowptr = torch.from_numpy(np.concatenate(indptr)).to(device)
+        self.colidx = torch.empty(off, dtype=torch.int32, device=device)
+        self.vals = torch.empty(off, dtype=dtype, device=device)
+        self.h2d_bytes = self.rowptr.numel() * 8
+        for o, idx, val in pieces:
+            n = idx.shape[0]
+            if n == 0:
+                continue
+            ti = torch.from_numpy(np.ascontiguousarray(idx))
+            tv = torch.from_numpy(np.ascontiguousarray(val))
+            self.h2d_bytes += ti.numel() * ti.element_size() + tv.numel() * tv.element_size()
+            if pin:
+                ti, tv = ti.pin_memory(), tv.pin_memory()
+            di = ti.to(device, non_blocking=pin)
+            dv = tv.to(device, non_blocking=pin)
+            self.colidx[o:o + n].copy_(di)   # device-side casts (int64 -> int32, float64 -> T) if needed
+            self.vals[o:o + n].copy_(dv)
 
 
 class InmfEngine(object):

@@ -15,6 +15,8 @@ Keyword-only extensions (defaults preserve reference behaviour):
 Multi-GPU: when torch.distributed is initialised the cells are sharded over the ranks and the k x k
 and genes x k statistics are all-reduced once per iteration.
 """
+import threading
+
 import numpy as np
 from tqdm import tqdm
 
@@ -66,13 +68,31 @@ def optimize_ALS(
         raise ValueError(
             "Select k lower than the number of variable genes: {}".format(len(liger_object.var_genes)))
 
-    engine = InmfEngine(X, k, value_lambda, dtype=resolve_dtype(dtype), device=device, presharded=presharded)
+    # The first repetition's host-side init (numpy's legacy RNG, for identical streams) is drawn on a
+    # worker thread while the main thread uploads X and builds the device formats.
+    import torch.distributed as _dist
+    _rank = _dist.get_rank() if (_dist.is_available() and _dist.is_initialized()) else 0
+    _world = _dist.get_world_size() if (_dist.is_available() and _dist.is_initialized()) else 1
+    h_stream = _rank if (presharded and _world > 1) else None
+    first_init = {}
+
+    def _draw_first():
+        first_init["v"] = _als_init_host(ns, num_genes, k, rand_seed - 1, h_stream=h_stream)
+
+    worker = threading.Thread(target=_draw_first)
+    worker.start()
+    try:
+        engine = InmfEngine(X, k, value_lambda, dtype=resolve_dtype(dtype), device=device, presharded=presharded)
+    finally:
+        worker.join()
     best_obj = np.inf
     best = None
-    info = {"objectives": [], "bpp": None, "iters_run": []}
+    info = {"objectives": [], "bpp": None, "iters_run": [], "h2d_bytes": engine.X.h2d_bytes}
     for j in range(nrep):
-        W, V, H = _als_init_host(ns, num_genes, k, rand_seed + j - 1,
-                                 h_stream=engine.rank if (presharded and engine.world > 1) else None)
+        if j == 0:
+            W, V, H = first_init["v"]
+        else:
+            W, V, H = _als_init_host(ns, num_genes, k, rand_seed + j - 1, h_stream=h_stream)
         if W_init is not None:
             W = W_init
         if V_init is not None:

@@ -324,3 +324,67 @@ def test_online_vs_oracle_medium_fp32():
     online_iNMF(lig, k=20, value_lambda=5.0, max_epochs=2, miniBatch_size=500, verbose=False, dtype="float32")
     assert relerr(lig.W, want["W"]) < 2e-2
     assert relerr(lig.H[0], want["H"][0]) < 5e-2
+
+
+# ----------------------------------------------------------------------------------- edge cases
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_als_ragged_inputs_with_empty_rows_and_columns(dtype):
+    """Empty cells, genes that are all-zero in one dataset, very unequal dataset sizes, k = 1 and k = 33."""
+    from pyliger_b200 import optimize_ALS
+    rng = np.random.default_rng(9)
+    g = 70
+    mats = []
+    for n, dens in ((400, 0.2), (37, 0.3), (1500, 0.05)):
+        m = sps.random(n, g, density=dens, random_state=int(rng.integers(1 << 30)), format="lil",
+                       data_rvs=lambda s: rng.gamma(2.0, 1.0, s))
+        m[::7] = 0           # empty cells
+        m[:, 5] = 0          # a gene that is all zero in this dataset
+        m[:, g - 1] = 0
+        mats.append(sps.csr_matrix(m))
+    for k in (1, 33):
+        want = orc.als(mats, k, 2.0, 1e-6, 4, rand_seed=3)
+        lig = _liger(mats)
+        info = optimize_ALS(lig, k, 2.0, 1e-6, 4, rand_seed=3, dtype=dtype, return_info=True, progress=False)
+        rel = np.abs(np.array(info["objectives"][0]) - want["objectives"]) / np.array(want["objectives"])
+        assert rel.max() < OBJ_TOL[dtype]
+        for i in range(3):
+            assert lig.H[i].shape == (mats[i].shape[0], k)
+            assert relerr(lig.H[i], want["H"][i]) < (1e-6 if dtype == "float64" else 5e-2)
+            assert np.all(lig.H[i][::7] == 0)  # empty cells stay at zero loading
+
+
+def test_online_ragged_minibatches_wrap_many_epochs():
+    """Mini-batch sizes that do not divide the dataset sizes, several epochs (window wrap-around)."""
+    from pyliger_b200 import online_iNMF
+    from pyliger_b200.synth import make_datasets
+    mats = make_datasets([333, 211], 90, 6, density=0.15, seed0=3300)
+    want = orc.online(mats, 6, 4.0, 4, 1, 97, 50, 2)
+    lig = _liger(mats)
+    online_iNMF(lig, k=6, value_lambda=4.0, max_epochs=4, miniBatch_size=97, h5_chunk_size=50, rand_seed=2,
+                verbose=False)
+    assert relerr(lig.W, want["W"]) < 1e-7
+    for i in range(2):
+        assert relerr(lig.H[i], want["H"][i]) < 1e-6
+        assert relerr(lig.adata_list[i].uns["A"], want["A"][i]) < 1e-7
+        assert relerr(lig.adata_list[i].varm["B"], want["B"][i]) < 1e-7
+
+
+def test_bpp_large_batch_properties():
+    """Size-independent properties at a large column count (fp32): KKT conditions, idempotence of the warm
+    start, linearity of the right-hand side scaling (x(c r) = c x(r))."""
+    from pyliger_b200 import nnlsm_blockpivot
+    rng = np.random.default_rng(12)
+    k, cols = 40, 200000
+    A = rng.uniform(0, 1, (120, k))
+    G = A.T @ A
+    R = G @ np.maximum(rng.normal(0.2, 1.0, (k, cols)), 0) + rng.normal(0, 0.5, (k, cols))
+    X, info = nnlsm_blockpivot(G, R, is_input_prod=True, dtype="float32")
+    assert info[0] is True and (X >= 0).all()
+    Y = G @ X - R
+    scale = np.abs(R).max()
+    assert np.maximum(-Y, 0)[X == 0].max() / scale < 2e-4          # dual feasibility on the active set
+    assert np.abs(Y[X > 0]).max() / scale < 2e-4                    # stationarity on the passive set
+    X2, info2 = nnlsm_blockpivot(G, R, is_input_prod=True, dtype="float32", init=X)
+    assert relerr(X2, X) < 1e-5 and info2[2] <= cols * 1.01         # already optimal: one solve per column
+    X3, _ = nnlsm_blockpivot(G, 3.0 * R, is_input_prod=True, dtype="float32")
+    assert relerr(X3, 3.0 * X) < 1e-4
