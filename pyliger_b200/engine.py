@@ -309,6 +309,7 @@ class InmfEngine(object):
     def set_als_state(self, W, V, H=None):
         """W: k x g, V: list of k x g, H: list of n_i x k (GLOBAL rows; the local slice is taken)."""
         dev, dt = self.device, self.dtype
+        self.h2d_state_bytes = 8 * (np.size(W) + sum(np.size(v) for v in V))
         self.Wt.copy_(torch.from_numpy(np.ascontiguousarray(np.asarray(W, dtype=np.float64).T)).to(dev, dt))
         for i, Vi in enumerate(V):
             self.Vt[i].copy_(torch.from_numpy(np.ascontiguousarray(np.asarray(Vi, dtype=np.float64).T)).to(dev, dt))
@@ -317,6 +318,7 @@ class InmfEngine(object):
                 lo, hi = self.X.own[i]
                 b0, b1 = int(self.X.own_off[i]), int(self.X.own_off[i + 1])
                 if b1 > b0:
+                    self.h2d_state_bytes += 8 * (b1 - b0) * self.k
                     self.H[b0:b1, :self.k].copy_(torch.from_numpy(np.ascontiguousarray(
                         np.asarray(Hi, dtype=np.float64)[lo:hi])).to(dev, dt))
 

@@ -100,6 +100,7 @@ def optimize_ALS(
         if H_init is not None:
             H = H_init
         engine.set_als_state(W, V, H)
+        info["h2d_bytes"] += engine.h2d_state_bytes
         delta = 1
         obj0 = engine.initial_objective()
         objs = [obj0]
@@ -116,8 +117,10 @@ def optimize_ALS(
                 continue
         info["objectives"].append(objs)
         info["iters_run"].append(iters_run)
+        info["d2h_bytes"] = info.get("d2h_bytes", 0) + 8 * len(objs)
         if obj0 < best_obj:
             best = (engine.gather_H(), engine.host_W(), engine.host_V())
+            info["d2h_bytes"] += sum(h.nbytes for h in best[0]) + best[1].nbytes + sum(v.nbytes for v in best[2])
             best_obj = obj0
         if print_obj:
             print("Objective: {}".format(best_obj))
