@@ -171,6 +171,11 @@ int32_t inmf_normal_eq_f32(const float* A, const float* B, int64_t m, int32_t n,
 int32_t inmf_normal_eq_f64(const double* A, const double* B, int64_t m, int32_t n, int64_t cols, double* G,
                            double* Rt, void* stream);
 
+/* Diagnostic: C (128 x n, row-major) = A (128 x 64) * B (64 x n) through one tcgen05 (kind::tf32) tile with
+ * the accumulator in TMEM; three_pass != 0 uses the 3xTF32 split (fp32-grade accuracy).  Exercises the
+ * shared-memory descriptor / instruction descriptor / TMEM plumbing of the dense-tile passes. */
+int32_t inmf_tc_selftest(const float* A, const float* B, float* C, int32_t n, int32_t three_pass, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

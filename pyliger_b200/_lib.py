@@ -28,7 +28,7 @@ _TYPED = {
     "inmf_blocked_spmm": [_PTR, _I32, _PTR, _PTR, _PTR, _I32, _PTR, _I64, _I32, _I32, _PTR, _PTR],
 }
 
-EXPORTED_SYMBOLS = ["inmf_version", "inmf_last_error", "inmf_launch_count"] + [
+EXPORTED_SYMBOLS = ["inmf_version", "inmf_last_error", "inmf_launch_count", "inmf_tc_selftest"] + [
     "%s_%s" % (n, t) for n in _TYPED for t in ("f32", "f64")
 ]
 
@@ -55,6 +55,8 @@ def load():
     lib.inmf_last_error.argtypes = []
     lib.inmf_launch_count.restype = _I64
     lib.inmf_launch_count.argtypes = []
+    lib.inmf_tc_selftest.restype = _I32
+    lib.inmf_tc_selftest.argtypes = [_PTR, _PTR, _PTR, _I32, _I32, _PTR]
     for name, argtypes in _TYPED.items():
         for suffix in ("f32", "f64"):
             fn = getattr(lib, "%s_%s" % (name, suffix))

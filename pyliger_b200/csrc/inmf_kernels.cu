@@ -3,6 +3,7 @@
 #include "inmf_common.cuh"
 #include "bpp.cuh"
 #include "blocked.cuh"
+#include "tc_common.cuh"
 
 thread_local char g_inmf_err[512] = "";
 
@@ -959,4 +960,21 @@ extern "C" int32_t inmf_blocked_spmm_f64(const int64_t* work, int32_t nwork, con
                                          const double* dense, int32_t kp, double* out, int64_t ldo, int32_t k,
                                          int32_t max_tile_rows, double* gram_out, void* stream) {
     return blocked_launch<double>(work, nwork, ptr, pairs, dense, kp, out, ldo, k, max_tile_rows, gram_out, stream);
+}
+
+// =================================================================================================
+// tcgen05 diagnostics
+// =================================================================================================
+extern "C" int32_t inmf_tc_selftest(const float* A, const float* B, float* C, int32_t n, int32_t three_pass,
+                                    void* stream) {
+    INMF_REQUIRE(n >= 16 && n <= 64 && n % 16 == 0, "n must be 16, 32, 48 or 64");
+    const size_t smem = 2 * TC_A_BYTES + 2 * TC_KC * 64 * 4 + 64;
+    static bool attr_done = false;
+    if (!attr_done) {
+        INMF_CUDA_CHECK(cudaFuncSetAttribute(tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_done = true;
+    }
+    tc_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(A, B, C, n, three_pass);
+    INMF_LAUNCH_CHECK();
+    return 0;
 }
