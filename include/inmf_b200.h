@@ -116,6 +116,13 @@ int32_t inmf_stats_f64(const int64_t* rowptr, const int32_t* colidx, const doubl
                        int64_t ldh, double* St, double* HtH, int64_t g, const int64_t* seg_desc,
                        int32_t nseg, int64_t max_seg_rows, int32_t k, void* stream);
 
+/* out[s] (k x k double, accumulated) += sum over the rows [out_off[s], out_off[s+1]) of A of a'a  (H'H alone;
+ * seg_desc as above, only the out_off column is used). */
+int32_t inmf_gram_rows_f32(const float* A, int64_t lda, const int64_t* seg_desc, int32_t nseg, int64_t max_seg_rows,
+                           double* out, int32_t k, void* stream);
+int32_t inmf_gram_rows_f64(const double* A, int64_t lda, const int64_t* seg_desc, int32_t nseg, int64_t max_seg_rows,
+                           double* out, int32_t k, void* stream);
+
 /* ||X_s||_F^2 per segment (double[nseg], overwritten); constant term of the objective. */
 int32_t inmf_sqnorm_f32(const int64_t* rowptr, const float* vals, const int64_t* seg_desc, int32_t nseg,
                         double* out, void* stream);
@@ -170,6 +177,25 @@ int32_t inmf_normal_eq_f32(const float* A, const float* B, int64_t m, int32_t n,
                            float* Rt, void* stream);
 int32_t inmf_normal_eq_f64(const double* A, const double* B, int64_t m, int32_t n, int64_t cols, double* G,
                            double* Rt, void* stream);
+
+/* Dense-tile (tcgen05 / TMEM) form of the two X-streaming passes, fp32 with 3xTF32 (three_pass != 0,
+ * fp32-grade accuracy) or single TF32 arithmetic.  Same maths as inmf_blocked_spmm_f32:
+ *   out[out_row0 + r, 0..k) (+)= sum over the tile's chunks of X_tile(128 x 64) * D_chunk(64 x k)
+ * inmf_tc_relayout_f32 rewrites the dense operand D (rows x ldd; Mt for pass 1, H for pass 2) into per-chunk
+ * UMMA operand tiles (npad x 64, K-major, no swizzle) split into TF32 hi / lo parts;
+ * segd = device int64[nseg][3] {first row in D, rows, first chunk index}.
+ * inmf_tc_pass_f32: work = device int64[nwork][8] {ptr_index0, dense_chunk0, nchunks, out_row0, tile_rows,
+ * atomic, 0, 0}; ptr = int64, 8 entries per (tile, chunk) (16-row bands) + 1; pairs = {uint32 byte offset of
+ * (row, k) inside the 128 x 64 A tile, float value}.  Plain stores unless `atomic`. */
+int32_t inmf_tc_relayout_f32(const float* D, int64_t ldd, const int64_t* segd, int32_t nseg, int64_t max_seg_chunks,
+                             float* out_hi, float* out_lo, int32_t k, int32_t npad, void* stream);
+int32_t inmf_tc_pass_f32(const int64_t* work, int32_t nwork, const int64_t* ptr, const void* pairs,
+                         const float* dc_hi, const float* dc_lo, float* out, int64_t ldo, int32_t k, int32_t npad,
+                         int32_t three_pass, int32_t max_ctas, void* stream);
+
+/* Profiling hook: with a library built with -DTC_DEBUG_TIMERS, inmf_tc_pass_f32 dumps per-role cycle counters
+ * (64 int64 per CTA) into this device buffer; NULL (default) disables it.  No effect in normal builds. */
+void inmf_tc_debug_buffer(void* device_int64_buffer);
 
 /* Diagnostic: C (128 x n, row-major) = A (128 x 64) * B (64 x n) through one tcgen05 (kind::tf32) tile with
  * the accumulator in TMEM; three_pass != 0 uses the 3xTF32 split (fp32-grade accuracy).  Exercises the

@@ -25,10 +25,12 @@ _TYPED = {
     "inmf_update_ab": [_PTR, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR, _F64, _I32, _I32, _I64, _I32, _PTR],
     "inmf_hals": [_PTR, _PTR, _PTR, _PTR, _F64, _I32, _I32, _I64, _I32, _I32, _PTR],
     "inmf_normal_eq": [_PTR, _PTR, _I64, _I32, _I64, _PTR, _PTR, _PTR],
+    "inmf_gram_rows": [_PTR, _I64, _PTR, _I32, _I64, _PTR, _I32, _PTR],
     "inmf_blocked_spmm": [_PTR, _I32, _PTR, _PTR, _PTR, _I32, _PTR, _I64, _I32, _I32, _PTR, _PTR],
 }
 
-EXPORTED_SYMBOLS = ["inmf_version", "inmf_last_error", "inmf_launch_count", "inmf_tc_selftest"] + [
+EXPORTED_SYMBOLS = ["inmf_version", "inmf_last_error", "inmf_launch_count", "inmf_tc_selftest",
+                    "inmf_tc_relayout_f32", "inmf_tc_pass_f32", "inmf_tc_debug_buffer"] + [
     "%s_%s" % (n, t) for n in _TYPED for t in ("f32", "f64")
 ]
 
@@ -57,6 +59,10 @@ def load():
     lib.inmf_launch_count.argtypes = []
     lib.inmf_tc_selftest.restype = _I32
     lib.inmf_tc_selftest.argtypes = [_PTR, _PTR, _PTR, _I32, _I32, _PTR]
+    lib.inmf_tc_relayout_f32.restype = _I32
+    lib.inmf_tc_relayout_f32.argtypes = [_PTR, _I64, _PTR, _I32, _I64, _PTR, _PTR, _I32, _I32, _PTR]
+    lib.inmf_tc_pass_f32.restype = _I32
+    lib.inmf_tc_pass_f32.argtypes = [_PTR, _I32, _PTR, _PTR, _PTR, _PTR, _PTR, _I64, _I32, _I32, _I32, _I32, _PTR]
     for name, argtypes in _TYPED.items():
         for suffix in ("f32", "f64"):
             fn = getattr(lib, "%s_%s" % (name, suffix))
@@ -78,7 +84,7 @@ def _ptr(x):
 def call(name, suffix, *args):
     """Invoke ``<name>_<suffix>``; tensors are passed by data pointer. Raises InmfError on failure."""
     lib = load()
-    fn = getattr(lib, "%s_%s" % (name, suffix))
+    fn = getattr(lib, "%s_%s" % (name, suffix) if suffix else name)
     conv = [_ptr(a) if not isinstance(a, (float, bool)) else a for a in args]
     rc = fn(*conv)
     if rc != 0:

@@ -139,3 +139,96 @@ def build_pass2(X, kp, esize, n_sms):
     bp.work = torch.tensor(work if work else [[0] * WORK_FIELDS], dtype=torch.int64, device=dev)
     bp.max_tile_rows = max(cbs) if cbs else 1
     return bp
+
+
+# ------------------------------------------------------------------------------------------------------
+# Dense-tile (tcgen05) formats: pairs grouped by (128-row tile, 64-wide contraction chunk, 16-row band)
+# ------------------------------------------------------------------------------------------------------
+TC_M, TC_KC, TC_BANDS = 128, 64, 8
+
+
+def _tc_a_offset(m, kk):
+    """Byte offset of element (m, kk) in the 128 x 64 fp32 UMMA A tile (K-major, no swizzle)."""
+    return (m >> 3) * ((TC_KC // 4) * 128) + (m & 7) * 16 + (kk >> 2) * 128 + (kk & 3) * 4
+
+
+class TcPass(object):
+    __slots__ = ("work", "nwork", "ptr", "pairs", "segd", "nseg", "total_chunks", "max_seg_chunks", "npad")
+
+
+def _tc_finish(tp, key, n_keys, m, kk, val, work, segd, total_chunks, max_seg_chunks, npad, dev):
+    order = torch.sort(key, stable=True)[1]
+    ptr = torch.zeros(n_keys + 1, dtype=torch.int64, device=dev)
+    if key.numel():
+        ptr[1:] = torch.cumsum(torch.bincount(key, minlength=n_keys), 0)
+    tp.ptr = ptr
+    tp.pairs = _pack_pairs(_tc_a_offset(m, kk)[order], val[order])
+    tp.nwork = len(work)
+    tp.work = torch.tensor(work if work else [[0] * WORK_FIELDS], dtype=torch.int64, device=dev)
+    tp.segd = torch.tensor(segd, dtype=torch.int64, device=dev)
+    tp.nseg = len(segd)
+    tp.total_chunks = int(total_chunks)
+    tp.max_seg_chunks = int(max_seg_chunks)
+    tp.npad = npad
+    return tp
+
+
+def build_tc_pass1(X, k):
+    """rows = cells (tiles of 128 per dataset), contraction = genes (chunks of 64), dense operand = Mt."""
+    dev = X.rowptr.device
+    g, N = X.g, X.N
+    npad = max(16, -(-k // 16) * 16)
+    nch = -(-g // TC_KC)
+    nt = [-(-n // TC_M) for n in X.n_own]
+    tile_off = np.concatenate([[0], np.cumsum(nt)]).astype(np.int64)
+    own_row, col, val = _own_nnz(X)
+    own_off = torch.from_numpy(np.asarray(X.own_off, dtype=np.int64)).to(dev)
+    seg = torch.bucketize(own_row, own_off[1:], right=True)
+    local_row = own_row - own_off[seg]
+    col = col.to(torch.int64)
+    tile = torch.from_numpy(tile_off).to(dev)[seg] + local_row // TC_M
+    m, chunk, kk = local_row % TC_M, col // TC_KC, col % TC_KC
+    key = (tile * nch + chunk) * TC_BANDS + m // 16
+    work = []
+    for s in range(N):
+        for tl in range(nt[s]):
+            work.append([(int(tile_off[s]) + tl) * nch, s * nch, nch, int(X.own_off[s]) + tl * TC_M,
+                         min(TC_M, X.n_own[s] - tl * TC_M), 0, 0, 0])
+    segd = [[s * g, g, s * nch] for s in range(N)]
+    return _tc_finish(TcPass(), key, int(tile_off[-1]) * nch * TC_BANDS, m, kk, val, work, segd, N * nch, nch, npad, dev)
+
+
+def build_tc_pass2(X, k, n_sms):
+    """rows = genes (tiles of 128), contraction = the dataset's cells (chunks of 64), dense operand = H."""
+    dev = X.rowptr.device
+    g, N = X.g, X.N
+    npad = max(16, -(-k // 16) * 16)
+    ntg = -(-g // TC_M)
+    nch = [-(-n // TC_KC) for n in X.n_own]
+    chunk_off = np.concatenate([[0], np.cumsum(nch)]).astype(np.int64)
+    pbase = np.concatenate([[0], np.cumsum([ntg * c for c in nch])]).astype(np.int64)
+    own_row, col, val = _own_nnz(X)
+    own_off = torch.from_numpy(np.asarray(X.own_off, dtype=np.int64)).to(dev)
+    seg = torch.bucketize(own_row, own_off[1:], right=True)
+    local_row = own_row - own_off[seg]
+    col = col.to(torch.int64)
+    nch_t = torch.tensor(nch, dtype=torch.int64, device=dev)
+    pbase_t = torch.from_numpy(pbase).to(dev)
+    m, kk = col % TC_M, local_row % TC_KC
+    pidx = pbase_t[seg] + (col // TC_M) * nch_t[seg] + local_row // TC_KC
+    key = pidx * TC_BANDS + m // 16
+    n_items = max(1, N * ntg)
+    split = max(1, -(-3 * n_sms // n_items))
+    work = []
+    for s in range(N):
+        if nch[s] == 0:
+            continue
+        parts = min(split, nch[s])
+        per = -(-nch[s] // parts)
+        for tl in range(ntg):
+            for c0 in range(0, nch[s], per):
+                work.append([int(pbase[s]) + tl * nch[s] + c0, int(chunk_off[s]) + c0, min(per, nch[s] - c0),
+                             s * g + tl * TC_M, min(TC_M, g - tl * TC_M), 1 if parts > 1 else 0, 0, 0])
+    segd = [[int(X.own_off[s]), X.n_own[s], int(chunk_off[s])] for s in range(N)]
+    return _tc_finish(TcPass(), key, int(pbase[-1]) * TC_BANDS, m, kk, val, work, segd, int(chunk_off[-1]),
+                      max(nch) if nch else 0, npad, dev)

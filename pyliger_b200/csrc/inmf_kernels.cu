@@ -4,6 +4,7 @@
 #include "bpp.cuh"
 #include "blocked.cuh"
 #include "tc_common.cuh"
+#include "tc_pass.cuh"
 
 thread_local char g_inmf_err[512] = "";
 
@@ -414,6 +415,30 @@ static int32_t stats_launch(const int64_t* rowptr, const int32_t* colidx, const 
     INMF_LAUNCH_CHECK();
     return 0;
 }
+template <typename T>
+static int32_t gram_rows_launch(const T* A, int64_t lda, const int64_t* seg_desc, int32_t nseg, int64_t max_seg_rows,
+                                double* out, int32_t k, void* stream) {
+    INMF_REQUIRE(k >= 1 && k <= INMF_MAX_K && lda >= k, "bad k / lda");
+    INMF_REQUIRE(nseg >= 1 && nseg <= 65535, "nseg out of range");
+    if (max_seg_rows <= 0) return 0;
+    int64_t tiles = (max_seg_rows + GRAM_TILE_ROWS - 1) / GRAM_TILE_ROWS;
+    const int64_t tcap = (int64_t)inmf_num_sms() * 8;
+    if (tiles > tcap) tiles = tcap;
+    const int ldt = ((k + 3) & ~3) + 4;
+    gram_rows_kernel<T><<<dim3((unsigned)tiles, (unsigned)nseg), 256, (size_t)GRAM_TILE_ROWS * ldt * sizeof(T),
+                          (cudaStream_t)stream>>>(A, lda, seg_desc, out, k);
+    INMF_LAUNCH_CHECK();
+    return 0;
+}
+extern "C" int32_t inmf_gram_rows_f32(const float* A, int64_t lda, const int64_t* seg_desc, int32_t nseg,
+                                      int64_t max_seg_rows, double* out, int32_t k, void* stream) {
+    return gram_rows_launch<float>(A, lda, seg_desc, nseg, max_seg_rows, out, k, stream);
+}
+extern "C" int32_t inmf_gram_rows_f64(const double* A, int64_t lda, const int64_t* seg_desc, int32_t nseg,
+                                      int64_t max_seg_rows, double* out, int32_t k, void* stream) {
+    return gram_rows_launch<double>(A, lda, seg_desc, nseg, max_seg_rows, out, k, stream);
+}
+
 extern "C" int32_t inmf_stats_f32(const int64_t* rowptr, const int32_t* colidx, const float* vals, const float* H,
                                   int64_t ldh, float* St, double* HtH, int64_t g, const int64_t* seg_desc,
                                   int32_t nseg, int64_t max_seg_rows, int32_t k, void* stream) {
@@ -975,6 +1000,49 @@ extern "C" int32_t inmf_tc_selftest(const float* A, const float* B, float* C, in
         attr_done = true;
     }
     tc_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(A, B, C, n, three_pass);
+    INMF_LAUNCH_CHECK();
+    return 0;
+}
+
+// =================================================================================================
+// Dense-tile (tcgen05) passes, fp32 only
+// =================================================================================================
+static long long* g_tc_dbg = nullptr;  // optional cycle-counter dump (set through inmf_tc_debug_buffer)
+extern "C" void inmf_tc_debug_buffer(void* p) { g_tc_dbg = (long long*)p; }
+
+extern "C" int32_t inmf_tc_relayout_f32(const float* D, int64_t ldd, const int64_t* segd, int32_t nseg,
+                                        int64_t max_seg_chunks, float* out_hi, float* out_lo, int32_t k, int32_t npad,
+                                        void* stream) {
+    INMF_REQUIRE(k >= 1 && k <= INMF_MAX_K && npad >= k && npad % 16 == 0 && npad <= 64, "bad k / npad");
+    INMF_REQUIRE(nseg >= 1 && nseg <= 65535, "nseg out of range");
+    if (max_seg_chunks <= 0) return 0;
+    int64_t blocks = max_seg_chunks;
+    if (blocks > inmf_num_sms() * 16) blocks = inmf_num_sms() * 16;
+    tc_relayout_kernel<<<dim3((unsigned)blocks, (unsigned)nseg), 256, 0, (cudaStream_t)stream>>>(D, ldd, segd, out_hi,
+                                                                                               out_lo, k, npad);
+    INMF_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int32_t inmf_tc_pass_f32(const int64_t* work, int32_t nwork, const int64_t* ptr, const void* pairs,
+                                    const float* dc_hi, const float* dc_lo, float* out, int64_t ldo, int32_t k,
+                                    int32_t npad, int32_t three_pass, int32_t max_ctas, void* stream) {
+    INMF_REQUIRE(k >= 1 && k <= INMF_MAX_K && npad >= k && npad % 16 == 0 && npad <= 64, "bad k / npad");
+    INMF_REQUIRE(ldo >= k, "ldo must be >= k");
+    if (nwork <= 0) return 0;
+    const TcSmemLayout L = tc_smem_layout(npad);
+    INMF_REQUIRE(L.total + 1024 <= 227 * 1024, "shared memory budget exceeded");
+    static bool attr_done = false;
+    if (!attr_done) {
+        INMF_CUDA_CHECK(cudaFuncSetAttribute(tc_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_done = true;
+    }
+    int grid = inmf_num_sms();
+    if (max_ctas > 0 && max_ctas < grid) grid = max_ctas;
+    if (grid > nwork) grid = nwork;
+    tc_pass_kernel<<<grid, TC_THREADS, L.total + 1024, (cudaStream_t)stream>>>(
+        work, nwork, ptr, reinterpret_cast<const int2*>(pairs), dc_hi, dc_lo, out, ldo, k, npad, three_pass,
+        g_tc_dbg);
     INMF_LAUNCH_CHECK();
     return 0;
 }

@@ -136,7 +136,11 @@ class InmfEngine(object):
     """Buffers + step functions shared by optimize_ALS and online_iNMF."""
 
     def __init__(self, mats, k, value_lambda, dtype=torch.float64, device=None, group=None, pin=False,
-                 replicate=False, n_prev=0, presharded=False, use_blocked=True, need_stats=True):
+                 replicate=False, n_prev=0, presharded=False, use_blocked=True, need_stats=True, use_tc=False,
+                 tc_three_pass=True):
+        # use_tc: dense-tile tcgen05 form of the two passes (fp32 only): 3xTF32 (fp32-grade) by default
+        self.use_tc = bool(use_tc) and resolve_dtype(dtype) == torch.float32
+        self.tc_three_pass = bool(tc_three_pass)
         self.use_blocked = bool(use_blocked)
         self.need_stats = bool(need_stats)
         self.device = require_cuda(device)
@@ -210,9 +214,21 @@ class InmfEngine(object):
         if self.use_blocked and X.n_own_total > 0:
             esize = 4 if dt == torch.float32 else 8
             sms = torch.cuda.get_device_properties(dev).multi_processor_count
-            self.pass1 = blocked.build_pass1(X, self.ldm, esize, sms)
+            if not self.use_tc:
+                self.pass1 = blocked.build_pass1(X, self.ldm, esize, sms)
+                if self.need_stats:
+                    self.pass2 = blocked.build_pass2(X, self.ldm, esize, sms)
+        self.tc1 = self.tc2 = None
+        if self.use_tc and X.n_own_total > 0:
+            sms = torch.cuda.get_device_properties(dev).multi_processor_count
+            self.tc1 = blocked.build_tc_pass1(X, k)
+            per = self.tc1.npad * blocked.TC_KC
+            self.dc1_hi = torch.empty(self.tc1.total_chunks * per, dtype=dt, device=dev)
+            self.dc1_lo = torch.empty_like(self.dc1_hi)
             if self.need_stats:
-                self.pass2 = blocked.build_pass2(X, self.ldm, esize, sms)
+                self.tc2 = blocked.build_tc_pass2(X, k, sms)
+                self.dc2_hi = torch.empty(self.tc2.total_chunks * per, dtype=dt, device=dev)
+                self.dc2_lo = torch.empty_like(self.dc2_hi)
 
     def _allreduce(self, *tensors):
         if self.world > 1:
@@ -234,7 +250,13 @@ class InmfEngine(object):
         if max_rows <= 0:
             return
         X, k = self.X, self.k
-        if full and out is self.H and self.pass1 is not None:
+        if full and out is self.H and self.tc1 is not None:
+            t = self.tc1
+            _lib.call("inmf_tc_relayout_f32", "", self.Mt, self.ldm, t.segd, t.nseg, t.max_seg_chunks, self.dc1_hi,
+                      self.dc1_lo, k, t.npad, _stream())
+            _lib.call("inmf_tc_pass_f32", "", t.work, t.nwork, t.ptr, t.pairs, self.dc1_hi, self.dc1_lo, out, self.ldm,
+                      k, t.npad, 1 if self.tc_three_pass else 0, 0, _stream())
+        elif full and out is self.H and self.pass1 is not None:
             out.zero_()
             p = self.pass1
             _lib.call("inmf_blocked_spmm", self.sfx, p.work, p.nwork, p.ptr, p.pairs, self.Mt, self.ldm, out,
@@ -275,7 +297,14 @@ class InmfEngine(object):
         HtH.zero_()
         X, k = self.X, self.k
         if max_rows > 0:
-            if full and self.pass2 is not None:
+            if full and self.tc2 is not None:
+                t = self.tc2
+                _lib.call("inmf_tc_relayout_f32", "", H, self.ldm, t.segd, t.nseg, t.max_seg_chunks, self.dc2_hi,
+                          self.dc2_lo, k, t.npad, _stream())
+                _lib.call("inmf_tc_pass_f32", "", t.work, t.nwork, t.ptr, t.pairs, self.dc2_hi, self.dc2_lo, St, k, k,
+                          t.npad, 1 if self.tc_three_pass else 0, 0, _stream())
+                _lib.call("inmf_gram_rows", self.sfx, H, self.ldm, self.seg_full, nseg, max_rows, HtH, k, _stream())
+            elif full and self.pass2 is not None:
                 p = self.pass2
                 _lib.call("inmf_blocked_spmm", self.sfx, p.work, p.nwork, p.ptr, p.pairs, H, self.ldm, St, k, k,
                           p.max_tile_rows, HtH, _stream())

@@ -8,6 +8,8 @@ Keyword-only extensions (defaults preserve reference behaviour):
               solution, fewer pivoting rounds); default False = the reference's cold start
   return_info if True, return a dict with the per-iteration objectives and solver counters
               (the reference returns None; the default stays None)
+  tensor_core None (default) = CUDA-core passes; "tf32x3" / "tf32" = experimental dense-tile tcgen05 form
+              of the two X-streaming passes (float32 only; "tf32" is reduced precision, ~1e-3 per product)
   presharded  multi-GPU only (one process per GPU under torchrun): if True every process passes ONLY
               its own cells of each dataset (H is written back for those cells); if False every process
               passes the full datasets and works on its 1/world row slice, and the full H is gathered.
@@ -55,6 +57,7 @@ def optimize_ALS(
     return_info=False,
     progress=True,
     presharded=False,
+    tensor_core=None,
 ):
     N = liger_object.num_samples
     ns = [adata.shape[0] for adata in liger_object.adata_list]
@@ -82,7 +85,10 @@ def optimize_ALS(
     worker = threading.Thread(target=_draw_first)
     worker.start()
     try:
-        engine = InmfEngine(X, k, value_lambda, dtype=resolve_dtype(dtype), device=device, presharded=presharded)
+        if tensor_core not in (None, "tf32x3", "tf32"):
+            raise ValueError("tensor_core must be None, 'tf32x3' or 'tf32'")
+        engine = InmfEngine(X, k, value_lambda, dtype=resolve_dtype(dtype), device=device, presharded=presharded,
+                            use_tc=tensor_core is not None, tc_three_pass=tensor_core != "tf32")
     finally:
         worker.join()
     best_obj = np.inf

@@ -188,3 +188,55 @@ def test_error_reporting(dev):
     from pyliger_b200 import _lib
     with pytest.raises(_lib.InmfError, match="k must be"):
         _lib.call("inmf_bpp", "f32", 0, 0, 1, 0, 1, 0, 1, 0, 0, 0, 1, 1, 65, 0, 0, 0)
+
+
+def test_tcgen05_selftest_tile(dev):
+    """One 128 x 64 x n tcgen05 (kind::tf32) tile with the accumulator in TMEM: TF32 and 3xTF32 accuracy."""
+    from pyliger_b200 import _lib
+    from pyliger_b200.engine import _stream
+    lib = _lib.load()
+    rng = np.random.default_rng(0)
+    for n in (16, 32, 48, 64):
+        A = rng.uniform(-1, 1, (128, 64)).astype(np.float32)
+        B = rng.uniform(-1, 1, (64, n)).astype(np.float32)
+        want = A.astype(np.float64) @ B.astype(np.float64)
+        for three, tol in ((0, 3e-3), (1, 1e-5)):
+            C = torch.full((128, n), float("nan"), device=dev)
+            Ad, Bd = torch.from_numpy(A).to(dev), torch.from_numpy(B).to(dev)
+            rc = lib.inmf_tc_selftest(Ad.data_ptr(), Bd.data_ptr(), C.data_ptr(), n, three, _stream())
+            torch.cuda.synchronize()
+            assert rc == 0
+            assert np.abs(C.cpu().numpy() - want).max() / np.abs(want).max() < tol
+
+
+@pytest.mark.parametrize("mode,tol", [("tf32x3", 5e-5), ("tf32", 5e-3)])
+def test_tcgen05_passes_match_cuda_core_passes(dev, mode, tol):
+    """Dense-tile tcgen05 form of both passes against the CUDA-core blocked form (ragged sizes, k = 9, 33)."""
+    from pyliger_b200.engine import InmfEngine
+    for k in (9, 33):
+        mats, W, V, H = _rand_problem(11 + k, ns=(700, 333, 130), g=210, k=k, density=0.12)
+        ref = InmfEngine(mats, k, 5.0, dtype=torch.float32)
+        tc = InmfEngine(mats, k, 5.0, dtype=torch.float32, use_tc=True, tc_three_pass=(mode == "tf32x3"))
+        assert tc.tc1 is not None and tc.tc2 is not None
+        for e in (ref, tc):
+            e.set_als_state(W, V, H)
+            e.prep()
+            e.stats()
+        assert relerr(tc.St.cpu().numpy(), ref.St.cpu().numpy()) < tol
+        assert relerr(tc.HtH.cpu().numpy(), ref.HtH.cpu().numpy()) < 1e-6
+        ref.rhs_H()
+        tc.rhs_H()
+        assert relerr(tc.H.cpu().numpy(), ref.H.cpu().numpy()) < tol
+
+
+def test_als_with_tensor_core_passes(dev):
+    from pyliger_b200 import liger_from_matrices, optimize_ALS
+    from pyliger_b200.synth import make_datasets
+    mats = make_datasets([900, 700], 400, 20, density=0.10, seed0=3000)
+    want = orc.als(mats, 20, 5.0, 1e-6, 5, rand_seed=1)
+    lig = liger_from_matrices(mats)
+    info = optimize_ALS(lig, 20, 5.0, 1e-6, 5, rand_seed=1, dtype="float32", tensor_core="tf32x3", return_info=True,
+                        progress=False)
+    rel = np.abs(np.array(info["objectives"][0]) - want["objectives"]) / np.array(want["objectives"])
+    assert rel.max() < 1e-3
+    assert relerr(lig.H[0], want["H"][0]) < 1e-2

@@ -246,3 +246,57 @@ def test_blocked_formats_reproduce_products(world, rank, dtype):
     # every owned non-zero appears exactly once in each pass
     own_nnz = sum(m[lo:hi].nnz for m, (lo, hi) in zip(mats, X.own))
     assert p1.pairs.shape[0] == own_nnz == p2.pairs.shape[0]
+
+
+def _emulate_tc(tp, dense, k, out):
+    """numpy statement of inmf_tc_relayout + inmf_tc_pass from (work, ptr, pairs, segd)."""
+    from pyliger_b200 import blocked
+    work = tp.work.numpy()[:tp.nwork]
+    ptr = tp.ptr.numpy()
+    pairs = tp.pairs.numpy()
+    off = pairs[:, 0].astype(np.int64)
+    vals = pairs[:, 1].copy().view(np.float32).astype(np.float64)
+    # invert the A-tile offset: (m, kk)
+    m = (off // 2048) * 8 + (off % 128) // 16
+    kk = ((off % 2048) // 128) * 4 + (off % 16) // 4
+    assert np.all(blocked._tc_a_offset(m, kk) == off)
+    segd = tp.segd.numpy()
+    chunk_rows = {}
+    for row0, rows, chunk0 in segd:
+        for c in range(-(-rows // 64)):
+            chunk_rows[chunk0 + c] = (row0 + c * 64, min(64, rows - c * 64))
+    for pidx0, dchunk0, nch, out_row0, tile_rows, atomic, _, _ in work:
+        for c in range(nch):
+            b, e = ptr[(pidx0 + c) * 8], ptr[(pidx0 + c) * 8 + 8]
+            r0, nr = chunk_rows[dchunk0 + c]
+            if e > b:
+                assert m[b:e].max() < tile_rows and kk[b:e].max() < nr
+                bands = np.repeat(np.arange(8), np.diff(ptr[(pidx0 + c) * 8:(pidx0 + c) * 8 + 9]))
+                assert np.all(m[b:e] // 16 == bands)
+                np.add.at(out, out_row0 + m[b:e], vals[b:e, None] * dense[r0 + kk[b:e], :k])
+
+
+@pytest.mark.parametrize("world,rank", [(1, 0), (2, 1)])
+def test_tc_formats_reproduce_products(world, rank):
+    from pyliger_b200 import blocked
+    from pyliger_b200.engine import DeviceCSR
+    rng = np.random.default_rng(6)
+    g, k = 300, 6
+    mats = [sps.random(n, g, density=0.1, random_state=13 + i, format="csr") for i, n in enumerate((401, 130, 64))]
+    X = DeviceCSR(mats, torch.float32, torch.device("cpu"), rank, world)
+    p1 = blocked.build_tc_pass1(X, k)
+    p2 = blocked.build_tc_pass2(X, k, n_sms=4)
+    assert p1.npad == 16 and p2.npad == 16
+    N = len(mats)
+    Mt = rng.uniform(0, 1, (N * g, 8))
+    H = rng.uniform(0, 1, (X.n_own_total, 8))
+    R = np.zeros((X.n_own_total, k))
+    _emulate_tc(p1, Mt, k, R)
+    St = np.zeros((N * g, k))
+    _emulate_tc(p2, H, k, St)
+    for s, mm in enumerate(mats):
+        lo, hi = X.own[s]
+        o0, o1 = X.own_off[s], X.own_off[s + 1]
+        sub = mm[lo:hi]
+        np.testing.assert_allclose(R[o0:o1], sub @ Mt[s * g:(s + 1) * g, :k], rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(St[s * g:(s + 1) * g], sub.T @ H[o0:o1, :k], rtol=1e-5, atol=1e-5)
