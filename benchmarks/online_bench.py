@@ -65,7 +65,7 @@ def main():
         epoch = ((it + 1) * mbs[0]) // ns[0]
         epoch_state[0] = epoch
         scales = [0.0] * len(mats) if it == 0 else ([1.0 / m for m in mbs] if it == 1 else [(it - 1) / it] * len(mats))
-        eng.online_step(plan[it], scales, bool(epoch > 0 and epoch - epoch_prev == 1), 1)
+        eng.online_step(plan[it], scales, bool(epoch > 0 and epoch - epoch_prev == 1), 1, step=it)
 
     st = [0]
     for it in range(min(3, total_iters)):  # warm-up (then restart from the same state)

@@ -232,3 +232,76 @@ def build_tc_pass2(X, k, n_sms):
     segd = [[int(X.own_off[s]), X.n_own[s], int(chunk_off[s])] for s in range(N)]
     return _tc_finish(TcPass(), key, int(pbase[-1]) * TC_BANDS, m, kk, val, work, segd, int(chunk_off[-1]),
                       max(nch) if nch else 0, npad, dev)
+
+
+# ------------------------------------------------------------------------------------------------------
+# Pass-1 format over ALL resident cells + per-step work lists for mini-batch row windows (online iNMF)
+# ------------------------------------------------------------------------------------------------------
+def build_pass1_resident(X, kp, esize):
+    """Gene-blocked CSR over every resident cell (replicated datasets of online_iNMF).  Row windows of a
+    mini-batch are then just row ranges of the (dataset, gene block) sub-matrices: see window_work."""
+    dev = X.rowptr.device
+    g, N = X.g, X.N
+    cap = tile_cap_rows(kp, esize)
+    NB = max(1, -(-g // cap))
+    gbs = -(-g // NB)
+    rows, cols, vals = [], [], []
+    for s in range(N):
+        r0, n = int(X.row_base[s]), X.n_local[s]
+        if n == 0:
+            continue
+        rp = X.rowptr[r0:r0 + n + 1]
+        p0, p1 = int(rp[0].item()), int(rp[-1].item())
+        rows.append(torch.repeat_interleave(torch.arange(n, device=dev, dtype=torch.int64) + r0, rp[1:] - rp[:-1]))
+        cols.append(X.colidx[p0:p1])
+        vals.append(X.vals[p0:p1])
+    row = torch.cat(rows) if rows else torch.zeros(0, dtype=torch.int64, device=dev)
+    col = (torch.cat(cols) if cols else torch.zeros(0, dtype=torch.int32, device=dev)).to(torch.int64)
+    val = torch.cat(vals) if vals else X.vals[:0]
+    base = torch.from_numpy(np.asarray(X.row_base, dtype=np.int64)).to(dev)
+    nloc = torch.from_numpy(np.asarray(X.n_local, dtype=np.int64)).to(dev)
+    seg = torch.bucketize(row, base[1:], right=True)
+    gb = col // gbs
+    cidx = NB * base[seg] + gb * nloc[seg] + (row - base[seg])
+    order = torch.sort(cidx, stable=True)[1]
+    ptr = torch.zeros(NB * X.n_total + 1, dtype=torch.int64, device=dev)
+    if cidx.numel():
+        ptr[1:] = torch.cumsum(torch.bincount(cidx, minlength=NB * X.n_total), 0)
+    bp = BlockedPass()
+    bp.pairs = _pack_pairs((col - gb * gbs)[order] * (kp * esize), val[order])
+    bp.ptr = ptr
+    bp.work, bp.nwork = None, 0
+    bp.max_tile_rows = min(gbs, g)
+    return bp, NB, gbs
+
+
+def window_work(X, NB, gbs, plan, pieces):
+    """Work lists [steps][items][8] for the row windows of ``plan`` (the seg_desc array of online_windows):
+    window q -> row (win_start + q) % n of dataset s lands in output row out_off + q."""
+    g, N = X.g, X.N
+    steps = plan.shape[0]
+    items = N * NB * pieces * 2  # every window piece may wrap once
+    work = np.zeros((steps, items, WORK_FIELDS), dtype=np.int64)
+    work[:, :, 6] = -1
+    counts = np.zeros(steps, dtype=np.int64)
+    for t in range(steps):
+        it = 0
+        for s in range(N):
+            out_off, win_start, n = int(plan[t, s, 0]), int(plan[t, s, 2]), int(plan[t, s, 3])
+            count = int(plan[t, s + 1, 0]) - out_off
+            per = -(-count // pieces) if count else 0
+            for b in range(NB):
+                rows_b = min(gbs, g - b * gbs)
+                pbase = NB * int(X.row_base[s]) + b * X.n_local[s]
+                for q0 in range(0, count, max(per, 1)):
+                    q1 = min(count, q0 + per)
+                    lo = (win_start + q0) % n
+                    hi = lo + (q1 - q0)
+                    # piece [lo, hi) possibly wrapping at n
+                    for a, e, obase in ((lo, min(hi, n), out_off + q0 - lo),
+                                        (0, max(hi - n, 0), out_off + q0 + (n - lo))):
+                        if e > a:
+                            work[t, it] = [pbase, s * g + b * gbs, rows_b, a, e, obase, -1, 0]
+                            it += 1
+        counts[t] = it
+    return work, counts

@@ -829,12 +829,180 @@ __global__ void hals_kernel(const double* __restrict__ A, const T* __restrict__ 
         __syncwarp();
     }
 }
+// Incremental form of the same Gauss-Seidel sweeps (used when the statistics fit in shared memory and
+// there are at most HALS_MAX_SETS current datasets).  Per gene the warp keeps, distributed over lanes
+// (lane owns factors lane and lane+32),
+//   D[j']   = sum_i ( B_i[j'] - sum_a (W_a + V_ia) A_i[a][j'] )        (all datasets; drives the W sweep)
+//   Q_i[j'] = sum_a ( W_a + (1+lambda) V_ia ) A_i[a][j']               (current datasets; drives the V sweep)
+// and applies rank-1 corrections with row j of A_i whenever W_j or V_ij changes, instead of recomputing a
+// k-term dot product per (factor, dataset).  Same update order as _update_W_HALS / _update_V_HALS.
+template <typename T>
+__global__ void hals_inc_kernel(const double* __restrict__ A, const T* __restrict__ B, T* __restrict__ Wt,
+                                T* __restrict__ Vt, double lambda, int n_prev, int nall, int64_t g, int k,
+                                int n_inner) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kk = k * k;
+    T* As = reinterpret_cast<T*>(smem_raw);              // [nall][k][k]   A_i (row-major, as given)
+    T* SAs = As + (size_t)nall * kk;                     // [k][k]         sum_i A_i
+    for (int e = threadIdx.x; e < nall * kk; e += blockDim.x) As[e] = (T)A[e];
+    for (int e = threadIdx.x; e < kk; e += blockDim.x) {
+        double acc = 0.0;
+        for (int i = 0; i < nall; ++i) acc += A[(size_t)i * kk + e];
+        SAs[e] = (T)acc;
+    }
+    __syncthreads();
+    const size_t shared_elems = (((size_t)(nall + 1) * kk) + 3) & ~(size_t)3;
+    const int per_warp = (1 + 2 * nall) * k;
+    T* ws = reinterpret_cast<T*>(smem_raw) + shared_elems + (size_t)warp * per_warp;
+    T* vs = ws + k;                 // [nall][k]
+    T* bs = vs + (size_t)nall * k;  // [nall][k]
+    const T eps = T(1e-16);
+    const T one_lam = (T)(1.0 + lambda), lam = (T)lambda;
+    const int ncur = nall - n_prev;
+    const int j0 = lane, j1 = lane + 32;
+    const bool has0 = j0 < k, has1 = j1 < k;
+    const int c0 = has0 ? j0 : 0, c1 = has1 ? j1 : 0;  // clamped column indices for loads
+    for (int64_t w = (int64_t)blockIdx.x * nwarps + warp; w < g; w += (int64_t)gridDim.x * nwarps) {
+        for (int j = lane; j < k; j += 32) ws[j] = Wt[w * k + j];
+        for (int i = 0; i < nall; ++i)
+            for (int j = lane; j < k; j += 32) {
+                vs[i * k + j] = Vt[((size_t)i * g + w) * k + j];
+                bs[i * k + j] = B[((size_t)i * g + w) * k + j];
+            }
+        __syncwarp();
+        for (int it = 0; it < n_inner; ++it) {
+            // ---- phase 0: D, and for the current datasets P_i = (W+V_i) A_i and VA_i = V_i A_i ----
+            T D0 = T(0), D1 = T(0);
+            T P0[HALS_MAX_SETS], P1[HALS_MAX_SETS], VA0[HALS_MAX_SETS], VA1[HALS_MAX_SETS];
+#pragma unroll
+            for (int u = 0; u < HALS_MAX_SETS; ++u) P0[u] = P1[u] = VA0[u] = VA1[u] = T(0);
+            for (int i = 0; i < n_prev; ++i) {  // previous datasets only enter D
+                T p0 = T(0), p1 = T(0);
+                const T* Ai = As + (size_t)i * kk;
+                for (int a = 0; a < k; ++a) {
+                    const T u = ws[a] + vs[i * k + a];
+                    p0 = fma(u, Ai[a * k + c0], p0);
+                    p1 = fma(u, Ai[a * k + c1], p1);
+                }
+                D0 += bs[i * k + c0] - p0;
+                D1 += bs[i * k + c1] - p1;
+            }
+            for (int a = 0; a < k; ++a) {
+                const T wa = ws[a];
+#pragma unroll
+                for (int u = 0; u < HALS_MAX_SETS; ++u) {
+                    if (u >= ncur) break;
+                    const int i = n_prev + u;
+                    const T va = vs[i * k + a];
+                    const T a0 = As[(size_t)i * kk + a * k + c0], a1 = As[(size_t)i * kk + a * k + c1];
+                    P0[u] = fma(wa + va, a0, P0[u]);
+                    P1[u] = fma(wa + va, a1, P1[u]);
+                    VA0[u] = fma(va, a0, VA0[u]);
+                    VA1[u] = fma(va, a1, VA1[u]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < HALS_MAX_SETS; ++u) {
+                if (u >= ncur) break;
+                const int i = n_prev + u;
+                D0 += bs[i * k + c0] - P0[u];
+                D1 += bs[i * k + c1] - P1[u];
+            }
+            // ---- W sweep ----
+            for (int j = 0; j < k; ++j) {
+                const T d = __shfl_sync(INMF_FULL_MASK, (j < 32) ? D0 : D1, j & 31);
+                const T wj = ws[j];
+                T nw = wj + d / SAs[j * k + j];
+                nw = nw < eps ? eps : nw;
+                const T delta = nw - wj;
+                D0 = fma(-delta, SAs[j * k + c0], D0);
+                D1 = fma(-delta, SAs[j * k + c1], D1);
+#pragma unroll
+                for (int u = 0; u < HALS_MAX_SETS; ++u) {
+                    if (u >= ncur) break;
+                    const T* Ar = As + (size_t)(n_prev + u) * kk + j * k;
+                    P0[u] = fma(delta, Ar[c0], P0[u]);
+                    P1[u] = fma(delta, Ar[c1], P1[u]);
+                }
+                __syncwarp();
+                if (lane == 0) ws[j] = nw;
+                __syncwarp();
+            }
+            // Q_i = P_i (with the new W) + lambda * VA_i
+#pragma unroll
+            for (int u = 0; u < HALS_MAX_SETS; ++u) {
+                P0[u] = fma(lam, VA0[u], P0[u]);
+                P1[u] = fma(lam, VA1[u], P1[u]);
+            }
+            // ---- V sweep: lane u finishes dataset u, all lanes apply the rank-1 corrections ----
+            for (int j = 0; j < k; ++j) {
+                T q = T(0);
+#pragma unroll
+                for (int u = 0; u < HALS_MAX_SETS; ++u) {
+                    if (u >= ncur) break;
+                    const T t = __shfl_sync(INMF_FULL_MASK, (j < 32) ? P0[u] : P1[u], j & 31);
+                    q = (lane == u) ? t : q;
+                }
+                T delta = T(0);
+                if (lane < ncur) {
+                    const int i = n_prev + lane;
+                    const T vij = vs[i * k + j];
+                    T nv = vij + (bs[i * k + j] - q) / (one_lam * As[(size_t)i * kk + j * k + j]);
+                    nv = nv < eps ? eps : nv;
+                    delta = one_lam * (nv - vij);
+                    vs[i * k + j] = nv;
+                }
+#pragma unroll
+                for (int u = 0; u < HALS_MAX_SETS; ++u) {
+                    if (u >= ncur) break;
+                    const T du = __shfl_sync(INMF_FULL_MASK, delta, u);
+                    const T* Ar = As + (size_t)(n_prev + u) * kk + j * k;
+                    P0[u] = fma(du, Ar[c0], P0[u]);
+                    P1[u] = fma(du, Ar[c1], P1[u]);
+                }
+            }
+            __syncwarp();
+        }
+        for (int j = lane; j < k; j += 32) Wt[w * k + j] = ws[j];
+        for (int i = n_prev; i < nall; ++i)
+            for (int j = lane; j < k; j += 32) Vt[((size_t)i * g + w) * k + j] = vs[i * k + j];
+        __syncwarp();
+    }
+}
+
 template <typename T>
 static int32_t hals_launch(const double* A, const T* B, T* Wt, T* Vt, double lambda, int32_t n_prev, int32_t nall,
                            int64_t g, int32_t k, int32_t n_inner, void* stream) {
     INMF_REQUIRE(k >= 1 && k <= INMF_MAX_K && nall >= 1 && g >= 1, "bad shape");
     INMF_REQUIRE(n_prev >= 0 && n_prev <= nall && n_inner >= 0, "bad n_prev / n_inner");
     const size_t per_warp = (size_t)(1 + 2 * nall) * k * sizeof(T);
+    {   // incremental kernel: A_i and their sum resident in shared memory
+        const size_t shared_bytes = ((((size_t)(nall + 1) * k * k) + 3) & ~(size_t)3) * sizeof(T);
+        if (nall - n_prev <= HALS_MAX_SETS && shared_bytes <= 120 * 1024) {
+            int nw = 8;
+            while (nw > 1 && shared_bytes + nw * per_warp > 220 * 1024) nw >>= 1;
+            const size_t smem_inc = shared_bytes + nw * per_warp;
+            if (smem_inc <= 227 * 1024) {
+                static bool inc_attr[2] = {false, false};
+                const int tix = sizeof(T) == 8;
+                if (!inc_attr[tix]) {
+                    INMF_CUDA_CHECK(cudaFuncSetAttribute(hals_inc_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                         227 * 1024));
+                    inc_attr[tix] = true;
+                }
+                int64_t blocks = (g + nw - 1) / nw;
+                int per_sm = (int)((220 * 1024) / smem_inc);  // persistent: the A_i staging is paid once per CTA
+                if (per_sm < 1) per_sm = 1;
+                if (per_sm > 4) per_sm = 4;
+                if (blocks > (int64_t)inmf_num_sms() * per_sm) blocks = (int64_t)inmf_num_sms() * per_sm;
+                hals_inc_kernel<T><<<(unsigned)blocks, nw * 32, smem_inc, (cudaStream_t)stream>>>(
+                    A, B, Wt, Vt, lambda, n_prev, nall, g, k, n_inner);
+                INMF_LAUNCH_CHECK();
+                return 0;
+            }
+        }
+    }
     const size_t a_bytes = ((((size_t)nall * k * k) + 3) & ~(size_t)3) * sizeof(T);
     const bool a_smem = a_bytes <= 112 * 1024;
     const size_t budget = 220 * 1024 - (a_smem ? a_bytes : 0);

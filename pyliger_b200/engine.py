@@ -412,18 +412,35 @@ class InmfEngine(object):
         self.sub = [shard_bounds(m, self.rank, self.world) for m in self.mbs]  # this rank's part of a batch
         self.max_sub = max(hi - lo for lo, hi in self.sub)
         self.H_mb = torch.zeros(max(sum(hi - lo for lo, hi in self.sub), 1), self.ldm, dtype=dt, device=dev)
+        self.win = None  # blocked pass-1 copy over all resident cells for the mini-batch windows
         self.inv_mb = torch.tensor([1.0 / m for m in self.mbs], dtype=f64, device=dev)
 
     def online_plan(self, total_iters):
-        """Device seg_desc of every step (see ``online_windows``). Needs replicate=True."""
+        """Device seg_desc of every step (see ``online_windows``). Needs replicate=True.
+        Also builds the per-step work lists of the tiled (blocked) right-hand-side kernel."""
         plan = online_windows(total_iters, self.mbs, self.sub, self.X.n_global, self.X.row_base)
+        if self.use_blocked and total_iters > 0:
+            esize = 4 if self.dtype == torch.float32 else 8
+            sms = torch.cuda.get_device_properties(self.device).multi_processor_count
+            bp, NB, gbs = blocked.build_pass1_resident(self.X, self.ldm, esize)
+            pieces = max(1, sms // max(1, self.N * NB))
+            work, counts = blocked.window_work(self.X, NB, gbs, plan, pieces)
+            self.win = (bp, torch.from_numpy(work).to(self.device), counts)
         return torch.from_numpy(plan).to(self.device)
 
-    def online_step(self, seg_desc_t, scales, rollover, n_inner):
+    def online_step(self, seg_desc_t, scales, rollover, n_inner, step=None):
         """One mini-batch: H_mb by BPP, A/B update, HALS on W and V (_online_iNMF.py:416-460).
-        ``scales`` = per-dataset scale_param of _update_A_B (they only differ at iteration 1)."""
+        ``scales`` = per-dataset scale_param of _update_A_B (they only differ at iteration 1).
+        With ``step`` given and the window work lists built, the right-hand sides come from the tiled kernel."""
         self.prep()
-        self.solve_H(seg_desc=seg_desc_t, max_rows=self.max_sub, out=self.H_mb)
+        if step is not None and self.win is not None:
+            bp, work, counts = self.win
+            self.H_mb.zero_()
+            _lib.call("inmf_blocked_spmm", self.sfx, work[step], int(counts[step]), bp.ptr, bp.pairs, self.Mt, self.ldm, self.H_mb,
+                      self.ldm, self.k, bp.max_tile_rows, None, _stream())
+            self.bpp_H(seg_desc=seg_desc_t, max_rows=self.max_sub, out=self.H_mb)
+        else:
+            self.solve_H(seg_desc=seg_desc_t, max_rows=self.max_sub, out=self.H_mb)
         self.stats(seg_desc=seg_desc_t, max_rows=self.max_sub, H=self.H_mb, St=self.XHt, HtH=self.HHt)
         if len(set(scales)) == 1:
             _lib.call("inmf_update_ab", self.sfx, self.A, self.A_old, self.B, self.B_old, self.HHt, self.XHt,

@@ -93,7 +93,7 @@ def _cal_W_V(Xs, num_genes, num_cells, prev_info, W_init, V_init, A_init, B_init
         else:
             scales = [(it - 1) / it] * num_files
         rollover = bool(epoch > 0 and epoch - epoch_prev == 1)
-        engine.online_step(plan[it], scales, rollover, miniBatch_max_iters)
+        engine.online_step(plan[it], scales, rollover, miniBatch_max_iters, step=it)
     return engine
 
 

@@ -248,6 +248,44 @@ def test_blocked_formats_reproduce_products(world, rank, dtype):
     assert p1.pairs.shape[0] == own_nnz == p2.pairs.shape[0]
 
 
+@pytest.mark.parametrize("world,rank", [(1, 0), (2, 1)])
+def test_window_work_lists_reproduce_minibatch_rhs(world, rank):
+    """Blocked format over all resident cells + per-step work lists == X[window rows] @ M of online_iNMF."""
+    from pyliger_b200 import blocked
+    from pyliger_b200.engine import DeviceCSR, online_windows, shard_bounds
+    rng = np.random.default_rng(11)
+    g, k, kp = 93, 5, 8
+    mats = [sps.random(n, g, density=0.25, random_state=20 + i, format="csr") for i, n in enumerate((131, 58))]
+    X = DeviceCSR(mats, torch.float64, torch.device("cpu"), rank, world, replicate=True)
+    mbs = [40, 18]
+    sub = [shard_bounds(m, rank, world) for m in mbs]  # rank r handles [lo, hi) of every mini-batch
+    steps = 9  # > one epoch of the first dataset: windows wrap
+    plan = online_windows(steps, mbs, sub, X.n_global, X.row_base)
+    old = blocked.SMEM_BUDGET
+    blocked.SMEM_BUDGET = 40 * kp * 8
+    try:
+        bp, NB, gbs = blocked.build_pass1_resident(X, kp, 8)
+    finally:
+        blocked.SMEM_BUDGET = old
+    assert NB > 1
+    work, counts = blocked.window_work(X, NB, gbs, plan, pieces=3)
+    Mt = rng.uniform(0, 1, (len(mats) * g, kp)); Mt[:, k:] = 0
+    wrapped = 0
+    for t in range(steps):
+        bp.work, bp.nwork = torch.from_numpy(work[t]), int(counts[t])
+        rows = sum(hi - lo for lo, hi in sub)
+        out = np.zeros((rows, kp))
+        _emulate_blocked(bp, Mt, kp, out, k)
+        for s, m in enumerate(mats):
+            out_off, win_start, n = int(plan[t, s, 0]), int(plan[t, s, 2]), int(plan[t, s, 3])
+            cnt = int(plan[t, s + 1, 0]) - out_off
+            idx = (win_start + np.arange(cnt)) % n
+            wrapped += int(cnt > 0 and idx[-1] < idx[0])
+            np.testing.assert_allclose(out[out_off:out_off + cnt, :k], m[idx] @ Mt[s * g:(s + 1) * g, :k],
+                                       rtol=1e-12, atol=1e-12)
+    assert wrapped > 0
+
+
 def _emulate_tc(tp, dense, k, out):
     """numpy statement of inmf_tc_relayout + inmf_tc_pass from (work, ptr, pairs, segd)."""
     from pyliger_b200 import blocked
