@@ -25,6 +25,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 C2 = dict(datasets=4, cells_per_dataset=50000, genes=3000, k=30, density=0.08, value_lambda=5.0)
+# configs[3]: 8 x 250k cells, cell-sharded over the ranks (strong scaling: cells per rank = 250k / world)
+C4 = dict(datasets=8, cells_per_dataset=250000, genes=5000, k=40, density=0.08, value_lambda=5.0)
 CPU_SAMPLE_CELLS = 5000  # per dataset, for the CPU legs
 
 
@@ -148,7 +150,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
     ap.add_argument("--warm-start", type=int, default=1)
-    ap.add_argument("--cells", type=int, default=C2["cells_per_dataset"], help="cells per dataset per GPU")
+    ap.add_argument("--config", default="C2", choices=["C2", "C4"],
+                    help="C2 (default, the headline: weak scaling) or C4 (8 x 250k cells sharded over the ranks)")
+    ap.add_argument("--cells", type=int, default=0, help="cells per dataset per GPU (default: the config's)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -173,7 +177,10 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         torch.distributed.init_process_group("nccl", device_id=dev)
-    cfg = dict(C2, cells_per_dataset=args.cells)
+    base = C2 if args.config == "C2" else C4
+    strong = args.config == "C4"
+    cfg = dict(base, cells_per_dataset=args.cells or (base["cells_per_dataset"] // world if strong
+                                                      else base["cells_per_dataset"]))
     k, lam, g = cfg["k"], cfg["value_lambda"], cfg["genes"]
     dtype = torch.float32 if args.dtype == "f32" else torch.float64
     esize = 4 if args.dtype == "f32" else 8
@@ -339,8 +346,8 @@ def main():
         out = {
             "metric": "optimize_ALS cell-iterations/s", "value": value, "unit": "cell-iters/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-            "config": {"workload": "C2 optimize_ALS: %d datasets x %d cells x %d genes per GPU, density %.2f, k=%d, "
+            "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": args.config + " optimize_ALS: %d datasets x %d cells x %d genes per GPU, density %.2f, k=%d, "
                                    "lambda=%g" % (len(mats), cfg["cells_per_dataset"], g, cfg["density"], k, lam),
                        "cells_total": cells_total, "nnz_per_cell": nnz_c, "warm_start": bool(args.warm_start),
                        "l2": "inputs larger than L2 (CSR %.0f MB per GPU streamed twice per step)" % (

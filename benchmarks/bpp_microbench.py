@@ -71,7 +71,7 @@ def main():
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
                 _lib.call("inmf_bpp", args.dtype, Gd, Rt, k, Xo, k, None, 0, mask, warm, seg, 1, args.cols, k, stats,
-                          None if (warm or args.no_ginv) else ginv, _stream())
+                          None if ((warm and k <= 31) or args.no_ginv) else ginv, _stream())
                 e1.record()
                 torch.cuda.synchronize()
                 if rep > 0:

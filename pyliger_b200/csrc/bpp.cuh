@@ -10,7 +10,9 @@
 //       - fast path (|P| <= 31): lane i keeps row i of L in REGISTERS (fully unrolled), the pivot
 //         row is broadcast from a per-warp shared copy with 128-bit loads, back substitution is
 //         right-looking with one shuffle per step;
-//       - general path (|P| up to 64): L lives in the per-warp shared scratch.
+//       - complement path (|P| > 31, k - |P| <= 31, G^-1 available): the same register routine on
+//         (G^-1)_FF for the active set F, see bpp_solve_passive;
+//       - general path (anything else, |P| up to 64): L lives in the per-warp shared scratch.
 //   * y = G x - r is formed for the non-passive rows from the shared copy of G.
 // The reference solves with LAPACK LU (numpy.linalg.solve); for symmetric positive definite G_PP the
 // Cholesky solution is the same up to round-off.
@@ -47,6 +49,7 @@ struct BppWarpScratch {
     T* r;          // k   right-hand side of this column
     T* z;          // k   compacted solution (general path)
     T* dinv;       // k   1 / L[c][c]         (general path)
+    T* xf;         // k   unconstrained solution G^-1 r of this column (complement path)
     uint8_t* idx;  // 64  compacted position -> factor index
     int ldl;       // general-path leading dimension
 };
@@ -60,7 +63,7 @@ __host__ __device__ inline size_t bpp_warp_scratch_elems(int k) {
     l_elems = (l_elems + 3) & ~(size_t)3;
     const size_t kp = (k + 3) & ~3;
     const size_t zk = kp < 36 ? 36 : kp;  // the fast path writes z for all 32 lanes (+ padded reads)
-    size_t total = l_elems + 2 * kp + zk + 64 / sizeof(T);
+    size_t total = l_elems + 3 * kp + zk + 64 / sizeof(T);
     return (total + 3) & ~(size_t)3;
 }
 
@@ -77,7 +80,8 @@ __device__ __forceinline__ BppWarpScratch<T> bpp_carve(T* base, int k) {
     s.r = s.L + l_elems;
     s.z = s.r + kp;
     s.dinv = s.z + (kp < 36 ? 36 : kp);
-    s.idx = reinterpret_cast<uint8_t*>(s.dinv + kp);
+    s.xf = s.dinv + kp;
+    s.idx = reinterpret_cast<uint8_t*>(s.xf + kp);
     return s;
 }
 
@@ -200,10 +204,9 @@ __device__ __noinline__ void bpp_solve_passive_general(const T* __restrict__ Gs,
     cnt.nfact++;
 }
 
-// All k indices passive: x = G^-1 r from the shared copy of the inverse, y = 0.
+// Unconstrained solution x_full = G^-1 r from the shared copy of the inverse (once per column).
 template <typename T>
-__device__ __forceinline__ void bpp_solve_full(const T* __restrict__ Gis, int ldg, BppWarpScratch<T>& sc, int k, T& x0,
-                                               T& x1, T& y0, T& y1, BppCounters& cnt) {
+__device__ __forceinline__ void bpp_unconstrained(const T* __restrict__ Gis, int ldg, BppWarpScratch<T>& sc, int k) {
     const int lane = threadIdx.x & 31;
     const bool has0 = lane < k, has1 = lane + 32 < k;
     const T* __restrict__ I0 = Gis + (has0 ? lane : 0) * ldg;
@@ -224,31 +227,46 @@ __device__ __forceinline__ void bpp_solve_full(const T* __restrict__ Gis, int ld
         a0 = fma(I0[c], r[c], a0);
         if (k > 32) a1 = fma(I1[c], r[c], a1);
     }
-    a0 = has0 ? a0 + b0 : T(0);
-    a1 = has1 ? a1 + b1 : T(0);
-    const T m = inmf_abs(a0) > inmf_abs(a1) ? inmf_abs(a0) : inmf_abs(a1);
-    const T zscale = warp_max(m);
-    x0 = zero_x<T>(a0, zscale);
-    x1 = zero_x<T>(a1, zscale);
-    y0 = T(0);
-    y1 = T(0);
-    cnt.nfact++;
+    if (has0) sc.xf[lane] = a0 + b0;  // kept in shared memory: no registers held across the rounds
+    if (has1) sc.xf[lane + 32] = a1 + b1;
+    __syncwarp();
 }
 
-template <typename T>
-__device__ __forceinline__ void bpp_solve_passive(const T* __restrict__ Gs, int ldg, BppWarpScratch<T>& sc, int k,
-                                                  uint64_t P, T r0, T r1, T& x0, T& x1, T& y0, T& y1,
-                                                  BppCounters& cnt) {
+// Passive-set solve for the partition P (0 < |P|; |P| < k whenever the inverse is available).
+//
+// |P| <= 31: Cholesky of G_PP in registers.
+// |P| >  31 and |F| = k - |P| <= 31 (every case for k <= 62), inverse available: solve on the complement.
+//   With x = G^-1 (r + y), y_P = 0, x_F = 0:   (G^-1)_FF y_F = -xfull_F,   x_P = xfull_P + (G^-1)_PF y_F.
+//   That is the same routine on M = G^-1, S = F, q = xfull: it returns u = -y_F on F and (M u - q) = -x_P on P.
+// otherwise: general path.
+// COMP = false (instantiated for k <= 31, where |P| <= 31 always) compiles the complement path away.
+template <typename T, bool COMP>
+__device__ __forceinline__ void bpp_solve_passive(const T* __restrict__ Gs, const T* __restrict__ Gis, int ldg,
+                                                  BppWarpScratch<T>& sc, int k, uint64_t kmask, uint64_t P, T r0,
+                                                  T r1, T& x0, T& x1, T& y0, T& y1, BppCounters& cnt) {
     const int p = __popcll(P);
-    if (p <= BPP_FAST_MAX_P)
-        bpp_solve_passive_fast<T>(Gs, ldg, sc, k, P, p, r0, r1, x0, x1, y0, y1, cnt);
-    else
+    const bool comp = COMP && Gis != nullptr && p > BPP_FAST_MAX_P && k - p <= BPP_FAST_MAX_P;
+    if (!COMP || p <= BPP_FAST_MAX_P || comp) {  // !COMP: k <= 31, so is p
+        T u0, u1, v0, v1;
+        if (comp) {
+            const int lane = threadIdx.x & 31;
+            r0 = (lane < k) ? sc.xf[lane] : T(0);
+            r1 = (lane + 32 < k) ? sc.xf[lane + 32] : T(0);
+        }
+        bpp_solve_passive_fast<T>(comp ? Gis : Gs, ldg, sc, comp ? sc.xf : sc.r, k, comp ? (kmask & ~P) : P,
+                                  comp ? k - p : p, r0, r1, u0, u1, v0, v1, cnt);
+        x0 = comp ? T(0) - v0 : u0;
+        x1 = comp ? T(0) - v1 : u1;
+        y0 = comp ? T(0) - u0 : v0;
+        y1 = comp ? T(0) - u1 : v1;
+    } else {
         bpp_solve_passive_general<T>(Gs, ldg, sc, k, P, p, r0, r1, x0, x1, y0, y1, cnt);
+    }
 }
 
 // Full BPP for one column.  r0/r1: this lane's entries of r (factor lane, lane+32; 0 beyond k).
 // P: in = warm-start passive set (ignored unless warm), out = final passive set.
-template <typename T>
+template <typename T, bool COMP>
 __device__ __forceinline__ void bpp_column(const T* __restrict__ Gs, const T* __restrict__ Gis, int ldg,
                                            BppWarpScratch<T>& sc, int k,
                                            T r0, T r1, uint64_t& P, bool warm, T& x0, T& x1, T& y0, T& y1,
@@ -264,12 +282,25 @@ __device__ __forceinline__ void bpp_column(const T* __restrict__ Gs, const T* __
     int pbar = 3;
     const int max_rounds = 5 * k;  // _utilities.py:220
     int rounds = 0;
+    bool have_xf = false;  // sc.xf = G^-1 r, formed the first time a partition with |P| > 31 comes up
     while (true) {
         // evaluate the current partition (single call site keeps the unrolled solver in one copy)
-        if (P == kmask && Gis != nullptr) {
-            bpp_solve_full<T>(Gis, ldg, sc, k, x0, x1, y0, y1, cnt);
+        if (Gis != nullptr && !have_xf && (P == kmask || (COMP && __popcll(P) > BPP_FAST_MAX_P))) {
+            bpp_unconstrained<T>(Gis, ldg, sc, k);
+            have_xf = true;
+        }
+        if (P == kmask && have_xf) {  // all indices passive: x = G^-1 r, y = 0
+            const T xf0 = has0 ? sc.xf[lane] : T(0);
+            const T xf1 = has1 ? sc.xf[lane + 32] : T(0);
+            const T m = inmf_abs(xf0) > inmf_abs(xf1) ? inmf_abs(xf0) : inmf_abs(xf1);
+            const T zscale = warp_max(m);
+            x0 = zero_x<T>(xf0, zscale);
+            x1 = zero_x<T>(xf1, zscale);
+            y0 = T(0);
+            y1 = T(0);
+            cnt.nfact++;
         } else if (P != 0ull) {
-            bpp_solve_passive<T>(Gs, ldg, sc, k, P, r0, r1, x0, x1, y0, y1, cnt);
+            bpp_solve_passive<T, COMP>(Gs, Gis, ldg, sc, k, kmask, P, r0, r1, x0, x1, y0, y1, cnt);
         } else {
             x0 = T(0);
             x1 = T(0);

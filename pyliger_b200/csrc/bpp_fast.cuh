@@ -13,12 +13,16 @@
 //                                                    strictly lower triangular: no masks later)
 // Back substitution is right-looking: one shuffle + one shared load + one FMA per step.
 // Lanes beyond p run the same instructions on finite dummy data; nothing they produce is read.
+//
+// The routine is written for a generic SPD system M_SS z = q_S with the residual a - q formed off S.  The
+// caller uses it two ways (bpp_solve_passive): directly (M = G, S = P, q = r), and -- for |P| > 31 --
+// on the COMPLEMENT F = ~P with M = G^-1, q = G^-1 r, which yields -y_F and -x_P (see there).
 #pragma once
 
 template <typename T>
 __device__ __forceinline__ void bpp_solve_passive_fast(const T* __restrict__ Gs, int ldg, BppWarpScratch<T>& sc,
-                                                       int k, uint64_t P, int p, T r0, T r1, T& x0, T& x1, T& y0,
-                                                       T& y1, BppCounters& cnt) {
+                                                       const T* __restrict__ rhs, int k, uint64_t P, int p, T r0,
+                                                       T r1, T& x0, T& x1, T& y0, T& y1, BppCounters& cnt) {
     typedef BppTraits<T> TR;
     typedef typename TR::Vec Vec;
     constexpr int VEC = TR::VEC;
@@ -36,7 +40,7 @@ __device__ __forceinline__ void bpp_solve_passive_fast(const T* __restrict__ Gs,
     const bool is_g = lane < p;
     const int myidx = is_g ? (int)sc.idx[lane] : 0;
     // one gather base per lane: G row of my factor, or the right-hand side for the augmented row
-    const T* __restrict__ gbase = is_g ? (Gs + myidx * ldg) : sc.r;
+    const T* __restrict__ gbase = is_g ? (Gs + myidx * ldg) : rhs;
     T* __restrict__ Ls = sc.L;
     T* __restrict__ Lmine = Ls + lane * LDL;
     T L[32];

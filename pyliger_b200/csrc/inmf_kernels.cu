@@ -57,8 +57,9 @@ __global__ void ginv_kernel(const double* __restrict__ G, double* __restrict__ G
         Ginv[(size_t)seg * k * k + e] = ok ? ginv_a[e] : __longlong_as_double(0x7ff8000000000000ll);
 }
 
-template <typename T>
-__global__ void __launch_bounds__(BPP_THREADS, BPP_MIN_BLOCKS) bpp_kernel(const double* __restrict__ G, const double* __restrict__ Ginv, const T* R, int64_t ldr, T* X, int64_t ldx,
+// COMP kernels (k > 31) are limited to <= 5 CTAs per SM by their shared-memory scratch anyway: give them the registers.
+template <typename T, bool COMP>
+__global__ void __launch_bounds__(BPP_THREADS, COMP ? BPP_MIN_BLOCKS - 1 : BPP_MIN_BLOCKS) bpp_kernel(const double* __restrict__ G, const double* __restrict__ Ginv, const T* R, int64_t ldr, T* X, int64_t ldx,
                            T* __restrict__ Y, int64_t ldy, uint64_t* __restrict__ mask, int warm, const int64_t* __restrict__ seg_off, int k,
                            long long* __restrict__ stats) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -98,7 +99,7 @@ __global__ void __launch_bounds__(BPP_THREADS, BPP_MIN_BLOCKS) bpp_kernel(const 
         uint64_t P = (warm && mask) ? mask[col] : 0ull;
         T x0, x1, y0, y1;
         BppCounters cnt = {0, 0, 0, 0, true, {0, 0, 0, 0, 0, 0}};
-        bpp_column<T>(Gs, Gis, ldg, sc, k, r0, r1, P, warm != 0, x0, x1, y0, y1, cnt);
+        bpp_column<T, COMP>(Gs, Gis, ldg, sc, k, r0, r1, P, warm != 0, x0, x1, y0, y1, cnt);
         T* x = X + col * ldx;
         if (lane < k) x[lane] = x0;
         if (lane + 32 < k) x[lane + 32] = x1;
@@ -156,7 +157,9 @@ static int32_t bpp_launch(const double* G, const T* R, int64_t ldr, T* X, int64_
     static bool attr_done[2] = {false, false};
     const int ti = sizeof(T) == 8;
     if (!attr_done[ti]) {
-        INMF_CUDA_CHECK(cudaFuncSetAttribute(bpp_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        INMF_CUDA_CHECK(cudaFuncSetAttribute(bpp_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             227 * 1024));
+        INMF_CUDA_CHECK(cudaFuncSetAttribute(bpp_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              227 * 1024));
         attr_done[ti] = true;
     }
@@ -168,8 +171,12 @@ static int32_t bpp_launch(const double* G, const T* R, int64_t ldr, T* X, int64_
         INMF_LAUNCH_CHECK();
     }
     dim3 grid((unsigned)blocks, (unsigned)nseg);
-    bpp_kernel<T><<<grid, nwarps * 32, smem, (cudaStream_t)stream>>>(
-        G, ginv_ws, R, ldr, X, ldx, Y, ldy, mask, warm, seg_off, k, (long long*)stats);
+    if (k > BPP_FAST_MAX_P)  // passive sets beyond the register solver exist: build with the complement path
+        bpp_kernel<T, true><<<grid, nwarps * 32, smem, (cudaStream_t)stream>>>(
+            G, ginv_ws, R, ldr, X, ldx, Y, ldy, mask, warm, seg_off, k, (long long*)stats);
+    else
+        bpp_kernel<T, false><<<grid, nwarps * 32, smem, (cudaStream_t)stream>>>(
+            G, ginv_ws, R, ldr, X, ldx, Y, ldy, mask, warm, seg_off, k, (long long*)stats);
     INMF_LAUNCH_CHECK();
     return 0;
 }

@@ -265,6 +265,11 @@ class InmfEngine(object):
             _lib.call("inmf_spmm", self.sfx, X.rowptr, X.colidx, X.vals, self.Mt, self.ldm, self.g, out, self.ldm,
                       seg_desc, nseg, max_rows, k, _stream())
 
+    def _ginv(self, warm):
+        """Workspace for G^-1: cold starts use it for the all-passive first round, k > 31 for passive sets
+        larger than the 31-row register solver (solved on the complement instead)."""
+        return self.ginv_ws if (not warm or self.k > 31) else None
+
     def bpp_H(self, seg_desc=None, max_rows=None, out=None, mask=None, warm=False, nseg=None):
         """In-place batched BPP on the right-hand sides produced by rhs_H."""
         if seg_desc is None:
@@ -278,7 +283,7 @@ class InmfEngine(object):
             return
         k = self.k
         _lib.call("inmf_bpp", self.sfx, self.G, out, self.ldm, out, self.ldm, None, 0, mask, 1 if warm else 0,
-                  seg_off, nseg, max_rows, k, self.bpp_stats[0], None if warm else self.ginv_ws, _stream())
+                  seg_off, nseg, max_rows, k, self.bpp_stats[0], self._ginv(warm), _stream())
 
     def solve_H(self, seg_desc=None, max_rows=None, out=None, mask=None, warm=False, nseg=None):
         """out[q,:] = argmin_{h>=0} for every row of the windows in seg_desc (default: all owned cells)."""
@@ -319,14 +324,14 @@ class InmfEngine(object):
         _lib.call("inmf_rhs_v", self.sfx, self.St, self.Wt, self.HtH, self.Rv, self.Gv, self.lam, N, g, k,
                   _stream())
         _lib.call("inmf_bpp", self.sfx, self.Gv, self.Rv, k, self.Vt, k, None, 0, self.mask_V,
-                  1 if warm else 0, self.seg_genes, N, g, k, self.bpp_stats[1], None if warm else self.ginv_ws,
+                  1 if warm else 0, self.seg_genes, N, g, k, self.bpp_stats[1], self._ginv(warm),
                   _stream())
 
     def solve_W(self, warm=False):
         k, g, N = self.k, self.g, self.N
         _lib.call("inmf_rhs_w", self.sfx, self.St, self.Vt, self.HtH, self.Rw, self.Gw, N, g, k, _stream())
         _lib.call("inmf_bpp", self.sfx, self.Gw, self.Rw, k, self.Wt, k, None, 0, self.mask_W,
-                  1 if warm else 0, self.seg_w, 1, g, k, self.bpp_stats[2], None if warm else self.ginv_ws, _stream())
+                  1 if warm else 0, self.seg_w, 1, g, k, self.bpp_stats[2], self._ginv(warm), _stream())
 
     def objective(self):
         """Objective from the current St/HtH and the Mt/Gwv/Gvv of the last prep(). Device scalar."""

@@ -119,6 +119,39 @@ def test_bpp_random_vs_oracle_and_kkt(k, dtype):
         assert np.linalg.norm(X[:, c] - ref) <= (1e-8 if dtype == "float64" else 5e-3) * max(1.0, np.linalg.norm(ref))
 
 
+@pytest.mark.parametrize("k", [33, 40, 47, 62, 63, 64])
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+@pytest.mark.parametrize("warm", [False, True])
+def test_bpp_large_passive_sets(k, dtype, warm):
+    """Mostly-positive solutions: passive sets of 32..k indices (complement-set / general solver paths)."""
+    from pyliger_b200 import nnlsm_blockpivot
+    rng = np.random.default_rng(300 + k)
+    m, cols = 4 * k, 600
+    A = rng.uniform(0, 1, (m, k)) + np.eye(m, k)
+    Xt = rng.uniform(0.2, 1.0, (k, cols))
+    Xt[rng.uniform(size=Xt.shape) < 0.08] = -0.5  # a few components want to be negative -> clamped
+    R_noise = 0.05 * rng.standard_normal((m, cols))
+    B = A @ Xt + R_noise
+    G, R = A.T @ A, A.T @ B
+    Xo, infoo = orc.nnlsm_blockpivot(G, R, is_input_prod=True)
+    psize = (Xo > 0).sum(0)
+    assert (psize > 31).any() and (psize < k).any()
+    assert k < 40 or (psize > 31).mean() > 0.5
+    init = None
+    if warm:  # start from a perturbed passive set: one wrong index per column
+        init = (Xo > 0).astype(float)
+        flip = rng.integers(0, k, cols)
+        init[flip, np.arange(cols)] = 1.0 - init[flip, np.arange(cols)]
+    X, info = nnlsm_blockpivot(G, R, is_input_prod=True, init=init, dtype=dtype)
+    assert info[0] is True and (X >= 0).all()
+    if dtype == "float64":
+        assert relerr(X, Xo) < 1e-9
+        assert orc.kkt_violation(G, R, X) < 1e-8
+        assert ((X > 0) == (Xo > 0)).all()
+    else:
+        assert relerr(X, Xo) < 5e-3
+
+
 def test_bpp_edge_cases():
     from pyliger_b200 import nnlsm_blockpivot
     G = np.array([[2.0, 0.5], [0.5, 1.0]])
