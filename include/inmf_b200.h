@@ -202,6 +202,38 @@ void inmf_tc_debug_buffer(void* device_int64_buffer);
  * shared-memory descriptor / instruction descriptor / TMEM plumbing of the dense-tile passes. */
 int32_t inmf_tc_selftest(const float* A, const float* B, float* C, int32_t n, int32_t three_pass, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Producers of scale_data: the O(nnz) passes just before the factorisation.
+ * CSR of one dataset (cells x genes): rowptr int64[n_rows + 1], colidx int32[nnz], vals T[nnz].
+ * ------------------------------------------------------------------------------------------------------- */
+
+/* normalize -> _normalize_matrix (/root/reference/src/pyliger/preprocessing/_normalization.py:91-99):
+ * norm_vals = vals / (row sum of |vals|) (rows with zero norm unchanged: sklearn normalize(norm="l1")),
+ * col_sum[g] += norm_vals, col_sumsq[g] += norm_vals^2 (double[genes], caller zeroes them: they become
+ * var["norm_sum"], var["norm_sum_sq"]), *n_missing += rows whose plain sum is 0 (_remove_missing_obs,
+ * /root/reference/src/pyliger/_utilities.py:74-75).  norm_vals may alias vals. */
+int32_t inmf_normalize_rows_f32(const int64_t* rowptr, const int32_t* colidx, const float* vals, int64_t n_rows,
+                                float* norm_vals, double* col_sum, double* col_sumsq, int64_t* n_missing,
+                                void* stream);
+int32_t inmf_normalize_rows_f64(const int64_t* rowptr, const int32_t* colidx, const double* vals, int64_t n_rows,
+                                double* norm_vals, double* col_sum, double* col_sumsq, int64_t* n_missing,
+                                void* stream);
+
+/* scale_not_center -> _scale_matrix (/root/reference/src/pyliger/preprocessing/_scale.py:92-102): keep the
+ * variable genes (colmap int32[genes]: new column index, or -1 = dropped; increasing on the kept genes) and
+ * multiply by the per-gene scaler (double[kept genes] = 1 / sqrt(norm_sum_sq / (n_rows - 1))).
+ * Two steps around one exclusive scan done by the caller:
+ *   inmf_select_count   row_counts[r] = kept non-zeros of row r
+ *   inmf_select_scale   writes new_colidx / new_vals at new_rowptr[r].. in the original order. */
+int32_t inmf_select_count(const int64_t* rowptr, const int32_t* colidx, int64_t n_rows, const int32_t* colmap,
+                          int64_t* row_counts, void* stream);
+int32_t inmf_select_scale_f32(const int64_t* rowptr, const int32_t* colidx, const float* vals, int64_t n_rows,
+                              const int32_t* colmap, const double* scaler, const int64_t* new_rowptr,
+                              int32_t* new_colidx, float* new_vals, void* stream);
+int32_t inmf_select_scale_f64(const int64_t* rowptr, const int32_t* colidx, const double* vals, int64_t n_rows,
+                              const int32_t* colmap, const double* scaler, const int64_t* new_rowptr,
+                              int32_t* new_colidx, double* new_vals, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -27,10 +27,12 @@ _TYPED = {
     "inmf_normal_eq": [_PTR, _PTR, _I64, _I32, _I64, _PTR, _PTR, _PTR],
     "inmf_gram_rows": [_PTR, _I64, _PTR, _I32, _I64, _PTR, _I32, _PTR],
     "inmf_blocked_spmm": [_PTR, _I32, _PTR, _PTR, _PTR, _I32, _PTR, _I64, _I32, _I32, _PTR, _PTR],
+    "inmf_normalize_rows": [_PTR, _PTR, _PTR, _I64, _PTR, _PTR, _PTR, _PTR, _PTR],
+    "inmf_select_scale": [_PTR, _PTR, _PTR, _I64, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR],
 }
 
 EXPORTED_SYMBOLS = ["inmf_version", "inmf_last_error", "inmf_launch_count", "inmf_tc_selftest",
-                    "inmf_tc_relayout_f32", "inmf_tc_pass_f32", "inmf_tc_debug_buffer"] + [
+                    "inmf_tc_relayout_f32", "inmf_tc_pass_f32", "inmf_tc_debug_buffer", "inmf_select_count"] + [
     "%s_%s" % (n, t) for n in _TYPED for t in ("f32", "f64")
 ]
 
@@ -63,6 +65,8 @@ def load():
     lib.inmf_tc_relayout_f32.argtypes = [_PTR, _I64, _PTR, _I32, _I64, _PTR, _PTR, _I32, _I32, _PTR]
     lib.inmf_tc_pass_f32.restype = _I32
     lib.inmf_tc_pass_f32.argtypes = [_PTR, _I32, _PTR, _PTR, _PTR, _PTR, _PTR, _I64, _I32, _I32, _I32, _I32, _PTR]
+    lib.inmf_select_count.restype = _I32
+    lib.inmf_select_count.argtypes = [_PTR, _PTR, _I64, _PTR, _PTR, _PTR]
     for name, argtypes in _TYPED.items():
         for suffix in ("f32", "f64"):
             fn = getattr(lib, "%s_%s" % (name, suffix))

@@ -4,24 +4,106 @@ pyliger keeps its data in ``anndata.AnnData`` objects held by a ``Liger`` object
 (/root/reference/src/pyliger/pyliger.py:12-105).  ``optimize_ALS`` / ``online_iNMF`` only touch
 ``liger.adata_list``, ``liger.num_samples``, ``liger.var_genes`` and, per AnnData, ``.shape``,
 ``.layers["scale_data"]``, ``.obsm``, ``.varm``, ``.uns``, ``.isbacked``
-(_iNMF_ANLS.py:79-84,182-185; _online_iNMF.py:131-137,171-176,192-198).  A real pyliger ``Liger`` of
+(_iNMF_ANLS.py:79-84,182-185; _online_iNMF.py:131-137,171-176,192-198); normalize / scale_not_center
+also use ``.X``, ``.var`` / ``.obs`` (pandas), ``.raw`` and ``adata[:, mask].copy()``
+(preprocessing/_normalization.py:42-55, _scale.py:92-102).  A real pyliger ``Liger`` of
 real AnnData objects works unchanged with this package; these classes exist so that the path can
 be driven (tests, bench) where anndata is not installed.
 """
 
 
-class AnnDataLike(object):
-    def __init__(self, scale_data, sample_name=None):
-        self.X = scale_data
-        self.layers = {"scale_data": scale_data}
-        self.obsm = {}
-        self.varm = {}
-        self.uns = {"sample_name": sample_name}
-        self.isbacked = False
+class _Raw(object):
+    """What ``adata.raw = adata`` keeps (anndata freezes X and var at that point)."""
+
+    def __init__(self, adata):
+        self.X = adata.X
+        self.var = adata.var.copy() if adata.var is not None else None
 
     @property
     def shape(self):
         return self.X.shape
+
+
+class AnnDataLike(object):
+    """Duck-typed AnnData: X, layers, obs / var (pandas), obsm / varm, uns, slicing by boolean masks and
+    ``copy()`` -- the surface that normalize / scale_not_center / optimize_ALS / online_iNMF use."""
+
+    def __init__(self, scale_data=None, sample_name=None, X=None, obs_names=None, var_names=None):
+        self.X = scale_data if X is None else X
+        self.layers = {} if scale_data is None else {"scale_data": scale_data}
+        self.obsm = {}
+        self.varm = {}
+        self.uns = {"sample_name": sample_name}
+        self.isbacked = False
+        self._raw = None
+        n, g = self.X.shape
+        import pandas as pd
+        self.obs = pd.DataFrame(index=pd.Index(obs_names if obs_names is not None
+                                               else ["cell%d" % i for i in range(n)]).astype(str))
+        self.var = pd.DataFrame(index=pd.Index(var_names if var_names is not None
+                                               else ["g%d" % j for j in range(g)]).astype(str))
+
+    @classmethod
+    def from_raw(cls, X, sample_name=None, obs_names=None, var_names=None):
+        """Dataset holding raw counts only (what create_liger starts from)."""
+        return cls(None, sample_name, X=X, obs_names=obs_names, var_names=var_names)
+
+    @property
+    def shape(self):
+        return self.X.shape
+
+    @property
+    def raw(self):
+        return self._raw
+
+    @raw.setter
+    def raw(self, adata):
+        self._raw = None if adata is None else _Raw(adata)
+
+    def copy(self):
+        import copy as _copy
+        out = AnnDataLike.__new__(AnnDataLike)
+        out.X = self.X.copy()
+        out.layers = {name: m.copy() for name, m in self.layers.items()}
+        out.obsm = {name: m.copy() for name, m in self.obsm.items()}
+        out.varm = {name: m.copy() for name, m in self.varm.items()}
+        out.uns = _copy.copy(self.uns)
+        out.isbacked = False
+        out._raw = self._raw
+        out.obs = self.obs.copy()
+        out.var = self.var.copy()
+        return out
+
+    def __getitem__(self, key):
+        """adata[rows, cols] with boolean masks, index arrays or slices (a new object, like a materialised view)."""
+        import numpy as np
+        rows, cols = key if isinstance(key, tuple) else (key, slice(None))
+
+        def pos(sel, n):
+            if isinstance(sel, slice):
+                return np.arange(n)[sel]
+            sel = np.asarray(sel)
+            return np.nonzero(sel)[0] if sel.dtype == bool else sel
+
+        n, g = self.shape
+        r, c = pos(rows, n), pos(cols, g)
+        all_rows, all_cols = len(r) == n and (r == np.arange(n)).all(), len(c) == g and (c == np.arange(g)).all()
+
+        def cut(m):
+            m = m if all_rows else m[r]
+            return m if all_cols else m[:, c]
+
+        out = AnnDataLike.__new__(AnnDataLike)
+        out.X = cut(self.X)
+        out.layers = {name: cut(m) for name, m in self.layers.items()}
+        out.obsm = {name: m[r] for name, m in self.obsm.items()}
+        out.varm = {name: m[c] for name, m in self.varm.items()}
+        out.uns = dict(self.uns)
+        out.isbacked = False
+        out._raw = self._raw
+        out.obs = self.obs.iloc[r]
+        out.var = self.var.iloc[c]
+        return out
 
 
 class Liger(object):
@@ -50,6 +132,12 @@ class Liger(object):
     @property
     def W(self):
         return self.adata_list[0].varm["W"]
+
+
+def liger_from_raw(mats, names=None, var_names=None):
+    """``Liger`` of datasets that carry raw count matrices only (the input of normalize)."""
+    names = names or ["sample%d" % i for i in range(len(mats))]
+    return Liger([AnnDataLike.from_raw(m, nm, var_names=var_names) for m, nm in zip(mats, names)])
 
 
 def liger_from_matrices(mats, names=None):

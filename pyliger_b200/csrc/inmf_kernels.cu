@@ -1221,3 +1221,75 @@ extern "C" int32_t inmf_tc_pass_f32(const int64_t* work, int32_t nwork, const in
     INMF_LAUNCH_CHECK();
     return 0;
 }
+
+// =================================================================================================
+// Preprocessing passes: normalize + scale_not_center (the producers of scale_data)
+// =================================================================================================
+#include "preprocess.cuh"
+
+static inline unsigned rows_grid(int64_t n_rows) {
+    int64_t blocks = (n_rows + 7) / 8;  // 8 warps (rows) per 256-thread CTA
+    const int64_t cap = (int64_t)inmf_num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    return (unsigned)(blocks < 1 ? 1 : blocks);
+}
+
+template <typename T>
+static int32_t normalize_rows_launch(const int64_t* rowptr, const int32_t* colidx, const T* vals, int64_t n_rows,
+                                     T* norm_vals, double* col_sum, double* col_sumsq, int64_t* n_missing,
+                                     void* stream) {
+    INMF_REQUIRE(n_rows >= 0, "n_rows must be >= 0");
+    if (n_rows == 0) return 0;
+    normalize_rows_kernel<T><<<rows_grid(n_rows), 256, 0, (cudaStream_t)stream>>>(
+        rowptr, colidx, vals, n_rows, norm_vals, col_sum, col_sumsq, (unsigned long long*)n_missing);
+    INMF_LAUNCH_CHECK();
+    return 0;
+}
+extern "C" int32_t inmf_normalize_rows_f32(const int64_t* rowptr, const int32_t* colidx, const float* vals,
+                                           int64_t n_rows, float* norm_vals, double* col_sum, double* col_sumsq,
+                                           int64_t* n_missing, void* stream) {
+    return normalize_rows_launch<float>(rowptr, colidx, vals, n_rows, norm_vals, col_sum, col_sumsq, n_missing,
+                                        stream);
+}
+extern "C" int32_t inmf_normalize_rows_f64(const int64_t* rowptr, const int32_t* colidx, const double* vals,
+                                           int64_t n_rows, double* norm_vals, double* col_sum, double* col_sumsq,
+                                           int64_t* n_missing, void* stream) {
+    return normalize_rows_launch<double>(rowptr, colidx, vals, n_rows, norm_vals, col_sum, col_sumsq, n_missing,
+                                         stream);
+}
+
+extern "C" int32_t inmf_select_count(const int64_t* rowptr, const int32_t* colidx, int64_t n_rows,
+                                     const int32_t* colmap, int64_t* row_counts, void* stream) {
+    INMF_REQUIRE(n_rows >= 0, "n_rows must be >= 0");
+    if (n_rows == 0) return 0;
+    select_count_kernel<<<rows_grid(n_rows), 256, 0, (cudaStream_t)stream>>>(rowptr, colidx, n_rows, colmap,
+                                                                             row_counts);
+    INMF_LAUNCH_CHECK();
+    return 0;
+}
+
+template <typename T>
+static int32_t select_scale_launch(const int64_t* rowptr, const int32_t* colidx, const T* vals, int64_t n_rows,
+                                   const int32_t* colmap, const double* scaler, const int64_t* new_rowptr,
+                                   int32_t* new_colidx, T* new_vals, void* stream) {
+    INMF_REQUIRE(n_rows >= 0, "n_rows must be >= 0");
+    if (n_rows == 0) return 0;
+    select_scale_kernel<T><<<rows_grid(n_rows), 256, 0, (cudaStream_t)stream>>>(
+        rowptr, colidx, vals, n_rows, colmap, scaler, new_rowptr, new_colidx, new_vals);
+    INMF_LAUNCH_CHECK();
+    return 0;
+}
+extern "C" int32_t inmf_select_scale_f32(const int64_t* rowptr, const int32_t* colidx, const float* vals,
+                                         int64_t n_rows, const int32_t* colmap, const double* scaler,
+                                         const int64_t* new_rowptr, int32_t* new_colidx, float* new_vals,
+                                         void* stream) {
+    return select_scale_launch<float>(rowptr, colidx, vals, n_rows, colmap, scaler, new_rowptr, new_colidx, new_vals,
+                                      stream);
+}
+extern "C" int32_t inmf_select_scale_f64(const int64_t* rowptr, const int32_t* colidx, const double* vals,
+                                         int64_t n_rows, const int32_t* colmap, const double* scaler,
+                                         const int64_t* new_rowptr, int32_t* new_colidx, double* new_vals,
+                                         void* stream) {
+    return select_scale_launch<double>(rowptr, colidx, vals, n_rows, colmap, scaler, new_rowptr, new_colidx,
+                                       new_vals, stream);
+}

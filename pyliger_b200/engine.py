@@ -12,7 +12,7 @@ import numpy as np
 import scipy.sparse as sps
 import torch
 
-from . import _lib, blocked
+from . import _lib, blocked, devcache
 
 _SUFFIX = {torch.float32: "f32", torch.float64: "f64"}
 
@@ -104,13 +104,17 @@ class DeviceCSR(object):
         for m, (lo, hi) in zip(mats, self.bounds):
             if m.shape[1] != self.g:
                 raise ValueError("all datasets must share the same genes (columns)")
+            twin = devcache.lookup(m, device)  # left on the device by scale_not_center: no upload
             if not sps.isspmatrix_csr(m):
                 m = sps.csr_matrix(m)
             if not m.has_sorted_indices:
                 m = m.sorted_indices()
             p0, p1 = int(m.indptr[lo]), int(m.indptr[hi])
             indptr.append(m.indptr[lo + 1:hi + 1].astype(np.int64) - p0 + off)
-            pieces.append((off, m.indices[p0:p1], m.data[p0:p1]))
+            if twin is not None:
+                pieces.append((off, twin[1][p0:p1], twin[2][p0:p1]))
+            else:
+                pieces.append((off, m.indices[p0:p1], m.data[p0:p1]))
             off += p1 - p0
         self.nnz = off
         self.rowptr = torch.from_numpy(np.concatenate(indptr)).to(device)
@@ -120,6 +124,10 @@ class DeviceCSR(object):
         for o, idx, val in pieces:
             n = idx.shape[0]
             if n == 0:
+                continue
+            if torch.is_tensor(idx):  # device twin: device-to-device copies (with casts)
+                self.colidx[o:o + n].copy_(idx)
+                self.vals[o:o + n].copy_(val)
                 continue
             ti = torch.from_numpy(np.ascontiguousarray(idx))
             tv = torch.from_numpy(np.ascontiguousarray(val))

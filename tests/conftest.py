@@ -49,3 +49,8 @@ def golden_als3():
 @pytest.fixture(scope="session")
 def golden_online():
     return load_golden("online.npz")
+
+
+@pytest.fixture(scope="session")
+def golden_pre():
+    return load_golden("preprocess.npz")

@@ -14,7 +14,9 @@ import os
 import sys
 
 import numpy as np
+import pandas  # noqa: F401  (before the shims: they stub pandas' optional numexpr)
 import scipy.sparse as sps
+import sklearn.preprocessing  # noqa: F401
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
@@ -237,10 +239,47 @@ def gen_online():
     print("online done; W sum", d["s1_W"].sum(), "s2 W sum", d["s2_W"].sum())
 
 
+def gen_preprocess():
+    """normalize + scale_not_center of the reference (preprocessing/_normalization.py, _scale.py), in-memory
+    mode, on raw counts held by the duck-typed AnnData of pyliger_b200.containers."""
+    from pyliger.preprocessing._normalization import normalize as ref_normalize
+    from pyliger.preprocessing._scale import scale_not_center as ref_scale
+    from pyliger_b200.containers import AnnDataLike
+
+    rng = np.random.default_rng(77)
+    g = 40
+    var_names = ["gene%d" % j for j in range(g)]
+    raws = []
+    for i, n in enumerate((60, 45)):
+        C = rng.poisson(0.35, size=(n, g)).astype(np.float64)
+        C[np.arange(n), rng.integers(0, g, n)] += 1.0  # no empty cells
+        C[:, 3 + i] = 0.0                              # a gene absent from this dataset
+        raws.append(sps.csr_matrix(C))
+    var_genes = [var_names[j] for j in sorted(rng.choice(g, 25, replace=False))]
+    lig = RefLiger([AnnDataLike.from_raw(m, "s%d" % i, var_names=var_names) for i, m in enumerate(raws)])
+    with contextlib.redirect_stdout(io.StringIO()):
+        ref_normalize(lig)
+    d = {"var_genes": np.asarray(var_genes), "var_names": np.asarray(var_names)}
+    for i, a in enumerate(lig.adata_list):
+        csr_pack("raw%d" % i, raws[i], d)
+        csr_pack("norm%d" % i, a.layers["norm_data"], d)
+        for col in ("norm_sum", "norm_sum_sq", "norm_mean"):
+            d["%s%d" % (col, i)] = a.var[col].to_numpy()
+    lig.var_genes = var_genes
+    with contextlib.redirect_stdout(io.StringIO()), np.errstate(divide="ignore"):
+        ref_scale(lig)
+    for i, a in enumerate(lig.adata_list):
+        csr_pack("scale%d" % i, a.layers["scale_data"], d)
+        d["scaled_var_names%d" % i] = np.asarray(list(a.var.index), dtype=str)
+        d["raw_shape%d" % i] = np.asarray(a.raw.shape)
+    np.savez_compressed(os.path.join(OUT, "preprocess.npz"), **d)
+    print("preprocess done; scale_data sums", [float(a.layers["scale_data"].sum()) for a in lig.adata_list])
+
+
 if __name__ == "__main__":
-    gen_bpp()
-    gen_als()
-    gen_online()
+    which = sys.argv[1:] or ["bpp", "als", "online", "preprocess"]
+    for name in which:
+        {"bpp": gen_bpp, "als": gen_als, "online": gen_online, "preprocess": gen_preprocess}[name]()
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")

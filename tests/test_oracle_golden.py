@@ -186,3 +186,27 @@ def test_online_scenario3_projection(golden_online):
     out = orc.projection([csr_unpack(d, "Xnew")], d["s1_W"], 5, 100)
     assert relerr(out["H"][0], d["s3_H"]) < 1e-8
     assert np.all(out["V"][0] == 0) and out["V"][0].shape == d["s3_V"].shape
+
+
+# ------------------------------------------------------------------ normalize / scale_not_center (8(f) rank 1)
+def test_preprocess_oracle_matches_reference(golden_pre):
+    from oracle import preprocess_oracle as pre
+    d = golden_pre
+    var_idx = np.isin(d["var_names"], d["var_genes"])
+    for i in range(2):
+        raw = csr_unpack(d, "raw%d" % i)
+        assert not pre.missing_rows(raw).any()
+        norm, s1, s2 = pre.normalize_matrix(raw)
+        ref = csr_unpack(d, "norm%d" % i)
+        assert (norm.indices == ref.indices).all() and (norm.indptr == ref.indptr).all()
+        np.testing.assert_allclose(norm.data, ref.data, rtol=1e-15, atol=0)
+        np.testing.assert_allclose(s1, d["norm_sum%d" % i], rtol=1e-13)
+        np.testing.assert_allclose(s2, d["norm_sum_sq%d" % i], rtol=1e-13)
+        sc = pre.scale_matrix(norm, s2, var_idx)
+        ref = csr_unpack(d, "scale%d" % i)
+        assert sc.shape == ref.shape and (sc.indices == ref.indices).all() and (sc.indptr == ref.indptr).all()
+        np.testing.assert_allclose(sc.data, ref.data, rtol=1e-13, atol=0)
+        # per-gene RMS of scale_data is 1 for every gene that is expressed (the property ALS relies on)
+        ms = np.asarray(sc.power(2).sum(axis=0)).ravel() / (sc.shape[0] - 1)
+        expressed = np.asarray((sc != 0).sum(axis=0)).ravel() > 0
+        np.testing.assert_allclose(ms[expressed], 1.0, rtol=1e-12)
