@@ -12,7 +12,7 @@ import numpy as np
 import scipy.sparse as sps
 import torch
 
-from . import _lib, blocked, devcache
+from . import _lib, blocked, devcache, staging
 
 _SUFFIX = {torch.float32: "f32", torch.float64: "f64"}
 
@@ -121,6 +121,7 @@ class DeviceCSR(object):
         self.colidx = torch.empty(off, dtype=torch.int32, device=device)
         self.vals = torch.empty(off, dtype=dtype, device=device)
         self.h2d_bytes = self.rowptr.numel() * 8
+        jobs = []
         for o, idx, val in pieces:
             n = idx.shape[0]
             if n == 0:
@@ -128,16 +129,15 @@ class DeviceCSR(object):
             if torch.is_tensor(idx):  # device twin: device-to-device copies (with casts)
                 self.colidx[o:o + n].copy_(idx)
                 self.vals[o:o + n].copy_(val)
-                continue
-            ti = torch.from_numpy(np.ascontiguousarray(idx))
-            tv = torch.from_numpy(np.ascontiguousarray(val))
-            self.h2d_bytes += ti.numel() * ti.element_size() + tv.numel() * tv.element_size()
-            if pin:
-                ti, tv = ti.pin_memory(), tv.pin_memory()
-            di = ti.to(device, non_blocking=pin)
-            dv = tv.to(device, non_blocking=pin)
-            self.colidx[o:o + n].copy_(di)   # device-side casts (int64 -> int32, float64 -> T) if needed
-            self.vals[o:o + n].copy_(dv)
+            elif device.type == "cuda":
+                # pinned staging ring; int64 indices / float64 values are narrowed on the host side of the bus
+                jobs.append((self.colidx[o:o + n], idx))
+                jobs.append((self.vals[o:o + n], val))
+            else:  # CPU tensors (host-logic tests)
+                self.colidx[o:o + n].copy_(torch.from_numpy(np.ascontiguousarray(idx)))
+                self.vals[o:o + n].copy_(torch.from_numpy(np.ascontiguousarray(val)))
+        if jobs:
+            self.h2d_bytes += staging.upload(device, jobs)
 
 
 class InmfEngine(object):
