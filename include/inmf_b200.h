@@ -234,6 +234,12 @@ int32_t inmf_select_scale_f64(const int64_t* rowptr, const int32_t* colidx, cons
                               const int32_t* colmap, const double* scaler, const int64_t* new_rowptr,
                               int32_t* new_colidx, double* new_vals, void* stream);
 
+/* Seeded initial factors without a host round trip: out[i] = i-th value of
+ *   np.random.seed(seed); np.random.uniform(0, scale, n)
+ * (numpy's legacy MT19937 stream, bit-identical), the draw the reference initialises W, V_i, H_i with
+ * (/root/reference/src/pyliger/factorization/_iNMF_ANLS.py:103-108). */
+int32_t inmf_mt19937_uniform(uint32_t seed, int64_t n, double scale, double* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1293,3 +1293,73 @@ extern "C" int32_t inmf_select_scale_f64(const int64_t* rowptr, const int32_t* c
     return select_scale_launch<double>(rowptr, colidx, vals, n_rows, colmap, scaler, new_rowptr, new_colidx,
                                        new_vals, stream);
 }
+
+// =================================================================================================
+// Seeded initial factors on the device: the stream of numpy's legacy global RNG,
+//   np.random.seed(seed); np.random.uniform(0, scale, n)      (_iNMF_ANLS.py:103-108, _online_iNMF.py:147-160)
+// = MT19937 seeded by init_genrand, two 32-bit outputs per double ((a >> 5) * 2^26 + (b >> 6)) / 2^53.
+// The twist of a 624-word block is 227-wide parallel in three dependent phases, so one CTA walks the stream;
+// every arithmetic step is exact in double, which makes the result bit-identical to numpy's.
+// =================================================================================================
+__device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
+    y ^= y >> 11;
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= y >> 18;
+    return y;
+}
+
+// 512 threads: threads 0..255 twist block b into the other state buffer (three phases, one barrier each) while
+// threads 256..511 temper and write block b-1 from the current one, so a 624-word block costs three barriers.
+__global__ void __launch_bounds__(512, 1) mt19937_uniform_kernel(uint32_t seed, int64_t n, double scale,
+                                                                 double* __restrict__ out) {
+    __shared__ uint32_t st[2][624];
+    const int t = threadIdx.x;
+    if (t == 0) {
+        uint32_t s = seed;
+        st[0][0] = s;
+        for (int i = 1; i < 624; ++i) {
+            s = 1812433253u * (s ^ (s >> 30)) + (uint32_t)i;
+            st[0][i] = s;
+        }
+    }
+    __syncthreads();
+    const int64_t nblocks = (n + 311) / 312;
+    int cur = 0;
+    for (int64_t b = 0; b <= nblocks; ++b) {
+        const uint32_t* __restrict__ C = st[cur];
+        uint32_t* __restrict__ N = st[cur ^ 1];
+        const bool twist = t < 227 && b < nblocks;
+        const int e = t - 256;
+        const bool emit = e >= 0 && e < 104 && b >= 1;
+#pragma unroll
+        for (int ph = 0; ph < 3; ++ph) {
+            const int i = ph * 227 + t;
+            if (twist && i < 624) {
+                const uint32_t x1 = (i + 1 == 624) ? N[0] : C[i + 1];
+                const uint32_t xm = (i + 397 < 624) ? C[i + 397] : N[i + 397 - 624];
+                const uint32_t y = (C[i] & 0x80000000u) | (x1 & 0x7fffffffu);
+                N[i] = xm ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+            }
+            if (emit) {
+                const int d = ph * 104 + e;
+                const int64_t o = (b - 1) * 312 + d;
+                if (o < n) {
+                    const uint32_t a = mt_temper(C[2 * d]) >> 5, bb = mt_temper(C[2 * d + 1]) >> 6;
+                    const double u = ((double)a * 67108864.0 + (double)bb) / 9007199254740992.0;
+                    out[o] = 0.0 + scale * u;
+                }
+            }
+            __syncthreads();
+        }
+        cur ^= 1;
+    }
+}
+
+extern "C" int32_t inmf_mt19937_uniform(uint32_t seed, int64_t n, double scale, double* out, void* stream) {
+    INMF_REQUIRE(n >= 0, "n must be >= 0");
+    if (n == 0) return 0;
+    mt19937_uniform_kernel<<<1, 512, 0, (cudaStream_t)stream>>>(seed, n, scale, out);
+    INMF_LAUNCH_CHECK();
+    return 0;
+}

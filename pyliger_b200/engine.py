@@ -140,6 +140,31 @@ class DeviceCSR(object):
             self.h2d_bytes += staging.upload(device, jobs)
 
 
+_draw_streams = {}
+
+
+def launch_als_draw(device, ns, g, k, seed, h_stream=None):
+    """Start the seeded draw of (W, V_1..V_N, H_1..H_N) on a side stream; returns (flat double buffer, event).
+    ``h_stream``: pre-sharded multi-GPU runs draw their local H from a per-rank stream (see _als_init_host)."""
+    device = torch.device(device)
+    side = _draw_streams.get(device)
+    if side is None:
+        side = _draw_streams[device] = torch.cuda.Stream(device)
+    n_wv = (len(ns) + 1) * k * g
+    n_h = int(sum(ns)) * k
+    with torch.cuda.device(device), torch.cuda.stream(side):
+        buf = torch.empty(n_wv + n_h, dtype=torch.float64, device=device)
+        if h_stream is None:
+            _lib.call("inmf_mt19937_uniform", "", int(seed) % (2 ** 32), n_wv + n_h, 2.0, buf, side.cuda_stream)
+        else:
+            _lib.call("inmf_mt19937_uniform", "", int(seed) % (2 ** 32), n_wv, 2.0, buf, side.cuda_stream)
+            _lib.call("inmf_mt19937_uniform", "", (int(seed) + 7919 * (h_stream + 1)) % (2 ** 32), n_h, 2.0,
+                      buf[n_wv:], side.cuda_stream)
+        done = torch.cuda.Event()
+        done.record(side)
+    return buf, done
+
+
 class InmfEngine(object):
     """Buffers + step functions shared by optimize_ALS and online_iNMF."""
 
@@ -363,6 +388,29 @@ class InmfEngine(object):
                     self.h2d_state_bytes += 8 * (b1 - b0) * self.k
                     self.H[b0:b1, :self.k].copy_(torch.from_numpy(np.ascontiguousarray(
                         np.asarray(Hi, dtype=np.float64)[lo:hi])).to(dev, dt))
+
+    def draw_als_state(self, seed, h_stream=None, pending=None):
+        """Seeded W, V_i, H_i in the reference's draw order (_iNMF_ANLS.py:103-108: W, then every V_i, then every
+        H_i, all abs(uniform(0, 2)) from numpy's global RNG) generated on the device -- the same bits as
+        ``_als_init_host`` without the host RNG pass and the upload.  ``pending``: a draw started earlier with
+        ``launch_als_draw`` (so that it overlapped the upload of X)."""
+        k, g, N = self.k, self.g, self.N
+        ns = self.X.n_global
+        buf, done = pending if pending is not None else launch_als_draw(self.device, ns, g, k, seed, h_stream)
+        torch.cuda.current_stream(self.device).wait_event(done)
+        n_wv = (N + 1) * k * g
+        self.Wt.copy_(buf[:k * g].view(k, g).t())
+        for i in range(N):
+            self.Vt[i].copy_(buf[(i + 1) * k * g:(i + 2) * k * g].view(k, g).t())
+        off = n_wv
+        for i, n in enumerate(ns):
+            lo, hi = self.X.own[i]
+            b0, b1 = int(self.X.own_off[i]), int(self.X.own_off[i + 1])
+            if b1 > b0:
+                self.H[b0:b1, :k].copy_(buf[off + lo * k:off + hi * k].view(hi - lo, k))
+            off += n * k
+        buf.record_stream(torch.cuda.current_stream(self.device))
+        self.h2d_state_bytes = 0
 
     def initial_objective(self):
         """obj0 of _iNMF_ANLS.py:122-129 from the H currently in self.H (one statistics pass)."""

@@ -17,12 +17,11 @@ Keyword-only extensions (defaults preserve reference behaviour):
 Multi-GPU: when torch.distributed is initialised the cells are sharded over the ranks and the k x k
 and genes x k statistics are all-reduced once per iteration.
 """
-import threading
 
 import numpy as np
 from tqdm import tqdm
 
-from ..engine import InmfEngine, resolve_dtype
+from ..engine import InmfEngine, launch_als_draw, require_cuda, resolve_dtype
 
 
 def _als_init_host(ns, num_genes, k, seed, h_stream=None):
@@ -71,41 +70,35 @@ def optimize_ALS(
         raise ValueError(
             "Select k lower than the number of variable genes: {}".format(len(liger_object.var_genes)))
 
-    # The first repetition's host-side init (numpy's legacy RNG, for identical streams) is drawn on a
-    # worker thread while the main thread uploads X and builds the device formats.
+    # The first repetition's seeded init (numpy's legacy RNG stream, reproduced on the device) is generated
+    # on a side stream while the main thread uploads X and builds the device formats.
     import torch.distributed as _dist
     _rank = _dist.get_rank() if (_dist.is_available() and _dist.is_initialized()) else 0
     _world = _dist.get_world_size() if (_dist.is_available() and _dist.is_initialized()) else 1
     h_stream = _rank if (presharded and _world > 1) else None
-    first_init = {}
-
-    def _draw_first():
-        first_init["v"] = _als_init_host(ns, num_genes, k, rand_seed - 1, h_stream=h_stream)
-
-    worker = threading.Thread(target=_draw_first)
-    worker.start()
-    try:
-        if tensor_core not in (None, "tf32x3", "tf32"):
-            raise ValueError("tensor_core must be None, 'tf32x3' or 'tf32'")
-        engine = InmfEngine(X, k, value_lambda, dtype=resolve_dtype(dtype), device=device, presharded=presharded,
-                            use_tc=tensor_core is not None, tc_three_pass=tensor_core != "tf32")
-    finally:
-        worker.join()
+    if tensor_core not in (None, "tf32x3", "tf32"):
+        raise ValueError("tensor_core must be None, 'tf32x3' or 'tf32'")
+    user_init = not (W_init is None and V_init is None and H_init is None)
+    pending = None
+    if not user_init:  # the first seeded draw runs on one SM while X is uploaded and laid out
+        pending = launch_als_draw(require_cuda(device), ns, num_genes, k, rand_seed - 1, h_stream)
+    engine = InmfEngine(X, k, value_lambda, dtype=resolve_dtype(dtype), device=device, presharded=presharded,
+                        use_tc=tensor_core is not None, tc_three_pass=tensor_core != "tf32")
     best_obj = np.inf
     best = None
     info = {"objectives": [], "bpp": None, "iters_run": [], "h2d_bytes": engine.X.h2d_bytes}
     for j in range(nrep):
-        if j == 0:
-            W, V, H = first_init["v"]
+        if not user_init:  # the seeded draw, generated on the device (same bits as numpy's stream)
+            engine.draw_als_state(rand_seed + j - 1, h_stream=h_stream, pending=pending if j == 0 else None)
         else:
             W, V, H = _als_init_host(ns, num_genes, k, rand_seed + j - 1, h_stream=h_stream)
-        if W_init is not None:
-            W = W_init
-        if V_init is not None:
-            V = V_init
-        if H_init is not None:
-            H = H_init
-        engine.set_als_state(W, V, H)
+            if W_init is not None:
+                W = W_init
+            if V_init is not None:
+                V = V_init
+            if H_init is not None:
+                H = H_init
+            engine.set_als_state(W, V, H)
         info["h2d_bytes"] += engine.h2d_state_bytes
         delta = 1
         obj0 = engine.initial_objective()

@@ -240,3 +240,14 @@ def test_als_with_tensor_core_passes(dev):
     rel = np.abs(np.array(info["objectives"][0]) - want["objectives"]) / np.array(want["objectives"])
     assert rel.max() < 1e-3
     assert relerr(lig.H[0], want["H"][0]) < 1e-2
+
+
+@pytest.mark.parametrize("seed,n", [(0, 1), (0, 311), (1, 312), (12345, 313), (4294967295, 1000003)])
+def test_device_mt19937_stream_is_numpys(dev, seed, n):
+    """inmf_mt19937_uniform == np.random.seed(seed); np.random.uniform(0, 2, n), bit for bit."""
+    from pyliger_b200 import _lib
+    out = torch.empty(n, dtype=torch.float64, device=dev)
+    _lib.call("inmf_mt19937_uniform", "", seed, n, 2.0, out, torch.cuda.current_stream().cuda_stream)
+    np.random.seed(seed)
+    ref = np.random.uniform(0, 2, n)
+    assert np.array_equal(out.cpu().numpy(), ref)
