@@ -234,6 +234,29 @@ int32_t inmf_select_scale_f64(const int64_t* rowptr, const int32_t* colidx, cons
                               const int32_t* colmap, const double* scaler, const int64_t* new_rowptr,
                               int32_t* new_colidx, double* new_vals, void* stream);
 
+/* Device builders of the two blocked copies of X that inmf_blocked_spmm_* streams (stable counting sorts of the CSR
+ * non-zeros; deterministic).  Call with fill = 0 (histogram), scan the counts into ptr, call with fill = 1.
+ * Format 1 (gene-blocked CSR, pass 1): seg1 = int64[nseg][4] {own_off, n_own, csr_row0, 0}; owned row i of the H
+ * buffer is CSR row csr_row0 + (i - own_off); key(s, b, local_row) = NB * own_off + b * n_own + local_row; gene block
+ * b = col / gbs; pairs = {(col - b * gbs) * row_bytes, value}.  fill = 0: cnt_or_ptr[key] += count (caller zeroes);
+ * fill = 1: cnt_or_ptr = ptr (exclusive scan of the counts, keys + 1 entries). */
+int32_t inmf_blockfmt1_f32(int32_t fill, const int64_t* rowptr, const int32_t* colidx, const float* vals,
+                           const int64_t* seg1, int32_t nseg, int64_t n_rows, int32_t NB, int32_t gbs,
+                           int32_t row_bytes, int64_t* cnt_or_ptr, void* pairs, void* stream);
+int32_t inmf_blockfmt1_f64(int32_t fill, const int64_t* rowptr, const int32_t* colidx, const double* vals,
+                           const int64_t* seg1, int32_t nseg, int64_t n_rows, int32_t NB, int32_t gbs,
+                           int32_t row_bytes, int64_t* cnt_or_ptr, void* pairs, void* stream);
+/* Format 2 (cell-blocked CSC, pass 2): blk2 = int64[nblocks][4] {csr_row0, rows, key_base, 0}; key = key_base + gene;
+ * pairs = {(row in block) * row_bytes, value}, cells increasing inside every gene list.  One CTA (W warps) per cell
+ * block with W * g uint16 counters in shared memory (W * g * 2 <= 200 KB); offs = uint16[nblocks][W][g] scratch that
+ * carries the per-warp offsets from the fill = 0 call (which writes cnt[key]) to the fill = 1 call (which reads ptr). */
+int32_t inmf_blockfmt2_f32(int32_t fill, const int64_t* rowptr, const int32_t* colidx, const float* vals,
+                           const int64_t* blk2, int32_t nblocks, int32_t g, int32_t row_bytes, int32_t W, int64_t* cnt,
+                           const int64_t* ptr, uint16_t* offs, void* pairs, void* stream);
+int32_t inmf_blockfmt2_f64(int32_t fill, const int64_t* rowptr, const int32_t* colidx, const double* vals,
+                           const int64_t* blk2, int32_t nblocks, int32_t g, int32_t row_bytes, int32_t W, int64_t* cnt,
+                           const int64_t* ptr, uint16_t* offs, void* pairs, void* stream);
+
 /* Seeded initial factors without a host round trip: out[i] = i-th value of
  *   np.random.seed(seed); np.random.uniform(0, scale, n)
  * (numpy's legacy MT19937 stream, bit-identical), the draw the reference initialises W, V_i, H_i with

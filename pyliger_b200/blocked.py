@@ -9,8 +9,70 @@ pass 2  "cell-blocked CSC":  pairs ordered by (dataset, cell block, gene, cell);
 import numpy as np
 import torch
 
+from . import _lib
+
 WORK_FIELDS = 8
 SMEM_BUDGET = 227 * 1024 - 128 - 2048
+USE_DEVICE_BUILD = True      # count / scan / fill kernels (csrc/blockfmt.cuh); False = generic torch sort path
+BUILD2_SMEM = 200 * 1024     # uint16 counters [W][genes] of the format-2 builder
+
+
+def _sfx(vals):
+    return "f32" if vals.dtype == torch.float32 else "f64"
+
+
+def _stream(dev):
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def _empty_pairs(nnz, vals):
+    return torch.empty(nnz, 2, dtype=torch.int32 if vals.dtype == torch.float32 else torch.int64, device=vals.device)
+
+
+def _device_format1(X, kp, esize, NB, gbs):
+    """ptr, pairs of the gene-blocked CSR over the owned rows through inmf_blockfmt1_* (same arrays as the sort path)."""
+    dev = X.rowptr.device
+    seg1 = [[int(X.own_off[s]), X.n_own[s], int(X.row_base[s]) + (X.own[s][0] - X.bounds[s][0]), 0]
+            for s in range(X.N)]
+    seg1_t = torch.tensor(seg1, dtype=torch.int64, device=dev)
+    n_tot = X.n_own_total
+    ptr = torch.zeros(NB * n_tot + 1, dtype=torch.int64, device=dev)
+    sfx = _sfx(X.vals)
+    _lib.call("inmf_blockfmt1", sfx, 0, X.rowptr, X.colidx, X.vals, seg1_t, X.N, n_tot, NB, gbs, kp * esize,
+              ptr[1:], None, _stream(dev))
+    torch.cumsum(ptr[1:], 0, out=ptr[1:])
+    pairs = _empty_pairs(int(ptr[-1].item()), X.vals)
+    _lib.call("inmf_blockfmt1", sfx, 1, X.rowptr, X.colidx, X.vals, seg1_t, X.N, n_tot, NB, gbs, kp * esize,
+              ptr, pairs, _stream(dev))
+    return ptr, pairs
+
+
+def _device_format2(X, kp, esize, nb, cbs, blk_off):
+    """ptr, pairs of the cell-blocked CSC through inmf_blockfmt2_*; None if the gene counters do not fit."""
+    dev = X.rowptr.device
+    g = X.g
+    W = min(16, BUILD2_SMEM // (2 * g))
+    if W < 1 or max(cbs) > 60000 * W:
+        return None
+    blk2 = []
+    for s in range(X.N):
+        r0 = int(X.row_base[s]) + (X.own[s][0] - X.bounds[s][0])
+        for b in range(nb[s]):
+            blk2.append([r0 + b * cbs[s], min(cbs[s], X.n_own[s] - b * cbs[s]), g * (int(blk_off[s]) + b), 0])
+    total_blocks = len(blk2)
+    ptr = torch.zeros(g * total_blocks + 1, dtype=torch.int64, device=dev)
+    if total_blocks == 0:
+        return ptr, _empty_pairs(0, X.vals)
+    blk2_t = torch.tensor(blk2, dtype=torch.int64, device=dev)
+    offs = torch.empty(total_blocks * W * g, dtype=torch.int16, device=dev)
+    sfx = _sfx(X.vals)
+    _lib.call("inmf_blockfmt2", sfx, 0, X.rowptr, X.colidx, X.vals, blk2_t, total_blocks, g, kp * esize, W,
+              ptr[1:], None, offs, None, _stream(dev))
+    torch.cumsum(ptr[1:], 0, out=ptr[1:])
+    pairs = _empty_pairs(int(ptr[-1].item()), X.vals)
+    _lib.call("inmf_blockfmt2", sfx, 1, X.rowptr, X.colidx, X.vals, blk2_t, total_blocks, g, kp * esize, W,
+              None, ptr, offs, pairs, _stream(dev))
+    return ptr, pairs
 
 
 def tile_cap_rows(kp, esize):
@@ -63,22 +125,25 @@ def build_pass1(X, kp, esize, n_sms):
     cap = tile_cap_rows(kp, esize)
     NB = max(1, -(-g // cap))
     gbs = -(-g // NB)
-    own_row, col, val = _own_nnz(X)
-    own_off = torch.from_numpy(np.asarray(X.own_off, dtype=np.int64)).to(dev)
-    n_own = torch.from_numpy(np.asarray(X.n_own, dtype=np.int64)).to(dev)
-    seg = torch.bucketize(own_row, own_off[1:], right=True)
-    gb = (col.to(torch.int64) // gbs)
-    local_row = own_row - own_off[seg]
-    cidx = NB * own_off[seg] + gb * n_own[seg] + local_row
-    order = torch.sort(cidx, stable=True)[1]
-    n_tot = X.n_own_total
-    ptr = torch.zeros(NB * n_tot + 1, dtype=torch.int64, device=dev)
-    if cidx.numel():
-        ptr[1:] = torch.cumsum(torch.bincount(cidx, minlength=NB * n_tot), 0)
-    idx_local = (col.to(torch.int64) - gb * gbs)[order]
     bp = BlockedPass()
-    bp.pairs = _pack_pairs(idx_local * (kp * esize), val[order])  # byte offset of the gathered tile row
-    bp.ptr = ptr
+    if USE_DEVICE_BUILD and dev.type == "cuda" and X.n_own_total > 0:
+        bp.ptr, bp.pairs = _device_format1(X, kp, esize, NB, gbs)
+    else:
+        own_row, col, val = _own_nnz(X)
+        own_off = torch.from_numpy(np.asarray(X.own_off, dtype=np.int64)).to(dev)
+        n_own = torch.from_numpy(np.asarray(X.n_own, dtype=np.int64)).to(dev)
+        seg = torch.bucketize(own_row, own_off[1:], right=True)
+        gb = (col.to(torch.int64) // gbs)
+        local_row = own_row - own_off[seg]
+        cidx = NB * own_off[seg] + gb * n_own[seg] + local_row
+        order = torch.sort(cidx, stable=True)[1]
+        n_tot = X.n_own_total
+        ptr = torch.zeros(NB * n_tot + 1, dtype=torch.int64, device=dev)
+        if cidx.numel():
+            ptr[1:] = torch.cumsum(torch.bincount(cidx, minlength=NB * n_tot), 0)
+        idx_local = (col.to(torch.int64) - gb * gbs)[order]
+        bp.pairs = _pack_pairs(idx_local * (kp * esize), val[order])  # byte offset of the gathered tile row
+        bp.ptr = ptr
     chunks = max(1, n_sms // max(1, N * NB))
     work = []
     for s in range(N):
@@ -110,22 +175,28 @@ def build_pass2(X, kp, esize, n_sms):
     nb = [0 if n == 0 else -(-n // c) for n, c in zip(X.n_own, cbs)]
     blk_off = np.concatenate([[0], np.cumsum(nb)]).astype(np.int64)
     total_blocks = int(blk_off[-1])
-    own_row, col, val = _own_nnz(X)
-    own_off = torch.from_numpy(np.asarray(X.own_off, dtype=np.int64)).to(dev)
-    seg = torch.bucketize(own_row, own_off[1:], right=True)
-    local_row = own_row - own_off[seg]
-    cbs_t = torch.tensor(cbs, dtype=torch.int64, device=dev)
-    blk_off_t = torch.from_numpy(blk_off).to(dev)
-    cb = local_row // cbs_t[seg]
-    cidx = (blk_off_t[seg] + cb) * g + col.to(torch.int64)
-    order = torch.sort(cidx, stable=True)[1]
-    ptr = torch.zeros(g * total_blocks + 1, dtype=torch.int64, device=dev)
-    if cidx.numel():
-        ptr[1:] = torch.cumsum(torch.bincount(cidx, minlength=g * total_blocks), 0)
-    idx_local = (local_row - cb * cbs_t[seg])[order]
     bp = BlockedPass()
-    bp.pairs = _pack_pairs(idx_local * (kp * esize), val[order])  # byte offset of the gathered tile row
-    bp.ptr = ptr
+    built = None
+    if USE_DEVICE_BUILD and dev.type == "cuda" and X.n_own_total > 0:
+        built = _device_format2(X, kp, esize, nb, cbs, blk_off)
+    if built is not None:
+        bp.ptr, bp.pairs = built
+    else:
+        own_row, col, val = _own_nnz(X)
+        own_off = torch.from_numpy(np.asarray(X.own_off, dtype=np.int64)).to(dev)
+        seg = torch.bucketize(own_row, own_off[1:], right=True)
+        local_row = own_row - own_off[seg]
+        cbs_t = torch.tensor(cbs, dtype=torch.int64, device=dev)
+        blk_off_t = torch.from_numpy(blk_off).to(dev)
+        cb = local_row // cbs_t[seg]
+        cidx = (blk_off_t[seg] + cb) * g + col.to(torch.int64)
+        order = torch.sort(cidx, stable=True)[1]
+        ptr = torch.zeros(g * total_blocks + 1, dtype=torch.int64, device=dev)
+        if cidx.numel():
+            ptr[1:] = torch.cumsum(torch.bincount(cidx, minlength=g * total_blocks), 0)
+        idx_local = (local_row - cb * cbs_t[seg])[order]
+        bp.pairs = _pack_pairs(idx_local * (kp * esize), val[order])  # byte offset of the gathered tile row
+        bp.ptr = ptr
     chunks = max(1, n_sms // max(1, total_blocks))
     per = -(-g // chunks)
     work = []

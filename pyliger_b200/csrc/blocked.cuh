@@ -28,6 +28,7 @@ struct PairTraits<float> {
     typedef int2 Pair;
     static constexpr int VEC = 4;
     __device__ static __forceinline__ Pair zero() { return make_int2(0, 0); }
+    __device__ static __forceinline__ int bits(float v) { return __float_as_int(v); }
     __device__ static __forceinline__ Pair ld(const Pair* p) {
         int2 r;
         asm volatile("ld.global.nc.L1::no_allocate.v2.s32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
@@ -51,6 +52,7 @@ struct PairTraits<double> {
     typedef longlong2 Pair;
     static constexpr int VEC = 2;
     __device__ static __forceinline__ Pair zero() { return make_longlong2(0, 0); }
+    __device__ static __forceinline__ long long bits(double v) { return __double_as_longlong(v); }
     __device__ static __forceinline__ Pair ld(const Pair* p) {
         longlong2 r;
         asm volatile("ld.global.nc.L1::no_allocate.v2.s64 {%0, %1}, [%2];" : "=l"(r.x), "=l"(r.y) : "l"(p));

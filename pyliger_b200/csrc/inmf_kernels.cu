@@ -1363,3 +1363,79 @@ extern "C" int32_t inmf_mt19937_uniform(uint32_t seed, int64_t n, double scale, 
     INMF_LAUNCH_CHECK();
     return 0;
 }
+
+// =================================================================================================
+// Device builders of the blocked copies of X (count / fill around a scan done by the caller)
+// =================================================================================================
+#include "blockfmt.cuh"
+
+template <typename T>
+static int32_t blockfmt1_launch(int32_t fill, const int64_t* rowptr, const int32_t* colidx, const T* vals,
+                                const int64_t* seg1, int32_t nseg, int64_t n_rows, int32_t NB, int32_t gbs,
+                                int32_t row_bytes, int64_t* cnt_or_ptr, void* pairs, void* stream) {
+    INMF_REQUIRE(nseg >= 1 && NB >= 1 && gbs >= 1 && row_bytes >= 1, "bad format-1 geometry");
+    if (n_rows <= 0) return 0;
+    typedef typename PairTraits<T>::Pair Pair;
+    if (fill)
+        blockfmt1_kernel<true, T><<<rows_grid(n_rows), 256, 0, (cudaStream_t)stream>>>(
+            rowptr, colidx, vals, seg1, nseg, n_rows, NB, gbs, row_bytes, cnt_or_ptr, (Pair*)pairs);
+    else
+        blockfmt1_kernel<false, T><<<rows_grid(n_rows), 256, 0, (cudaStream_t)stream>>>(
+            rowptr, colidx, vals, seg1, nseg, n_rows, NB, gbs, row_bytes, cnt_or_ptr, (Pair*)pairs);
+    INMF_LAUNCH_CHECK();
+    return 0;
+}
+extern "C" int32_t inmf_blockfmt1_f32(int32_t fill, const int64_t* rowptr, const int32_t* colidx, const float* vals,
+                                      const int64_t* seg1, int32_t nseg, int64_t n_rows, int32_t NB, int32_t gbs,
+                                      int32_t row_bytes, int64_t* cnt_or_ptr, void* pairs, void* stream) {
+    return blockfmt1_launch<float>(fill, rowptr, colidx, vals, seg1, nseg, n_rows, NB, gbs, row_bytes, cnt_or_ptr,
+                                   pairs, stream);
+}
+extern "C" int32_t inmf_blockfmt1_f64(int32_t fill, const int64_t* rowptr, const int32_t* colidx, const double* vals,
+                                      const int64_t* seg1, int32_t nseg, int64_t n_rows, int32_t NB, int32_t gbs,
+                                      int32_t row_bytes, int64_t* cnt_or_ptr, void* pairs, void* stream) {
+    return blockfmt1_launch<double>(fill, rowptr, colidx, vals, seg1, nseg, n_rows, NB, gbs, row_bytes, cnt_or_ptr,
+                                    pairs, stream);
+}
+
+template <typename T>
+static int32_t blockfmt2_launch(int32_t fill, const int64_t* rowptr, const int32_t* colidx, const T* vals,
+                                const int64_t* blk2, int32_t nblocks, int32_t g, int32_t row_bytes, int32_t W,
+                                int64_t* cnt, const int64_t* ptr, uint16_t* offs, void* pairs, void* stream) {
+    INMF_REQUIRE(g >= 1 && row_bytes >= 1 && W >= 1 && W <= 32, "bad format-2 geometry");
+    const size_t smem = (size_t)W * g * sizeof(uint16_t);
+    INMF_REQUIRE(smem <= 200 * 1024, "format-2 builder: W * genes counters exceed shared memory");
+    if (nblocks <= 0) return 0;
+    typedef typename PairTraits<T>::Pair Pair;
+    static bool attr_done[2][2] = {{false, false}, {false, false}};
+    const int ti = sizeof(T) == 8;
+    if (!attr_done[ti][fill != 0]) {
+        if (fill)
+            INMF_CUDA_CHECK(cudaFuncSetAttribute(blockfmt2_kernel<true, T>,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        else
+            INMF_CUDA_CHECK(cudaFuncSetAttribute(blockfmt2_kernel<false, T>,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_done[ti][fill != 0] = true;
+    }
+    if (fill)
+        blockfmt2_kernel<true, T><<<(unsigned)nblocks, W * 32, smem, (cudaStream_t)stream>>>(
+            rowptr, colidx, vals, blk2, g, row_bytes, cnt, ptr, offs, (Pair*)pairs);
+    else
+        blockfmt2_kernel<false, T><<<(unsigned)nblocks, W * 32, smem, (cudaStream_t)stream>>>(
+            rowptr, colidx, vals, blk2, g, row_bytes, cnt, ptr, offs, (Pair*)pairs);
+    INMF_LAUNCH_CHECK();
+    return 0;
+}
+extern "C" int32_t inmf_blockfmt2_f32(int32_t fill, const int64_t* rowptr, const int32_t* colidx, const float* vals,
+                                      const int64_t* blk2, int32_t nblocks, int32_t g, int32_t row_bytes, int32_t W,
+                                      int64_t* cnt, const int64_t* ptr, uint16_t* offs, void* pairs, void* stream) {
+    return blockfmt2_launch<float>(fill, rowptr, colidx, vals, blk2, nblocks, g, row_bytes, W, cnt, ptr, offs, pairs,
+                                   stream);
+}
+extern "C" int32_t inmf_blockfmt2_f64(int32_t fill, const int64_t* rowptr, const int32_t* colidx, const double* vals,
+                                      const int64_t* blk2, int32_t nblocks, int32_t g, int32_t row_bytes, int32_t W,
+                                      int64_t* cnt, const int64_t* ptr, uint16_t* offs, void* pairs, void* stream) {
+    return blockfmt2_launch<double>(fill, rowptr, colidx, vals, blk2, nblocks, g, row_bytes, W, cnt, ptr, offs, pairs,
+                                    stream);
+}

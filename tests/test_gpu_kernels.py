@@ -251,3 +251,37 @@ def test_device_mt19937_stream_is_numpys(dev, seed, n):
     np.random.seed(seed)
     ref = np.random.uniform(0, 2, n)
     assert np.array_equal(out.cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize("world,rank,replicate", [(1, 0, False), (3, 1, False), (2, 1, True)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_device_format_builders_equal_sort_path(dev, dtype, world, rank, replicate):
+    """inmf_blockfmt1/2 (count / scan / fill) produce exactly the arrays of the generic stable-sort path,
+    including rows that are empty and a matrix with duplicate (unsummed) column entries."""
+    from pyliger_b200 import blocked
+    from pyliger_b200.engine import DeviceCSR
+    rng = np.random.default_rng(17)
+    g, kp = 523, 12
+    mats = [sps.random(n, g, density=0.12, random_state=40 + i, format="csr") for i, n in enumerate((2011, 640, 3))]
+    dup = sps.random(300, g, density=0.1, random_state=7, format="coo")
+    dup = sps.csr_matrix((np.r_[dup.data, dup.data[:500]], (np.r_[dup.row, dup.row[:500]], np.r_[dup.col, dup.col[:500]])),
+                         shape=dup.shape)
+    dup_raw = sps.csr_matrix((dup.data, dup.indices, dup.indptr), shape=dup.shape)
+    mats.append(dup_raw)
+    mats[0] = sps.csr_matrix(mats[0].multiply(rng.uniform(size=(2011, 1)) > 0.1))  # some empty cells
+    X = DeviceCSR(mats, dtype, dev, rank, world, replicate=replicate)
+    esize = 4 if dtype == torch.float32 else 8
+    old = blocked.SMEM_BUDGET
+    blocked.SMEM_BUDGET = 200 * kp * esize  # several gene / cell blocks
+    try:
+        out = {}
+        for flag in (True, False):
+            blocked.USE_DEVICE_BUILD = flag
+            out[flag] = (blocked.build_pass1(X, kp, esize, 148), blocked.build_pass2(X, kp, esize, 148))
+    finally:
+        blocked.SMEM_BUDGET = old
+        blocked.USE_DEVICE_BUILD = True
+    for a, b in zip(out[True], out[False]):
+        assert torch.equal(a.ptr, b.ptr)
+        assert a.pairs.shape == b.pairs.shape and torch.equal(a.pairs, b.pairs)
+        assert torch.equal(a.work, b.work) and a.max_tile_rows == b.max_tile_rows
