@@ -448,6 +448,14 @@ class InmfEngine(object):
     def host_V(self):
         return [self.Vt[i].to(torch.float64).cpu().numpy() for i in range(self.N)]
 
+    def host_factors(self):
+        """(H list, W, V list) as host float64 arrays -- one staged download when no gather is needed."""
+        if self.world > 1 and not self.X.presharded:
+            return self.gather_H(), self.host_W(), self.host_V()
+        hs = [self.H[int(self.X.own_off[i]):int(self.X.own_off[i + 1]), :self.k] for i in range(self.N)]
+        outs = staging.to_host_f64(self.device, hs + [self.Wt] + [self.Vt[i] for i in range(self.N)])
+        return outs[:self.N], outs[self.N], outs[self.N + 1:]
+
     def bpp_report(self):
         s = self.bpp_stats.cpu().numpy()
         names = ("not_converged", "factorizations", "backup_flips", "pivot_failures", "rounds_sum",

@@ -19,6 +19,7 @@ and genes x k statistics are all-reduced once per iteration (SURVEY.md section 8
 """
 
 import numpy as np
+import torch
 from tqdm import tqdm
 
 from ..engine import InmfEngine, launch_als_draw, require_cuda, resolve_dtype
@@ -118,8 +119,9 @@ def optimize_ALS(
         info["iters_run"].append(iters_run)
         info["d2h_bytes"] = info.get("d2h_bytes", 0) + 8 * len(objs)
         if obj0 < best_obj:
-            best = (engine.gather_H(), engine.host_W(), engine.host_V())
-            info["d2h_bytes"] += sum(h.nbytes for h in best[0]) + best[1].nbytes + sum(v.nbytes for v in best[2])
+            best = engine.host_factors()
+            esz = 4 if engine.dtype == torch.float32 else 8  # the factors cross the bus in the compute dtype
+            info["d2h_bytes"] += esz * (sum(h.size for h in best[0]) + best[1].size + sum(v.size for v in best[2]))
             best_obj = obj0
         if print_obj:
             print("Objective: {}".format(best_obj))

@@ -44,6 +44,41 @@ class _Stager(object):
             if ev is not None:
                 ev.synchronize()
 
+    def _down_worker(self, b, chunks):
+        buf = self.bufs[b]
+        with torch.cuda.device(self.device):
+            for dst, src in chunks[b::NBUF]:
+                view = buf[:src.numel() * src.element_size()].view(src.dtype)
+                with torch.cuda.stream(self.stream):
+                    view.copy_(src, non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(self.stream)
+                ev.synchronize()
+                np.copyto(dst, view.numpy(), casting="unsafe")  # widens float32 -> float64 on the host side
+
+    def download(self, jobs):
+        """jobs: [(dst 1-D numpy array, src 1-D contiguous device tensor of the same length)]. Returns bytes."""
+        chunks = []
+        got = 0
+        for dst, src in jobs:
+            n = src.numel()
+            if n == 0:
+                continue
+            if dst.shape[0] != n:
+                raise ValueError("staged download: length mismatch")
+            per = CHUNK_BYTES // src.element_size()
+            for o in range(0, n, per):
+                chunks.append((dst[o:o + per], src[o:o + per]))
+            got += n * src.element_size()
+        if not chunks:
+            return 0
+        with self.busy:
+            self.stream.wait_stream(torch.cuda.current_stream(self.device))
+            futs = [self.pool.submit(self._down_worker, b, chunks) for b in range(min(NBUF, len(chunks)))]
+            for f in futs:
+                f.result()
+        return got
+
     def upload(self, jobs):
         """jobs: [(dst 1-D device tensor, src 1-D numpy array of the same length)]. Returns the bytes sent."""
         chunks = []
@@ -69,10 +104,31 @@ class _Stager(object):
         return sent
 
 
-def upload(device, jobs):
+def _get(device):
     device = torch.device(device)
     with _lock:
         st = _stagers.get(device)
         if st is None:
             st = _stagers[device] = _Stager(device)
-    return st.upload(jobs)
+    return st
+
+
+def upload(device, jobs):
+    return _get(device).upload(jobs)
+
+
+def download(device, jobs):
+    return _get(device).download(jobs)
+
+
+def to_host_f64(device, tensors):
+    """Device tensors (any float dtype, any strides) -> new host float64 arrays of the same shapes, in one
+    overlapped staged download (the narrow dtype crosses the bus; widening happens on the host)."""
+    outs, jobs = [], []
+    for t in tensors:
+        flat = t.contiguous().view(-1)
+        out = np.empty(tuple(t.shape), dtype=np.float64)
+        outs.append(out)
+        jobs.append((out.reshape(-1), flat))
+    download(device, jobs)
+    return outs
