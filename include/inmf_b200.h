@@ -52,13 +52,17 @@ int64_t inmf_launch_count(void);
  *   R        T, column c at R + c*ldr (k contiguous values of AtB[:, c])
  *   X        T out, column c at X + c*ldx (X may alias R: in-place solve)
  *   Y        T out or NULL (G x - r, zero on the passive set)
- *   mask     uint64 per column or NULL: final passive set; if warm != 0 it is also the start set
+ *   mask     uint64 per column or NULL: final passive set; if (warm & 1) it is also the start set
  *            (the reference's `init` argument, _utilities.py:222-225)
+ *   warm     bit 0: warm start from mask; bit 1 (needs ginv_ws): solve a partition on its active-set
+ *            complement through G^-1 whenever that is the smaller system (same solution; meant for
+ *            well-conditioned G such as the H-update's, whose solutions are mostly passive)
  *   seg_off  device int64[nseg+1] column ranges;  max_seg_cols = max segment length (host value)
  *   stats    device int64[INMF_BPP_NSTATS], accumulated (caller zeroes)
  *   ginv_ws  device double[nseg][k][k] workspace or NULL.  If given, G^-1 is formed per segment first
  *            and the "all indices passive" solves (the first round of every cold start on non-negative
- *            right-hand sides) become one k x k mat-vec; the result is the same NNLS solution.
+ *            right-hand sides) become one k x k mat-vec, and passive sets larger than 31 (k > 31) are
+ *            solved on the complement; the result is the same NNLS solution.
  */
 int32_t inmf_bpp_f32(const double* G, const float* R, int64_t ldr, float* X, int64_t ldx, float* Y,
                      int64_t ldy, uint64_t* mask, int32_t warm, const int64_t* seg_off, int32_t nseg,

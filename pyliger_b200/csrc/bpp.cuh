@@ -239,13 +239,18 @@ __device__ __forceinline__ void bpp_unconstrained(const T* __restrict__ Gis, int
 //   With x = G^-1 (r + y), y_P = 0, x_F = 0:   (G^-1)_FF y_F = -xfull_F,   x_P = xfull_P + (G^-1)_PF y_F.
 //   That is the same routine on M = G^-1, S = F, q = xfull: it returns u = -y_F on F and (M u - q) = -x_P on P.
 // otherwise: general path.
-// COMP = false (instantiated for k <= 31, where |P| <= 31 always) compiles the complement path away.
+// `prefer`: take the complement whenever it is the smaller system (|F| < |P|) -- for well-conditioned G (the
+// H-update's (W+V)(W+V)' + lambda VV') with mostly-passive solutions this replaces a |P| ~ 0.8k factorisation by
+// a |F| ~ 0.2k one.
+// COMP = false (k <= 31 without `prefer`, where |P| <= 31 always) compiles the complement path away.
 template <typename T, bool COMP>
 __device__ __forceinline__ void bpp_solve_passive(const T* __restrict__ Gs, const T* __restrict__ Gis, int ldg,
-                                                  BppWarpScratch<T>& sc, int k, uint64_t kmask, uint64_t P, T r0,
-                                                  T r1, T& x0, T& x1, T& y0, T& y1, BppCounters& cnt) {
+                                                  BppWarpScratch<T>& sc, int k, uint64_t kmask, uint64_t P,
+                                                  bool prefer, T r0, T r1, T& x0, T& x1, T& y0, T& y1,
+                                                  BppCounters& cnt) {
     const int p = __popcll(P);
-    const bool comp = COMP && Gis != nullptr && p > BPP_FAST_MAX_P && k - p <= BPP_FAST_MAX_P;
+    const bool comp = COMP && Gis != nullptr && k - p <= BPP_FAST_MAX_P &&
+                      (p > BPP_FAST_MAX_P || (prefer && k - p < p));
     if (!COMP || p <= BPP_FAST_MAX_P || comp) {  // !COMP: k <= 31, so is p
         T u0, u1, v0, v1;
         if (comp) {
@@ -269,8 +274,8 @@ __device__ __forceinline__ void bpp_solve_passive(const T* __restrict__ Gs, cons
 template <typename T, bool COMP>
 __device__ __forceinline__ void bpp_column(const T* __restrict__ Gs, const T* __restrict__ Gis, int ldg,
                                            BppWarpScratch<T>& sc, int k,
-                                           T r0, T r1, uint64_t& P, bool warm, T& x0, T& x1, T& y0, T& y1,
-                                           BppCounters& cnt) {
+                                           T r0, T r1, uint64_t& P, bool warm, bool prefer, T& x0, T& x1, T& y0,
+                                           T& y1, BppCounters& cnt) {
     const int lane = threadIdx.x & 31;
     const bool has0 = lane < k, has1 = lane + 32 < k;
     const uint64_t kmask = (k >= 64) ? ~0ull : ((1ull << k) - 1ull);
@@ -285,7 +290,8 @@ __device__ __forceinline__ void bpp_column(const T* __restrict__ Gs, const T* __
     bool have_xf = false;  // sc.xf = G^-1 r, formed the first time a partition with |P| > 31 comes up
     while (true) {
         // evaluate the current partition (single call site keeps the unrolled solver in one copy)
-        if (Gis != nullptr && !have_xf && (P == kmask || (COMP && __popcll(P) > BPP_FAST_MAX_P))) {
+        if (Gis != nullptr && !have_xf &&
+            (P == kmask || (COMP && (__popcll(P) > BPP_FAST_MAX_P || (prefer && 2 * __popcll(P) > k))))) {
             bpp_unconstrained<T>(Gis, ldg, sc, k);
             have_xf = true;
         }
@@ -300,7 +306,7 @@ __device__ __forceinline__ void bpp_column(const T* __restrict__ Gs, const T* __
             y1 = T(0);
             cnt.nfact++;
         } else if (P != 0ull) {
-            bpp_solve_passive<T, COMP>(Gs, Gis, ldg, sc, k, kmask, P, r0, r1, x0, x1, y0, y1, cnt);
+            bpp_solve_passive<T, COMP>(Gs, Gis, ldg, sc, k, kmask, P, prefer, r0, r1, x0, x1, y0, y1, cnt);
         } else {
             x0 = T(0);
             x1 = T(0);

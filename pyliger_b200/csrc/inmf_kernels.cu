@@ -96,10 +96,10 @@ __global__ void __launch_bounds__(BPP_THREADS, COMP ? BPP_MIN_BLOCKS - 1 : BPP_M
         const T* r = R + col * ldr;
         const T r0 = (lane < k) ? r[lane] : T(0);
         const T r1 = (lane + 32 < k) ? r[lane + 32] : T(0);
-        uint64_t P = (warm && mask) ? mask[col] : 0ull;
+        uint64_t P = ((warm & 1) && mask) ? mask[col] : 0ull;
         T x0, x1, y0, y1;
         BppCounters cnt = {0, 0, 0, 0, true, {0, 0, 0, 0, 0, 0}};
-        bpp_column<T, COMP>(Gs, Gis, ldg, sc, k, r0, r1, P, warm != 0, x0, x1, y0, y1, cnt);
+        bpp_column<T, COMP>(Gs, Gis, ldg, sc, k, r0, r1, P, (warm & 1) != 0, (warm & 2) != 0, x0, x1, y0, y1, cnt);
         T* x = X + col * ldx;
         if (lane < k) x[lane] = x0;
         if (lane + 32 < k) x[lane + 32] = x1;
@@ -171,7 +171,7 @@ static int32_t bpp_launch(const double* G, const T* R, int64_t ldr, T* X, int64_
         INMF_LAUNCH_CHECK();
     }
     dim3 grid((unsigned)blocks, (unsigned)nseg);
-    if (k > BPP_FAST_MAX_P)  // passive sets beyond the register solver exist: build with the complement path
+    if (k > BPP_FAST_MAX_P || ((warm & 2) && ginv_ws != nullptr))  // complement path needed / asked for
         bpp_kernel<T, true><<<grid, nwarps * 32, smem, (cudaStream_t)stream>>>(
             G, ginv_ws, R, ldr, X, ldx, Y, ldy, mask, warm, seg_off, k, (long long*)stats);
     else

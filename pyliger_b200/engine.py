@@ -315,8 +315,9 @@ class InmfEngine(object):
         if max_rows <= 0:
             return
         k = self.k
-        _lib.call("inmf_bpp", self.sfx, self.G, out, self.ldm, out, self.ldm, None, 0, mask, 1 if warm else 0,
-                  seg_off, nseg, max_rows, k, self.bpp_stats[0], self._ginv(warm), _stream())
+        # bit 1: G = (W+V)(W+V)' + lambda VV' is well conditioned and H is mostly passive -> complement solves
+        _lib.call("inmf_bpp", self.sfx, self.G, out, self.ldm, out, self.ldm, None, 0, mask, (1 if warm else 0) | 2,
+                  seg_off, nseg, max_rows, k, self.bpp_stats[0], self.ginv_ws, _stream())
 
     def solve_H(self, seg_desc=None, max_rows=None, out=None, mask=None, warm=False, nseg=None):
         """out[q,:] = argmin_{h>=0} for every row of the windows in seg_desc (default: all owned cells)."""
