@@ -23,19 +23,24 @@ extern "C" const char* inmf_last_error(void) { return g_inmf_err; }
 // =================================================================================================
 // In-place Gauss-Jordan inverse of every segment's SPD normal matrix (double, one CTA per segment).
 // Used for the "all indices passive" solve x = G^-1 r, which is what the first round of a cold start
-// always asks for when the right-hand sides are non-negative.  A non-positive pivot marks the inverse
-// invalid (NaN in element 0) and the solver falls back to the Cholesky paths.
-__global__ void ginv_kernel(const double* __restrict__ G, double* __restrict__ Ginv, int k) {
+// always asks for when the right-hand sides are non-negative.  A pivot that is non-positive or smaller than
+// rcond_min times the largest diagonal entry (the Gauss-Jordan pivots of an SPD matrix are its successive Schur
+// complements: a cheap conditioning proxy) marks the inverse invalid (NaN in element 0) and the solver falls
+// back to the Cholesky paths, whose accuracy depends on cond(G_PP) only.
+__global__ void ginv_kernel(const double* __restrict__ G, double* __restrict__ Ginv, int k, double rcond_min) {
     extern __shared__ double ginv_a[];
     __shared__ double f[INMF_MAX_K];
     const int seg = blockIdx.x;
     const int t = threadIdx.x, nt = blockDim.x;
     for (int e = t; e < k * k; e += nt) ginv_a[e] = G[(size_t)seg * k * k + e];
     bool ok = true;
+    __syncthreads();
+    double dmax = 0.0;
+    for (int p = 0; p < k; ++p) dmax = fmax(dmax, ginv_a[p * k + p]);
     for (int p = 0; p < k; ++p) {
         __syncthreads();
         const double piv = ginv_a[p * k + p];
-        if (!(piv > 0.0)) {
+        if (!(piv > rcond_min * dmax)) {
             ok = false;
             break;
         }
@@ -58,8 +63,11 @@ __global__ void ginv_kernel(const double* __restrict__ G, double* __restrict__ G
 }
 
 // COMP kernels (k > 31) are limited to <= 5 CTAs per SM by their shared-memory scratch anyway: give them the registers.
+#ifndef BPP_COMP_MIN_BLOCKS
+#define BPP_COMP_MIN_BLOCKS (BPP_MIN_BLOCKS - 1)
+#endif
 template <typename T, bool COMP>
-__global__ void __launch_bounds__(BPP_THREADS, COMP ? BPP_MIN_BLOCKS - 1 : BPP_MIN_BLOCKS) bpp_kernel(const double* __restrict__ G, const double* __restrict__ Ginv, const T* R, int64_t ldr, T* X, int64_t ldx,
+__global__ void __launch_bounds__(BPP_THREADS, COMP ? BPP_COMP_MIN_BLOCKS : BPP_MIN_BLOCKS) bpp_kernel(const double* __restrict__ G, const double* __restrict__ Ginv, const T* R, int64_t ldr, T* X, int64_t ldx,
                            T* __restrict__ Y, int64_t ldy, uint64_t* __restrict__ mask, int warm, const int64_t* __restrict__ seg_off, int k,
                            long long* __restrict__ stats) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -167,7 +175,10 @@ static int32_t bpp_launch(const double* G, const T* R, int64_t ldr, T* X, int64_
     const int64_t cap = (int64_t)inmf_num_sms() * 16;
     if (blocks > cap) blocks = cap;
     if (ginv_ws != nullptr) {
-        ginv_kernel<<<(unsigned)nseg, 256, (size_t)k * k * sizeof(double), (cudaStream_t)stream>>>(G, ginv_ws, k);
+        // the inverse is used in T arithmetic: accept it only while cond(G) * eps(T) stays small
+        const double rcond_min = sizeof(T) == 4 ? 1e-4 : 1e-10;
+        ginv_kernel<<<(unsigned)nseg, 256, (size_t)k * k * sizeof(double), (cudaStream_t)stream>>>(G, ginv_ws, k,
+                                                                                                rcond_min);
         INMF_LAUNCH_CHECK();
     }
     dim3 grid((unsigned)blocks, (unsigned)nseg);

@@ -421,3 +421,28 @@ def test_bpp_large_batch_properties():
     assert relerr(X2, X) < 1e-5 and info2[2] <= cols * 1.01         # already optimal: one solve per column
     X3, _ = nnlsm_blockpivot(G, 3.0 * R, is_input_prod=True, dtype="float32")
     assert relerr(X3, 3.0 * X) < 1e-4
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_als_with_nearly_dead_factor_falls_back_from_inverse(dtype):
+    """A factor whose loadings are ~1e-3 of the others (G_55 ~ 1e-6 of the rest) makes G of the H-update nearly singular: the G^-1 based
+    complement path must be refused (conditioning guard) and the Cholesky paths give the oracle's answer."""
+    from pyliger_b200 import liger_from_matrices, optimize_ALS
+    from pyliger_b200.synth import make_datasets
+    mats = make_datasets([700, 500], 260, 8, density=0.12, seed0=7100)
+    k = 8
+    rng = np.random.default_rng(3)
+    W0 = rng.uniform(0, 2, (k, 260)); W0[5] *= 1e-3
+    V0 = [rng.uniform(0, 2, (k, 260)) for _ in mats]
+    for v in V0:
+        v[5] *= 1e-3
+    H0 = [rng.uniform(0, 2, (m.shape[0], k)) for m in mats]
+    want = orc.als(mats, k, 5.0, 0.0, 2, W_init=W0.copy(), V_init=[v.copy() for v in V0],
+                   H_init=[h.copy() for h in H0])
+    lig = liger_from_matrices(mats)
+    info = optimize_ALS(lig, k, 5.0, 0.0, 2, W_init=W0.copy(), V_init=[v.copy() for v in V0],
+                        H_init=[h.copy() for h in H0], dtype=dtype, progress=False, return_info=True)
+    tol = 1e-9 if dtype == "float64" else 1e-3
+    got, ref = np.array(info["objectives"][0]), np.array(want["objectives"])
+    assert np.max(np.abs(got - ref) / ref) < tol
+    assert info["bpp"]["H"]["not_converged"] == 0
