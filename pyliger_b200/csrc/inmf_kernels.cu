@@ -27,39 +27,50 @@ extern "C" const char* inmf_last_error(void) { return g_inmf_err; }
 // rcond_min times the largest diagonal entry (the Gauss-Jordan pivots of an SPD matrix are its successive Schur
 // complements: a cheap conditioning proxy) marks the inverse invalid (NaN in element 0) and the solver falls
 // back to the Cholesky paths, whose accuracy depends on cond(G_PP) only.
-__global__ void ginv_kernel(const double* __restrict__ G, double* __restrict__ Ginv, int k, double rcond_min) {
+// Two barriers per elimination step: every thread first READS what its elements need from the unmodified matrix
+// (a[i][p], a[p][j], a[p][p]), then all write.  Up to 4 elements per thread (k*k <= 4096, 1024 threads).
+__global__ void __launch_bounds__(1024) ginv_kernel(const double* __restrict__ G, double* __restrict__ Ginv, int k,
+                                                    double rcond_min) {
     extern __shared__ double ginv_a[];
-    __shared__ double f[INMF_MAX_K];
     const int seg = blockIdx.x;
     const int t = threadIdx.x, nt = blockDim.x;
-    for (int e = t; e < k * k; e += nt) ginv_a[e] = G[(size_t)seg * k * k + e];
-    bool ok = true;
+    const int kk = k * k;
+    int ei[4], ej[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int e = t + u * nt;
+        ei[u] = e < kk ? e / k : -1;
+        ej[u] = e < kk ? e - (e / k) * k : 0;
+    }
+    for (int e = t; e < kk; e += nt) ginv_a[e] = G[(size_t)seg * kk + e];
     __syncthreads();
     double dmax = 0.0;
     for (int p = 0; p < k; ++p) dmax = fmax(dmax, ginv_a[p * k + p]);
+    const double floor_piv = rcond_min * dmax;
+    bool ok = true;
     for (int p = 0; p < k; ++p) {
-        __syncthreads();
-        const double piv = ginv_a[p * k + p];
-        if (!(piv > rcond_min * dmax)) {
+        const double piv = ginv_a[p * k + p];  // uniform: all threads see the same value, so the break is too
+        if (!(piv > floor_piv)) {
             ok = false;
             break;
         }
-        __syncthreads();
-        if (t < k) {
-            ginv_a[p * k + t] = ((t == p) ? 1.0 : ginv_a[p * k + t]) / piv;
-        } else if (t - k < k && t - k != p) {  // a second group of threads saves / clears column p
-            f[t - k] = ginv_a[(t - k) * k + p];
-            ginv_a[(t - k) * k + p] = 0.0;
+        const double rp = 1.0 / piv;
+        double nv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = ei[u], j = ej[u];
+            if (i < 0) continue;
+            const double prow = ((j == p) ? 1.0 : ginv_a[p * k + j]) * rp;
+            nv[u] = (i == p) ? prow : ((j == p) ? 0.0 : ginv_a[i * k + j]) - ginv_a[i * k + p] * prow;
         }
         __syncthreads();
-        for (int e = t; e < k * k; e += nt) {
-            const int i = e / k, j = e - i * k;
-            if (i != p) ginv_a[e] -= f[i] * ginv_a[p * k + j];
-        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (ei[u] >= 0) ginv_a[ei[u] * k + ej[u]] = nv[u];
+        __syncthreads();
     }
-    __syncthreads();
-    for (int e = t; e < k * k; e += nt)
-        Ginv[(size_t)seg * k * k + e] = ok ? ginv_a[e] : __longlong_as_double(0x7ff8000000000000ll);
+    for (int e = t; e < kk; e += nt)
+        Ginv[(size_t)seg * kk + e] = ok ? ginv_a[e] : __longlong_as_double(0x7ff8000000000000ll);
 }
 
 // COMP kernels (k > 31) are limited to <= 5 CTAs per SM by their shared-memory scratch anyway: give them the registers.
@@ -177,7 +188,7 @@ static int32_t bpp_launch(const double* G, const T* R, int64_t ldr, T* X, int64_
     if (ginv_ws != nullptr) {
         // the inverse is used in T arithmetic: accept it only while cond(G) * eps(T) stays small
         const double rcond_min = sizeof(T) == 4 ? 1e-4 : 1e-10;
-        ginv_kernel<<<(unsigned)nseg, 256, (size_t)k * k * sizeof(double), (cudaStream_t)stream>>>(G, ginv_ws, k,
+        ginv_kernel<<<(unsigned)nseg, 1024, (size_t)k * k * sizeof(double), (cudaStream_t)stream>>>(G, ginv_ws, k,
                                                                                                 rcond_min);
         INMF_LAUNCH_CHECK();
     }
