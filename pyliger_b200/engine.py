@@ -78,7 +78,7 @@ def online_windows(total_iters, mbs, sub, n_global, row_base):
 class DeviceCSR(object):
     """All datasets' (local row slices of) scale_data concatenated by rows on the device."""
 
-    def __init__(self, mats, dtype, device, rank=0, world=1, pin=False, replicate=False, presharded=False):
+    def __init__(self, mats, dtype, device, rank=0, world=1, replicate=False, presharded=False):
         self.N = len(mats)
         self.g = int(mats[0].shape[1])
         self.n_global = [int(m.shape[0]) for m in mats]
@@ -168,7 +168,7 @@ def launch_als_draw(device, ns, g, k, seed, h_stream=None):
 class InmfEngine(object):
     """Buffers + step functions shared by optimize_ALS and online_iNMF."""
 
-    def __init__(self, mats, k, value_lambda, dtype=torch.float64, device=None, group=None, pin=False,
+    def __init__(self, mats, k, value_lambda, dtype=torch.float64, device=None, group=None,
                  replicate=False, n_prev=0, presharded=False, use_blocked=True, need_stats=True, use_tc=False,
                  tc_three_pass=True):
         # use_tc: dense-tile tcgen05 form of the two passes (fp32 only): 3xTF32 (fp32-grade) by default
@@ -191,7 +191,7 @@ class InmfEngine(object):
         self.lam = float(value_lambda)
         self.n_prev = int(n_prev)
         with torch.cuda.device(self.device):
-            self.X = DeviceCSR(mats, self.dtype, self.device, self.rank, self.world, pin=pin,
+            self.X = DeviceCSR(mats, self.dtype, self.device, self.rank, self.world,
                                replicate=replicate, presharded=presharded)
             self._alloc()
 
