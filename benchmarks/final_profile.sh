@@ -13,6 +13,6 @@ if [ $rc -eq 0 ]; then
   ncu --set full --clock-control none --import-source on -k regex:'blocked_spmm|bpp_kernel' -s 20 -c 5 \
       -o $OUT/prof_final -f python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e > $OUT/ncu_f_final.log 2>&1; echo "ncu full rc=$?"
 fi
-python benchmarks/bpp_microbench.py 2>/dev/null > $OUT/c5_bpp_final.jsonl; echo "c5 rc=$?"
-python benchmarks/c1_parity.py > $OUT/c1_parity_final.json 2> $OUT/c1_final.err; echo "c1 rc=$?"
+python tests/tools/bpp_microbench.py 2>/dev/null > $OUT/c5_bpp_final.jsonl; echo "c5 rc=$?"
+python tests/tools/c1_parity.py > $OUT/c1_parity_final.json 2> $OUT/c1_final.err; echo "c1 rc=$?"
 tail -1 $OUT/bench_final_n1.json | cut -c1-600

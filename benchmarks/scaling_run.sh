@@ -24,5 +24,5 @@ try:
 except Exception as e:
     print("C4 parse failed", e)
 PY
-timeout 900 $RUN benchmarks/online_bench.py --cpu-cells 0 > $OUT/scale_n${N}_c3.json 2> $OUT/scale_n${N}_c3.err
+timeout 900 $RUN tests/tools/online_bench.py --cpu-cells 0 > $OUT/scale_n${N}_c3.json 2> $OUT/scale_n${N}_c3.err
 echo "C3 rc=$?"; tail -1 $OUT/scale_n${N}_c3.json | cut -c1-700

@@ -15,7 +15,7 @@ def test_two_rank_nccl_parity():
     if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
-           "127.0.0.1", "--master-port", "29517", os.path.join(ROOT, "benchmarks", "multigpu_check.py")]
+           "127.0.0.1", "--master-port", "29517", os.path.join(ROOT, "tests", "tools", "multigpu_check.py")]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     sys.stdout.write(res.stdout[-3000:])
     assert res.returncode == 0, res.stderr[-3000:]

@@ -2,7 +2,7 @@
 """Multi-GPU parity check (launch with torchrun, one rank per GPU, NCCL):
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
-        --master-port 29511 benchmarks/multigpu_check.py
+        --master-port 29511 tests/tools/multigpu_check.py
 
 Every rank passes the FULL datasets; the engine shards the cells, all-reduces the statistics and
 gathers H.  Results must match the single-process numpy oracle (and hence the 1-GPU run) to fp64
@@ -12,7 +12,7 @@ import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 
