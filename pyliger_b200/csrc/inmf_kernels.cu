@@ -182,8 +182,11 @@ static int32_t bpp_launch(const double* G, const T* R, int64_t ldr, T* X, int64_
                                              227 * 1024));
         attr_done[ti] = true;
     }
+    // Grid: about two waves of resident CTAs over ALL segments, each warp striding over its share of the columns,
+    // so that the per-CTA staging of G (and G^-1) into shared memory is amortised over many columns.
     int64_t blocks = (max_seg_cols + nwarps - 1) / nwarps;
-    const int64_t cap = (int64_t)inmf_num_sms() * 16;
+    int64_t cap = ((int64_t)inmf_num_sms() * 2 * BPP_MIN_BLOCKS + nseg - 1) / nseg;
+    if (cap < 1) cap = 1;
     if (blocks > cap) blocks = cap;
     if (ginv_ws != nullptr) {
         // the inverse is used in T arithmetic: accept it only while cond(G) * eps(T) stays small
