@@ -4,12 +4,22 @@ pyliger's API hands scipy matrices from stage to stage (``layers["norm_data"]`` 
 optimize_ALS).  When a stage here has just computed such a matrix on the GPU it registers the device arrays
 under the identity of the host matrix it returned; the next stage finds them and skips the host->device copy
 ("X uploaded once ... never round-trips").  Entries die with the host matrix
-(weakref) or on ``clear()``; a matrix that was modified in place after registration must be dropped by the
-caller (``forget``) -- the stages only ever register matrices they have just created.
+(weakref) or on ``clear()``; a sampled fingerprint of the host matrix is re-checked on every lookup, so a matrix
+edited in place after registration falls back to a normal upload (``forget`` drops an entry explicitly).
 """
 import weakref
 
+import numpy as np
+
 _cache = {}
+
+
+def _fingerprint(m):
+    """Cheap content check of a host CSR matrix (strided samples of data / indices + the ends of indptr): catches
+    in-place edits made after the device twin was registered without touching all of the matrix."""
+    step = max(1, m.nnz // 4096)
+    return (int(m.nnz), tuple(m.shape), float(np.asarray(m.data[::step], dtype=np.float64).sum()),
+            int(np.asarray(m.indices[::step], dtype=np.int64).sum()), int(m.indptr[-1]))
 
 
 def register(host_matrix, device, rowptr, colidx, vals):
@@ -18,7 +28,7 @@ def register(host_matrix, device, rowptr, colidx, vals):
         ref = weakref.ref(host_matrix, lambda _r, key=key: _cache.pop(key, None))
     except TypeError:  # pragma: no cover - scipy matrices are weak-referenceable
         return
-    _cache[key] = (ref, str(device), rowptr, colidx, vals, host_matrix.shape, host_matrix.nnz)
+    _cache[key] = (ref, str(device), rowptr, colidx, vals, _fingerprint(host_matrix))
 
 
 def lookup(host_matrix, device):
@@ -26,8 +36,11 @@ def lookup(host_matrix, device):
     ent = _cache.get(id(host_matrix))
     if ent is None:
         return None
-    ref, dev, rowptr, colidx, vals, shape, nnz = ent
-    if ref() is not host_matrix or dev != str(device) or shape != host_matrix.shape or nnz != host_matrix.nnz:
+    ref, dev, rowptr, colidx, vals, fp = ent
+    if ref() is not host_matrix or dev != str(device):
+        return None
+    if fp != _fingerprint(host_matrix):  # edited in place since: the twin is stale
+        _cache.pop(id(host_matrix), None)
         return None
     return rowptr, colidx, vals
 

@@ -340,3 +340,43 @@ def test_tc_formats_reproduce_products(world, rank):
         sub = mm[lo:hi]
         np.testing.assert_allclose(R[o0:o1], sub @ Mt[s * g:(s + 1) * g, :k], rtol=1e-5, atol=1e-5)
         np.testing.assert_allclose(St[s * g:(s + 1) * g], sub.T @ H[o0:o1, :k], rtol=1e-5, atol=1e-5)
+
+
+def test_device_twin_cache_detects_edits_and_dies_with_the_matrix():
+    import gc
+    from pyliger_b200 import devcache
+    m = sps.random(50, 30, density=0.3, random_state=1, format="csr")
+    dev = torch.device("cpu")
+    t = (torch.from_numpy(m.indptr.astype(np.int64)), torch.from_numpy(m.indices.astype(np.int32)),
+         torch.from_numpy(m.data.copy()))
+    devcache.register(m, dev, *t)
+    assert devcache.lookup(m, dev) is not None
+    assert devcache.lookup(m, torch.device("meta")) is None       # other device
+    assert devcache.lookup(m.copy(), dev) is None                 # identity, not equality
+    m.data *= 2.0                                                 # in-place edit -> stale twin is dropped
+    assert devcache.lookup(m, dev) is None and devcache.lookup(m, dev) is None
+    m2 = sps.random(20, 30, density=0.3, random_state=2, format="csr")
+    devcache.register(m2, dev, *t)
+    n_before = len(devcache._cache)
+    del m2
+    gc.collect()
+    assert len(devcache._cache) == n_before - 1
+
+
+def test_anndata_like_slicing_and_raw():
+    from pyliger_b200.containers import AnnDataLike, liger_from_raw
+    X = sps.random(12, 7, density=0.5, random_state=0, format="csr")
+    a = AnnDataLike.from_raw(X, "s", var_names=["g%d" % j for j in range(7)])
+    a.layers["norm_data"] = X * 2.0
+    a.var["norm_sum_sq"] = np.arange(7.0)
+    a.obsm["H"] = np.arange(24.0).reshape(12, 2)
+    keep = np.array([True, False, True, True, False, False, True])
+    a.raw = a
+    b = a[:, keep].copy()
+    assert b.shape == (12, 4) and b.layers["norm_data"].shape == (12, 4)
+    assert list(b.var.index) == ["g0", "g2", "g3", "g6"] and list(b.var["norm_sum_sq"]) == [0.0, 2.0, 3.0, 6.0]
+    assert b.raw.shape == (12, 7) and b.obsm["H"].shape == (12, 2)
+    c = a[np.arange(12) % 2 == 0, :]
+    assert c.shape == (6, 7) and c.obsm["H"].shape == (6, 2) and len(c.obs) == 6
+    lig = liger_from_raw([X, X[:5]], ["a", "b"])
+    assert lig.num_samples == 2 and lig.adata_list[1].shape == (5, 7) and lig.adata_list[0].layers == {}
