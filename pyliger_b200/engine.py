@@ -431,12 +431,57 @@ class InmfEngine(object):
         """One (H, V, W) block update + objective; returns the device scalar objective.
 
         Requires prep() of the current W, V (done by initial_objective() / the previous iteration)."""
-        self.solve_H(mask=self.mask_H, warm=warm)
+        if not self._begun:
+            self.rhs_H()
+        self._begun = False
+        self.bpp_H(mask=self.mask_H, warm=warm)
         self.stats()
         self.solve_V(warm=warm)
         self.solve_W(warm=warm)
         self.prep()
         return self.objective()
+
+    # The reference decides after every iteration whether to go on (delta > thresh), which costs one host read-back
+    # of the objective per iteration.  To keep the GPU busy across that read-back, the first kernel of the NEXT
+    # iteration (pass 1, which only reads X and the already prepared W + V_i) is enqueued before the host waits; it
+    # writes into a spare H buffer, so stopping just drops it.
+    _begun = False
+    H_alt = None
+    _obj_host = None
+    _obj_event = None
+
+    def als_begin(self):
+        """Enqueue pass 1 of the next iteration into the spare H buffer (the current H stays intact in H_alt)."""
+        if self._begun:
+            return
+        if self.H_alt is None:
+            self.H_alt = torch.zeros_like(self.H)
+        self.H, self.H_alt = self.H_alt, self.H
+        self.rhs_H()
+        self._begun = True
+
+    def als_cancel(self):
+        """Drop a pass 1 started by als_begin(): self.H is the last completed iteration's H again."""
+        if self._begun:
+            self.H, self.H_alt = self.H_alt, self.H
+            self._begun = False
+
+    def als_iteration_value(self, warm=False, speculate=False):
+        """als_iteration() + host value of the objective; with ``speculate`` the next pass 1 overlaps the read-back
+        (call als_cancel() if no further iteration follows)."""
+        obj = self.als_iteration(warm=warm)
+        if not speculate:
+            return float(obj.item())
+        # the objective goes to pinned memory behind an event, so that the host does not wait for the pass 1
+        # enqueued after it
+        if self._obj_host is None:
+            self._obj_host = torch.empty(1, dtype=obj.dtype, pin_memory=True)
+            self._obj_event = torch.cuda.Event()
+        self._obj_host.copy_(obj.reshape(1), non_blocking=True)
+        self._obj_event.record()
+        self.als_begin()
+        self._obj_event.synchronize()
+        return float(self._obj_host[0])
 
     def gather_H(self):
         """Full H per dataset as host float64 arrays (all-gather of the row slices)."""

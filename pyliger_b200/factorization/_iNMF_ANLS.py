@@ -109,10 +109,12 @@ def optimize_ALS(
         for it in it_range:
             if delta > thresh:
                 obj_prev = obj0
-                obj0 = float(engine.als_iteration(warm=warm_start and iters_run > 0).item())
+                obj0 = engine.als_iteration_value(warm=warm_start and iters_run > 0, speculate=it + 1 < max_iters)
                 objs.append(obj0)
                 delta = np.absolute(obj_prev - obj0) / ((obj_prev + obj0) / 2)
                 iters_run += 1
+                if not delta > thresh:
+                    engine.als_cancel()  # converged: the speculative pass 1 of the next iteration is dropped
             else:
                 continue
         info["objectives"].append(objs)
