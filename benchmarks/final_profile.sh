@@ -4,6 +4,7 @@
 OUT=gpurun_out
 mkdir -p $OUT
 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -4
 python bench.py > $OUT/bench_final_n1.json 2> $OUT/bench_final_n1.err; echo "bench rc=$?"
 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/bench_final_ref.json 2> $OUT/bench_final_ref.err; echo "ref rc=$?"
 python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e > $OUT/plain_final.log 2>&1; rc=$?; echo "plain rc=$rc"
