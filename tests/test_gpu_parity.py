@@ -235,8 +235,13 @@ def test_als_user_inits_and_no_early_work(golden_als):
     np.testing.assert_allclose(info["objectives"][0], want["objectives"], rtol=1e-9)
     assert relerr(lig.H[0], want["H"][0]) < 1e-7
     stop = orc.als(mats, k, 4.0, 0.5, 6)
-    info = optimize_ALS(_liger(mats), k, 4.0, 0.5, 6, return_info=True, progress=False)
+    lig = _liger(mats)
+    info = optimize_ALS(lig, k, 4.0, 0.5, 6, return_info=True, progress=False)
     assert info["iters_run"] == [stop["iters_run"]] and 0 < stop["iters_run"] < 6
+    # the pass 1 of the iteration that was not run (enqueued speculatively into the spare H buffer) is dropped
+    for i in range(len(mats)):
+        assert relerr(lig.H[i], stop["H"][i]) < 1e-7
+    assert relerr(lig.W, stop["W"].T) < 1e-7
 
 
 @pytest.mark.parametrize("dtype", ["float64", "float32"])
