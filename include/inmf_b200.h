@@ -109,6 +109,14 @@ int32_t inmf_blocked_spmm_f64(const int64_t* work, int32_t nwork, const int64_t*
                               const double* dense, int32_t kp, double* out, int64_t ldo, int32_t k,
                               int32_t max_tile_rows, double* gram_out, void* stream);
 
+/* Same contract as inmf_blocked_spmm_f32 for 32 < k <= 64, with the dense tile held split in shared memory
+ * ([rows x 32] + [rows x remainder]) so that every 8-lane phase of the 128-bit operand loads is one contiguous
+ * 128-byte row.  Differences: the pairs' first field is (row of the tile) * 128 (not * kp * 4), and the tile may hold
+ * at most (227 KB - 128) / ((32 + rs) * 4) rows, rs = 8, 16 or 32 for kp - 32 <= 8, <= 16, <= 32. */
+int32_t inmf_blocked_split_f32(const int64_t* work, int32_t nwork, const int64_t* ptr, const void* pairs,
+                               const float* dense, int32_t kp, float* out, int64_t ldo, int32_t k,
+                               int32_t max_tile_rows, double* gram_out, void* stream);
+
 /* Sufficient statistics of one pass over the cells (accumulating; caller zeroes):
  *   St[s] (g x k) += sum_q X[row(q), :]' H[q, :],   HtH[s] (k x k, double) += sum_q H[q,:]' H[q,:]
  * Replaces the dense X - H@W / vstack products of _iNMF_ANLS.py:144-152 and the H H', X H' of

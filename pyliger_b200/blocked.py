@@ -6,6 +6,8 @@ arithmetic passes over these structures are libinmf_b200.so kernels).
 pass 1  "gene-blocked CSR":  pairs ordered by (dataset, gene block, cell, gene);  tile = rows of Mt
 pass 2  "cell-blocked CSC":  pairs ordered by (dataset, cell block, gene, cell);  tile = rows of H
 """
+import os
+
 import numpy as np
 import torch
 
@@ -38,11 +40,11 @@ def _device_format1(X, kp, esize, NB, gbs):
     n_tot = X.n_own_total
     ptr = torch.zeros(NB * n_tot + 1, dtype=torch.int64, device=dev)
     sfx = _sfx(X.vals)
-    _lib.call("inmf_blockfmt1", sfx, 0, X.rowptr, X.colidx, X.vals, seg1_t, X.N, n_tot, NB, gbs, kp * esize,
+    _lib.call("inmf_blockfmt1", sfx, 0, X.rowptr, X.colidx, X.vals, seg1_t, X.N, n_tot, NB, gbs, row_bytes(kp, esize),
               ptr[1:], None, _stream(dev))
     torch.cumsum(ptr[1:], 0, out=ptr[1:])
     pairs = _empty_pairs(int(ptr[-1].item()), X.vals)
-    _lib.call("inmf_blockfmt1", sfx, 1, X.rowptr, X.colidx, X.vals, seg1_t, X.N, n_tot, NB, gbs, kp * esize,
+    _lib.call("inmf_blockfmt1", sfx, 1, X.rowptr, X.colidx, X.vals, seg1_t, X.N, n_tot, NB, gbs, row_bytes(kp, esize),
               ptr, pairs, _stream(dev))
     return ptr, pairs
 
@@ -66,17 +68,38 @@ def _device_format2(X, kp, esize, nb, cbs, blk_off):
     blk2_t = torch.tensor(blk2, dtype=torch.int64, device=dev)
     offs = torch.empty(total_blocks * W * g, dtype=torch.int16, device=dev)
     sfx = _sfx(X.vals)
-    _lib.call("inmf_blockfmt2", sfx, 0, X.rowptr, X.colidx, X.vals, blk2_t, total_blocks, g, kp * esize, W,
+    _lib.call("inmf_blockfmt2", sfx, 0, X.rowptr, X.colidx, X.vals, blk2_t, total_blocks, g, row_bytes(kp, esize), W,
               ptr[1:], None, offs, None, _stream(dev))
     torch.cumsum(ptr[1:], 0, out=ptr[1:])
     pairs = _empty_pairs(int(ptr[-1].item()), X.vals)
-    _lib.call("inmf_blockfmt2", sfx, 1, X.rowptr, X.colidx, X.vals, blk2_t, total_blocks, g, kp * esize, W,
+    _lib.call("inmf_blockfmt2", sfx, 1, X.rowptr, X.colidx, X.vals, blk2_t, total_blocks, g, row_bytes(kp, esize), W,
               None, ptr, offs, pairs, _stream(dev))
     return ptr, pairs
 
 
+# Split-tile kernel (csrc/blocked.cuh, inmf_blocked_split_f32) for fp32 and 32 < KP <= 64: [rows x 32] + [rows x rs]
+# tile, pairs carry row * 128.  Off unless INMF_SPLIT_TILE=1 until it has been measured against the plain kernel.
+SPLIT_TILE = os.environ.get("INMF_SPLIT_TILE", "0") == "1"
+
+
+def split_applies(kp, esize):
+    return SPLIT_TILE and esize == 4 and 32 < kp <= 64
+
+
+def row_bytes(kp, esize):
+    """Stride that the pairs' byte offsets are premultiplied with."""
+    return 128 if split_applies(kp, esize) else kp * esize
+
+
+def smem_row_bytes(kp, esize):
+    if split_applies(kp, esize):
+        rem = kp - 32
+        return (32 + (8 if rem <= 8 else 16 if rem <= 16 else 32)) * 4
+    return kp * esize
+
+
 def tile_cap_rows(kp, esize):
-    return SMEM_BUDGET // (kp * esize)
+    return SMEM_BUDGET // smem_row_bytes(kp, esize)
 
 
 def _pack_pairs(idx_local, vals):
@@ -93,7 +116,7 @@ def _pack_pairs(idx_local, vals):
 
 
 class BlockedPass(object):
-    __slots__ = ("work", "nwork", "ptr", "pairs", "max_tile_rows")
+    __slots__ = ("work", "nwork", "ptr", "pairs", "max_tile_rows", "split")
 
 
 def _own_nnz(X):
@@ -126,6 +149,7 @@ def build_pass1(X, kp, esize, n_sms):
     NB = max(1, -(-g // cap))
     gbs = -(-g // NB)
     bp = BlockedPass()
+    bp.split = split_applies(kp, esize)
     if USE_DEVICE_BUILD and dev.type == "cuda" and X.n_own_total > 0:
         bp.ptr, bp.pairs = _device_format1(X, kp, esize, NB, gbs)
     else:
@@ -142,7 +166,7 @@ def build_pass1(X, kp, esize, n_sms):
         if cidx.numel():
             ptr[1:] = torch.cumsum(torch.bincount(cidx, minlength=NB * n_tot), 0)
         idx_local = (col.to(torch.int64) - gb * gbs)[order]
-        bp.pairs = _pack_pairs(idx_local * (kp * esize), val[order])  # byte offset of the gathered tile row
+        bp.pairs = _pack_pairs(idx_local * row_bytes(kp, esize), val[order])  # byte offset of the gathered tile row
         bp.ptr = ptr
     chunks = max(1, n_sms // max(1, N * NB))
     work = []
@@ -176,6 +200,7 @@ def build_pass2(X, kp, esize, n_sms):
     blk_off = np.concatenate([[0], np.cumsum(nb)]).astype(np.int64)
     total_blocks = int(blk_off[-1])
     bp = BlockedPass()
+    bp.split = split_applies(kp, esize)
     built = None
     if USE_DEVICE_BUILD and dev.type == "cuda" and X.n_own_total > 0:
         built = _device_format2(X, kp, esize, nb, cbs, blk_off)
@@ -195,7 +220,7 @@ def build_pass2(X, kp, esize, n_sms):
         if cidx.numel():
             ptr[1:] = torch.cumsum(torch.bincount(cidx, minlength=g * total_blocks), 0)
         idx_local = (local_row - cb * cbs_t[seg])[order]
-        bp.pairs = _pack_pairs(idx_local * (kp * esize), val[order])  # byte offset of the gathered tile row
+        bp.pairs = _pack_pairs(idx_local * row_bytes(kp, esize), val[order])  # byte offset of the gathered tile row
         bp.ptr = ptr
     chunks = max(1, n_sms // max(1, total_blocks))
     per = -(-g // chunks)
@@ -339,7 +364,8 @@ def build_pass1_resident(X, kp, esize):
     if cidx.numel():
         ptr[1:] = torch.cumsum(torch.bincount(cidx, minlength=NB * X.n_total), 0)
     bp = BlockedPass()
-    bp.pairs = _pack_pairs((col - gb * gbs)[order] * (kp * esize), val[order])
+    bp.split = split_applies(kp, esize)
+    bp.pairs = _pack_pairs((col - gb * gbs)[order] * row_bytes(kp, esize), val[order])
     bp.ptr = ptr
     bp.work, bp.nwork = None, 0
     bp.max_tile_rows = min(gbs, g)

@@ -243,3 +243,238 @@ blocked_spmm_kernel(const int64_t* __restrict__ work, const int64_t* __restrict_
         tile_gram_accumulate<T>(tile, KP, tile_rows, k, gram_out + (size_t)gram_seg * k * k, 1.0);
     }
 }
+
+// =====================================================================================================
+// Split-tile variant for 32 < KP <= 64 (fp32): the dense tile is held as a [rows x 32] part (128-byte rows) plus a
+// [rows x RS] remainder (RS = 8, 16 or 32 floats per row, RL = RS / 8 per lane).
+//
+// Why: a 128-bit shared load is served in four phases of 8 lanes.  With KP = 40 (10 lanes per non-zero) a phase mixes
+// the tail of one gathered row with the head of another, and one warp instruction (3 non-zeros) costs ~6 wavefronts
+// instead of 4.  Here 8 lanes own one non-zero: every phase of the main load is one contiguous 128-byte row (4
+// non-zeros per instruction, 4 wavefronts), and the remainder is one 32/64/128-bit load per lane.
+// Pairs carry the MAIN byte offset (row * 128); the remainder offset is a shift of it.
+// The tile arrives by per-row bulk copies (two per row) that all complete on one mbarrier.
+// =====================================================================================================
+template <int RL>
+struct SplitRem;
+template <>
+struct SplitRem<1> {
+    static constexpr int SHIFT = 2;  // row * 128 -> row * 32 bytes
+    __device__ static __forceinline__ void fma(float v, uint32_t addr, float (&acc)[1]) {
+        float m;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(m) : "r"(addr));
+        acc[0] = fmaf(v, m, acc[0]);
+    }
+};
+template <>
+struct SplitRem<2> {
+    static constexpr int SHIFT = 1;  // row * 64 bytes
+    __device__ static __forceinline__ void fma(float v, uint32_t addr, float (&acc)[2]) {
+        float m0, m1;
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(m0), "=f"(m1) : "r"(addr));
+        acc[0] = fmaf(v, m0, acc[0]);
+        acc[1] = fmaf(v, m1, acc[1]);
+    }
+};
+template <>
+struct SplitRem<4> {
+    static constexpr int SHIFT = 0;  // row * 128 bytes
+    __device__ static __forceinline__ void fma(float v, uint32_t addr, float (&acc)[4]) {
+        float m0, m1, m2, m3;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(m0), "=f"(m1), "=f"(m2), "=f"(m3) : "r"(addr));
+        acc[0] = fmaf(v, m0, acc[0]);
+        acc[1] = fmaf(v, m1, acc[1]);
+        acc[2] = fmaf(v, m2, acc[2]);
+        acc[3] = fmaf(v, m3, acc[3]);
+    }
+};
+
+template <int RL>
+__device__ __forceinline__ void split_fma(const int2& p, uint32_t tmain, uint32_t trem, float (&acc)[4],
+                                          float (&accr)[RL]) {
+    float m0, m1, m2, m3;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(m0), "=f"(m1), "=f"(m2), "=f"(m3)
+                 : "r"(tmain + (uint32_t)p.x));
+    const float v = __int_as_float(p.y);
+    acc[0] = fmaf(v, m0, acc[0]);
+    acc[1] = fmaf(v, m1, acc[1]);
+    acc[2] = fmaf(v, m2, acc[2]);
+    acc[3] = fmaf(v, m3, acc[3]);
+    SplitRem<RL>::fma(v, trem + ((uint32_t)p.x >> SplitRem<RL>::SHIFT), accr);
+}
+
+// One warp, one sparse row of m pairs: lane (grp = lane / 8, sub = lane % 8); sums end up in the lanes of group 0.
+template <int RL>
+__device__ __forceinline__ void warp_row_dot_split(const int2* __restrict__ pl0, int m, int grp, uint32_t tmain,
+                                                   uint32_t trem, float (&acc)[4], float (&accr)[RL]) {
+    typedef PairTraits<float> PT;
+    constexpr int NPI = 4;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) acc[u] = 0.f;
+#pragma unroll
+    for (int u = 0; u < RL; ++u) accr[u] = 0.f;
+    const int2* __restrict__ pl = pl0 + grp;
+    const int nfull = m / NPI;
+    const int nq = (m + NPI - 1) / NPI;
+    int j = 0;
+    if (nfull >= BLK_U) {
+        int2 A[BLK_U], B[BLK_U];
+#pragma unroll
+        for (int t = 0; t < BLK_U; ++t) A[t] = PT::ld(pl + t * NPI);
+        while (true) {
+            const int2* __restrict__ pn = pl + (size_t)(j + BLK_U) * NPI;
+            if (j + 2 * BLK_U <= nfull) {
+#pragma unroll
+                for (int t = 0; t < BLK_U; ++t) B[t] = PT::ld(pn + t * NPI);
+#pragma unroll
+                for (int t = 0; t < BLK_U; ++t) split_fma<RL>(A[t], tmain, trem, acc, accr);
+                j += BLK_U;
+            } else {
+#pragma unroll
+                for (int t = 0; t < BLK_U; ++t) split_fma<RL>(A[t], tmain, trem, acc, accr);
+                j += BLK_U;
+                break;
+            }
+            const int2* __restrict__ pm = pl + (size_t)(j + BLK_U) * NPI;
+            if (j + 2 * BLK_U <= nfull) {
+#pragma unroll
+                for (int t = 0; t < BLK_U; ++t) A[t] = PT::ld(pm + t * NPI);
+#pragma unroll
+                for (int t = 0; t < BLK_U; ++t) split_fma<RL>(B[t], tmain, trem, acc, accr);
+                j += BLK_U;
+            } else {
+#pragma unroll
+                for (int t = 0; t < BLK_U; ++t) split_fma<RL>(B[t], tmain, trem, acc, accr);
+                j += BLK_U;
+                break;
+            }
+        }
+    }
+    {
+        int2 C[BLK_U];
+#pragma unroll
+        for (int t = 0; t < BLK_U; ++t) {
+            const int q = (j + t) * NPI + grp;
+            C[t] = ((j + t) < nq && q < m) ? PT::ld(pl0 + q) : PT::zero();  // zero pair: offset 0, value 0
+        }
+#pragma unroll
+        for (int t = 0; t < BLK_U; ++t)
+            if (j + t < nq) split_fma<RL>(C[t], tmain, trem, acc, accr);
+    }
+#pragma unroll
+    for (int gq = 1; gq < NPI; ++gq) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float o = __shfl_down_sync(INMF_FULL_MASK, acc[u], gq * 8);
+            acc[u] += (grp == 0) ? o : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < RL; ++u) {
+            const float o = __shfl_down_sync(INMF_FULL_MASK, accr[u], gq * 8);
+            accr[u] += (grp == 0) ? o : 0.f;
+        }
+    }
+}
+
+// H'H of a split tile (columns < 32 in `tmain`, the others in `trem`), same blocking as tile_gram_accumulate.
+__device__ __forceinline__ void split_gram_accumulate(const float* __restrict__ tmain, const float* __restrict__ trem,
+                                                      int rs, int rows, int k, double* __restrict__ out) {
+    const int nb = (k + 3) >> 2;
+    for (int blk = threadIdx.x; blk < nb * nb; blk += blockDim.x) {
+        const int bi = blk / nb, bj = blk % nb;
+        const float* pa = (4 * bi < 32) ? tmain + 4 * bi : trem + (4 * bi - 32);
+        const float* pb = (4 * bj < 32) ? tmain + 4 * bj : trem + (4 * bj - 32);
+        const int sa = (4 * bi < 32) ? 32 : rs, sb = (4 * bj < 32) ? 32 : rs;
+        float acc[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+        for (int r = 0; r < rows; ++r) {
+            const float4 va = *reinterpret_cast<const float4*>(pa + (size_t)r * sa);
+            const float4 vb = *reinterpret_cast<const float4*>(pb + (size_t)r * sb);
+            const float xa[4] = {va.x, va.y, va.z, va.w}, xb[4] = {vb.x, vb.y, vb.z, vb.w};
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) acc[a][b] += xa[a] * xb[b];
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int i = 4 * bi + a, j = 4 * bj + b;
+                if (i < k && j < k) atomicAdd(&out[(size_t)i * k + j], (double)acc[a][b]);
+            }
+    }
+}
+
+template <int RL>
+__global__ void __launch_bounds__(1024, 1)
+blocked_split_kernel(const int64_t* __restrict__ work, const int64_t* __restrict__ ptr, const int2* __restrict__ pairs,
+                     const float* __restrict__ dense, int KP, float* __restrict__ out, int64_t ldo, int k,
+                     int max_tile_rows, double* __restrict__ gram_out) {
+    constexpr int RS = 8 * RL;  // remainder floats per row in shared memory
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+    float* tmain = reinterpret_cast<float*>(smem_raw + 128);
+    float* trem = tmain + (size_t)max_tile_rows * 32;
+    const int64_t* wd = work + (size_t)blockIdx.x * INMF_WORK_FIELDS;
+    const int64_t ptr_base = wd[0], dense_row0 = wd[1];
+    const int tile_rows = (int)wd[2];
+    const int64_t row_begin = wd[3], row_end = wd[4], out_row_base = wd[5];
+    const int gram_seg = (int)wd[6];
+    const int R = KP - 32;  // remainder floats per row in global memory (multiple of 4, zero padded beyond k)
+
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        mbar_expect_tx(bar, (uint32_t)((size_t)tile_rows * KP * sizeof(float)));
+    }
+    __syncthreads();
+    {
+        const float* src = dense + (size_t)dense_row0 * KP;
+        for (int r = threadIdx.x; r < tile_rows; r += blockDim.x) {
+            bulk_g2s(tmain + (size_t)r * 32, src + (size_t)r * KP, 128u, bar);
+            bulk_g2s(trem + (size_t)r * RS, src + (size_t)r * KP + 32, (uint32_t)(R * sizeof(float)), bar);
+        }
+    }
+    const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int grp = lane >> 3, sub = lane & 7;
+    const uint32_t ta = smem_u32(tmain) + (uint32_t)(sub * 16);
+    const uint32_t tr = smem_u32(trem) + (uint32_t)(sub * RL * 4);
+    int64_t r = row_begin + warp;
+    int64_t beg = 0, end = 0;
+    if (r < row_end) {
+        beg = ptr[ptr_base + r];
+        end = ptr[ptr_base + r + 1];
+    }
+    mbar_wait(bar, 0);
+
+    while (r < row_end) {
+        const int64_t rn = r + nwarps;
+        int64_t nbeg = 0, nend = 0;
+        if (rn < row_end) {
+            nbeg = ptr[ptr_base + rn];
+            nend = ptr[ptr_base + rn + 1];
+        }
+        if (beg != end) {
+            float acc[4], accr[RL];
+            warp_row_dot_split<RL>(pairs + beg, (int)(end - beg), grp, ta, tr, acc, accr);
+            if (grp == 0) {
+                float* o = out + (out_row_base + r) * ldo;
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (acc[u] != 0.f) atomicAdd(o + sub * 4 + u, acc[u]);
+#pragma unroll
+                for (int u = 0; u < RL; ++u)
+                    if (32 + sub * RL + u < k && accr[u] != 0.f) atomicAdd(o + 32 + sub * RL + u, accr[u]);
+            }
+        }
+        r = rn;
+        beg = nbeg;
+        end = nend;
+    }
+    if (gram_seg >= 0 && gram_out != nullptr)
+        split_gram_accumulate(tmain, trem, RS, tile_rows, k, gram_out + (size_t)gram_seg * k * k);
+}

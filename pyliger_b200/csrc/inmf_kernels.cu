@@ -1187,6 +1187,36 @@ extern "C" int32_t inmf_blocked_spmm_f64(const int64_t* work, int32_t nwork, con
     return blocked_launch<double>(work, nwork, ptr, pairs, dense, kp, out, ldo, k, max_tile_rows, gram_out, stream);
 }
 
+template <int RL>
+static int32_t blocked_split_one(const int64_t* work, int32_t nwork, const int64_t* ptr, const void* pairs,
+                                 const float* dense, int32_t kp, float* out, int64_t ldo, int32_t k,
+                                 int32_t max_tile_rows, double* gram_out, void* stream) {
+    const size_t smem = 128 + (size_t)max_tile_rows * (32 + 8 * RL) * sizeof(float);
+    INMF_REQUIRE(smem <= 227 * 1024, "dense tile does not fit in shared memory");
+    static bool attr_done = false;
+    if (!attr_done) {
+        INMF_CUDA_CHECK(cudaFuncSetAttribute(blocked_split_kernel<RL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             227 * 1024));
+        attr_done = true;
+    }
+    blocked_split_kernel<RL><<<(unsigned)nwork, 1024, smem, (cudaStream_t)stream>>>(
+        work, ptr, reinterpret_cast<const int2*>(pairs), dense, kp, out, ldo, k, max_tile_rows, gram_out);
+    INMF_LAUNCH_CHECK();
+    return 0;
+}
+extern "C" int32_t inmf_blocked_split_f32(const int64_t* work, int32_t nwork, const int64_t* ptr, const void* pairs,
+                                          const float* dense, int32_t kp, float* out, int64_t ldo, int32_t k,
+                                          int32_t max_tile_rows, double* gram_out, void* stream) {
+    INMF_REQUIRE(k > 32 && k <= INMF_MAX_K, "the split-tile kernel is for 32 < k <= 64");
+    INMF_REQUIRE(kp >= k && kp % 4 == 0 && kp <= 64, "kp must be a multiple of 4 in [k, 64]");
+    INMF_REQUIRE(ldo >= k, "ldo must be >= k");
+    if (nwork <= 0) return 0;
+    const int rem = kp - 32;
+    if (rem <= 8) return blocked_split_one<1>(work, nwork, ptr, pairs, dense, kp, out, ldo, k, max_tile_rows, gram_out, stream);
+    if (rem <= 16) return blocked_split_one<2>(work, nwork, ptr, pairs, dense, kp, out, ldo, k, max_tile_rows, gram_out, stream);
+    return blocked_split_one<4>(work, nwork, ptr, pairs, dense, kp, out, ldo, k, max_tile_rows, gram_out, stream);
+}
+
 // =================================================================================================
 // tcgen05 diagnostics
 // =================================================================================================

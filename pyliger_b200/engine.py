@@ -292,11 +292,16 @@ class InmfEngine(object):
         elif full and out is self.H and self.pass1 is not None:
             out.zero_()
             p = self.pass1
-            _lib.call("inmf_blocked_spmm", self.sfx, p.work, p.nwork, p.ptr, p.pairs, self.Mt, self.ldm, out,
-                      self.ldm, k, p.max_tile_rows, None, _stream())
+            self._blocked(p, p.work, p.nwork, self.Mt, out, self.ldm, None)
         else:
             _lib.call("inmf_spmm", self.sfx, X.rowptr, X.colidx, X.vals, self.Mt, self.ldm, self.g, out, self.ldm,
                       seg_desc, nseg, max_rows, k, _stream())
+
+    def _blocked(self, p, work, nwork, dense, out, ldo, gram):
+        """One tiled pass (out += X_blocked * dense tile): plain or split-tile kernel, as the format was built."""
+        name, sfx = ("inmf_blocked_split_f32", "") if p.split else ("inmf_blocked_spmm", self.sfx)
+        _lib.call(name, sfx, work, nwork, p.ptr, p.pairs, dense, self.ldm, out, ldo, self.k, p.max_tile_rows, gram,
+                  _stream())
 
     def _ginv(self, warm):
         """Workspace for G^-1: cold starts use it for the all-passive first round, k > 31 for passive sets
@@ -352,8 +357,7 @@ class InmfEngine(object):
                 _lib.call("inmf_gram_rows", self.sfx, H, self.ldm, self.seg_full, nseg, max_rows, HtH, k, _stream())
             elif full and self.pass2 is not None:
                 p = self.pass2
-                _lib.call("inmf_blocked_spmm", self.sfx, p.work, p.nwork, p.ptr, p.pairs, H, self.ldm, St, k, k,
-                          p.max_tile_rows, HtH, _stream())
+                self._blocked(p, p.work, p.nwork, H, St, k, HtH)
             else:
                 _lib.call("inmf_stats", self.sfx, X.rowptr, X.colidx, X.vals, H, self.ldm, St, HtH, self.g, seg_desc,
                           nseg, max_rows, k, _stream())
@@ -559,8 +563,7 @@ class InmfEngine(object):
         if step is not None and self.win is not None:
             bp, work, counts = self.win
             self.H_mb.zero_()
-            _lib.call("inmf_blocked_spmm", self.sfx, work[step], int(counts[step]), bp.ptr, bp.pairs, self.Mt, self.ldm, self.H_mb,
-                      self.ldm, self.k, bp.max_tile_rows, None, _stream())
+            self._blocked(bp, work[step], int(counts[step]), self.Mt, self.H_mb, self.ldm, None)
             self.bpp_H(seg_desc=seg_desc_t, max_rows=self.max_sub, out=self.H_mb)
         else:
             self.solve_H(seg_desc=seg_desc_t, max_rows=self.max_sub, out=self.H_mb)

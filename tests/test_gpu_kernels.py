@@ -285,3 +285,43 @@ def test_device_format_builders_equal_sort_path(dev, dtype, world, rank, replica
         assert torch.equal(a.ptr, b.ptr)
         assert a.pairs.shape == b.pairs.shape and torch.equal(a.pairs, b.pairs)
         assert torch.equal(a.work, b.work) and a.max_tile_rows == b.max_tile_rows
+
+
+@pytest.mark.parametrize("k", [33, 40, 47, 56, 64])
+def test_split_tile_passes_match_plain_passes(dev, k):
+    """inmf_blocked_split_f32 ([rows x 32] + remainder tile) against numpy and against the plain tiled kernel:
+    pass 1 (X (W+V)'), pass 2 (X'H and H'H), several gene / cell blocks, and one whole ALS run."""
+    from pyliger_b200 import blocked
+    lam = 2.0
+    mats, W, V, H = _rand_problem(k, k=k)
+    old = (blocked.SMEM_BUDGET, blocked.SPLIT_TILE)
+    blocked.SMEM_BUDGET = 40 * 256  # 40-64 tile rows: several gene and cell blocks at this toy size
+    res = {}
+    try:
+        for split in (False, True):
+            blocked.SPLIT_TILE = split
+            eng = _engine(mats, k, lam, "float32")
+            assert eng.pass1.split == split and eng.pass2.split == split
+            eng.set_als_state(W, V, H)
+            eng.prep()
+            eng.stats()
+            St, HtH = eng.St.clone(), eng.HtH.clone()
+            eng.rhs_H()
+            R = eng.H.clone()
+            eng.set_als_state(W, V, H)
+            objs = [float(eng.initial_objective())] + [float(eng.als_iteration(warm=i > 0).item()) for i in range(3)]
+            res[split] = (St, HtH, R, objs, eng.H.clone())
+    finally:
+        blocked.SMEM_BUDGET, blocked.SPLIT_TILE = old
+    N = len(mats)
+    St, HtH, R, objs, Hf = res[True]
+    off = 0
+    for i in range(N):
+        n = mats[i].shape[0]
+        assert relerr(St[i].cpu().numpy(), np.asarray(mats[i].T.dot(H[i]))) < 5e-6
+        assert relerr(HtH[i].cpu().numpy(), H[i].T @ H[i]) < 5e-6
+        assert relerr(R[off:off + n, :k].cpu().numpy(), np.asarray(mats[i].dot((W + V[i]).T))) < 5e-6
+        off += n
+    assert float(R[:, k:].abs().max().item() if R.shape[1] > k else 0.0) == 0.0  # pad columns stay zero
+    np.testing.assert_allclose(objs, res[False][3], rtol=2e-6)
+    assert relerr(Hf.cpu().numpy(), res[False][4].cpu().numpy()) < 1e-3

@@ -191,14 +191,16 @@ def test_two_rank_gloo_statistics_and_gather():
 
 
 # ------------------------------------------------------------------------------------------ blocked formats
-def _emulate_blocked(bp, dense, kp, out, k, gram=None):
-    """numpy statement of what inmf_blocked_spmm computes from (work, ptr, pairs)."""
+def _emulate_blocked(bp, dense, kp, out, k, gram=None, row_bytes=None):
+    """numpy statement of what inmf_blocked_spmm (or, with row_bytes = 128, inmf_blocked_split_f32) computes from
+    (work, ptr, pairs)."""
     work = bp.work.numpy()[:bp.nwork]
     ptr = bp.ptr.numpy()
     pairs = bp.pairs.numpy()
     esize = 4 if pairs.dtype == np.int32 else 8
-    assert np.all(pairs[:, 0] % (kp * esize) == 0)  # premultiplied byte offsets of tile rows
-    idx = pairs[:, 0].astype(np.int64) // (kp * esize)
+    row_bytes = kp * esize if row_bytes is None else row_bytes
+    assert np.all(pairs[:, 0] % row_bytes == 0)  # premultiplied byte offsets of tile rows
+    idx = pairs[:, 0].astype(np.int64) // row_bytes
     vals = pairs[:, 1].copy().view(np.float32 if pairs.dtype == np.int32 else np.float64).astype(np.float64)
     for ptr_base, dense_row0, tile_rows, r0, r1, out_base, gram_seg, _ in work:
         tile = dense[dense_row0:dense_row0 + tile_rows]
@@ -286,6 +288,37 @@ def test_window_work_lists_reproduce_minibatch_rhs(world, rank):
             np.testing.assert_allclose(out[out_off:out_off + cnt, :k], m[idx] @ Mt[s * g:(s + 1) * g, :k],
                                        rtol=1e-12, atol=1e-12)
     assert wrapped > 0
+
+
+def test_split_tile_formats_use_128_byte_rows():
+    """With the split-tile kernel selected (fp32, 32 < KP <= 64) the formats carry row * 128 offsets and the tile
+    row capacity follows the [rows x 32] + [rows x rs] shared-memory footprint."""
+    from pyliger_b200 import blocked
+    from pyliger_b200.engine import DeviceCSR
+    rng = np.random.default_rng(8)
+    g, k, kp = 211, 37, 40
+    mats = [sps.random(n, g, density=0.15, random_state=60 + i, format="csr") for i, n in enumerate((190, 44))]
+    X = DeviceCSR(mats, torch.float32, torch.device("cpu"))
+    old = (blocked.SMEM_BUDGET, blocked.SPLIT_TILE)
+    blocked.SMEM_BUDGET, blocked.SPLIT_TILE = 60 * 160, True
+    try:
+        assert blocked.split_applies(kp, 4) and not blocked.split_applies(kp, 8) and not blocked.split_applies(32, 4)
+        assert blocked.row_bytes(kp, 4) == 128 and blocked.smem_row_bytes(kp, 4) == 160
+        assert blocked.smem_row_bytes(48, 4) == 192 and blocked.smem_row_bytes(64, 4) == 256
+        p1 = blocked.build_pass1(X, kp, 4, n_sms=5)
+        p2 = blocked.build_pass2(X, kp, 4, n_sms=5)
+    finally:
+        blocked.SMEM_BUDGET, blocked.SPLIT_TILE = old
+    assert p1.split and p2.split and p1.max_tile_rows <= 60 and p2.max_tile_rows <= 60
+    Mt = rng.uniform(0, 1, (2 * g, kp)); Mt[:, k:] = 0
+    H = rng.uniform(0, 1, (X.n_own_total, kp)); H[:, k:] = 0
+    R = np.zeros((X.n_own_total, kp)); St = np.zeros((2 * g, k)); gram = np.zeros((2, k, k))
+    _emulate_blocked(p1, Mt, kp, R, k, row_bytes=128)
+    _emulate_blocked(p2, H, kp, St, k, gram, row_bytes=128)
+    for s_, m in enumerate(mats):
+        o0, o1 = X.own_off[s_], X.own_off[s_ + 1]
+        np.testing.assert_allclose(R[o0:o1, :k], m @ Mt[s_ * g:(s_ + 1) * g, :k], rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(St[s_ * g:(s_ + 1) * g], m.T @ H[o0:o1, :k], rtol=1e-5, atol=1e-5)
 
 
 def _emulate_tc(tp, dense, k, out):
