@@ -117,6 +117,12 @@ int32_t inmf_blocked_split_f32(const int64_t* work, int32_t nwork, const int64_t
                                const float* dense, int32_t kp, float* out, int64_t ldo, int32_t k,
                                int32_t max_tile_rows, double* gram_out, void* stream);
 
+/* Same contract and the same formats as inmf_blocked_spmm_f32 for kp == 32: 4 lanes per non-zero with 8 factors each
+ * (two bank-swizzled 128-bit loads), 8 non-zeros per warp instruction. */
+int32_t inmf_blocked_wide_f32(const int64_t* work, int32_t nwork, const int64_t* ptr, const void* pairs,
+                              const float* dense, int32_t kp, float* out, int64_t ldo, int32_t k,
+                              int32_t max_tile_rows, double* gram_out, void* stream);
+
 /* Sufficient statistics of one pass over the cells (accumulating; caller zeroes):
  *   St[s] (g x k) += sum_q X[row(q), :]' H[q, :],   HtH[s] (k x k, double) += sum_q H[q,:]' H[q,:]
  * Replaces the dense X - H@W / vstack products of _iNMF_ANLS.py:144-152 and the H H', X H' of

@@ -83,6 +83,10 @@ def _device_format2(X, kp, esize, nb, cbs, blk_off):
 SPLIT_TILE = os.environ.get("INMF_SPLIT_TILE", "1") == "1"
 
 
+# Wide kernel for fp32, KP == 32 (inmf_blocked_wide_f32): same formats as the plain kernel, chosen at call time.
+WIDE_TILE = os.environ.get("INMF_WIDE_TILE", "0") == "1"
+
+
 def split_applies(kp, esize):
     return SPLIT_TILE and esize == 4 and 32 < kp <= 64
 

@@ -478,3 +478,176 @@ blocked_split_kernel(const int64_t* __restrict__ work, const int64_t* __restrict
     if (gram_seg >= 0 && gram_out != nullptr)
         split_gram_accumulate(tmain, trem, RS, tile_rows, k, gram_out + (size_t)gram_seg * k * k);
 }
+
+// =====================================================================================================
+// Wide variant for KP == 32 (fp32): 4 lanes per non-zero, 8 factors per lane (two 128-bit loads), 8 non-zeros per warp
+// instruction -- one pair load now feeds 16 FMAs per lane instead of 8, which halves the pair-delivery share of the
+// L1 data pipe (0.72 -> 0.36 of ~1.7 wavefronts per non-zero).  To keep every 8-lane phase of a 128-bit load
+// conflict free, even lane groups read the first 64 bytes of their row with the first load and the second 64 bytes
+// with the second one, odd groups the other way round (a phase = one even + one odd group = banks 0-15 + 16-31).
+// Same tile (row-major, 128-byte rows) and same pairs as the plain kernel.
+// =====================================================================================================
+__device__ __forceinline__ void wide_fma(const int2& p, uint32_t tA, uint32_t tB, float (&a)[4], float (&b)[4]) {
+    float m0, m1, m2, m3, n0, n1, n2, n3;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(m0), "=f"(m1), "=f"(m2), "=f"(m3)
+                 : "r"(tA + (uint32_t)p.x));
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(n0), "=f"(n1), "=f"(n2), "=f"(n3)
+                 : "r"(tB + (uint32_t)p.x));
+    const float v = __int_as_float(p.y);
+    a[0] = fmaf(v, m0, a[0]);
+    a[1] = fmaf(v, m1, a[1]);
+    a[2] = fmaf(v, m2, a[2]);
+    a[3] = fmaf(v, m3, a[3]);
+    b[0] = fmaf(v, n0, b[0]);
+    b[1] = fmaf(v, n1, b[1]);
+    b[2] = fmaf(v, n2, b[2]);
+    b[3] = fmaf(v, n3, b[3]);
+}
+
+// One warp, one sparse row of m pairs.  lane = (grp = lane / 4, sub = lane % 4).  On return the lanes of group 0 hold
+// the row sums: a[] = factors 4*sub .. 4*sub+3, b[] = factors 16 + 4*sub .. 16 + 4*sub + 3.
+__device__ __forceinline__ void warp_row_dot_wide(const int2* __restrict__ pl0, int m, int grp, uint32_t tA,
+                                                  uint32_t tB, float (&a)[4], float (&b)[4]) {
+    typedef PairTraits<float> PT;
+    constexpr int NPI = 8;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) a[u] = b[u] = 0.f;
+    const int2* __restrict__ pl = pl0 + grp;
+    const int nfull = m / NPI;
+    const int nq = (m + NPI - 1) / NPI;
+    int j = 0;
+    if (nfull >= BLK_U) {
+        int2 A[BLK_U], B[BLK_U];
+#pragma unroll
+        for (int t = 0; t < BLK_U; ++t) A[t] = PT::ld(pl + t * NPI);
+        while (true) {
+            const int2* __restrict__ pn = pl + (size_t)(j + BLK_U) * NPI;
+            if (j + 2 * BLK_U <= nfull) {
+#pragma unroll
+                for (int t = 0; t < BLK_U; ++t) B[t] = PT::ld(pn + t * NPI);
+#pragma unroll
+                for (int t = 0; t < BLK_U; ++t) wide_fma(A[t], tA, tB, a, b);
+                j += BLK_U;
+            } else {
+#pragma unroll
+                for (int t = 0; t < BLK_U; ++t) wide_fma(A[t], tA, tB, a, b);
+                j += BLK_U;
+                break;
+            }
+            const int2* __restrict__ pm = pl + (size_t)(j + BLK_U) * NPI;
+            if (j + 2 * BLK_U <= nfull) {
+#pragma unroll
+                for (int t = 0; t < BLK_U; ++t) A[t] = PT::ld(pm + t * NPI);
+#pragma unroll
+                for (int t = 0; t < BLK_U; ++t) wide_fma(B[t], tA, tB, a, b);
+                j += BLK_U;
+            } else {
+#pragma unroll
+                for (int t = 0; t < BLK_U; ++t) wide_fma(B[t], tA, tB, a, b);
+                j += BLK_U;
+                break;
+            }
+        }
+    }
+    {
+        int2 C[BLK_U];
+#pragma unroll
+        for (int t = 0; t < BLK_U; ++t) {
+            const int q = (j + t) * NPI + grp;
+            C[t] = ((j + t) < nq && q < m) ? PT::ld(pl0 + q) : PT::zero();
+        }
+#pragma unroll
+        for (int t = 0; t < BLK_U; ++t)
+            if (j + t < nq) wide_fma(C[t], tA, tB, a, b);
+    }
+    // odd groups hold the halves the other way round: fold them onto their even neighbours with a swap
+    {
+        float oa[4], ob[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            oa[u] = __shfl_down_sync(INMF_FULL_MASK, a[u], 4);
+            ob[u] = __shfl_down_sync(INMF_FULL_MASK, b[u], 4);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            a[u] += ob[u];
+            b[u] += oa[u];
+        }
+    }
+    // even groups 4, 6 onto 0, 2; then 2 onto 0 (only the lanes of group 0 are read afterwards)
+#pragma unroll
+    for (int d = 16; d >= 8; d >>= 1) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            a[u] += __shfl_down_sync(INMF_FULL_MASK, a[u], d);
+            b[u] += __shfl_down_sync(INMF_FULL_MASK, b[u], d);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(1024, 1)
+blocked_wide_kernel(const int64_t* __restrict__ work, const int64_t* __restrict__ ptr, const int2* __restrict__ pairs,
+                    const float* __restrict__ dense, float* __restrict__ out, int64_t ldo, int k,
+                    double* __restrict__ gram_out) {
+    constexpr int KP = 32;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+    float* tile = reinterpret_cast<float*>(smem_raw + 128);
+    const int64_t* wd = work + (size_t)blockIdx.x * INMF_WORK_FIELDS;
+    const int64_t ptr_base = wd[0], dense_row0 = wd[1];
+    const int tile_rows = (int)wd[2];
+    const int64_t row_begin = wd[3], row_end = wd[4], out_row_base = wd[5];
+    const int gram_seg = (int)wd[6];
+
+    if (threadIdx.x == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const size_t total = (size_t)tile_rows * KP * sizeof(float);
+        mbar_expect_tx(bar, (uint32_t)total);
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(dense + (size_t)dense_row0 * KP);
+        unsigned char* dst = reinterpret_cast<unsigned char*>(tile);
+        for (size_t off = 0; off < total; off += 32768) {
+            const size_t n = (total - off < 32768) ? (total - off) : 32768;
+            bulk_g2s(dst + off, src + off, (uint32_t)n, bar);
+        }
+    }
+    const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int grp = lane >> 2, sub = lane & 3, par = grp & 1;
+    const uint32_t tA = smem_u32(tile) + (uint32_t)((sub + 4 * par) * 16);
+    const uint32_t tB = smem_u32(tile) + (uint32_t)((sub + 4 * (1 - par)) * 16);
+    int64_t r = row_begin + warp;
+    int64_t beg = 0, end = 0;
+    if (r < row_end) {
+        beg = ptr[ptr_base + r];
+        end = ptr[ptr_base + r + 1];
+    }
+    mbar_wait(bar, 0);
+
+    while (r < row_end) {
+        const int64_t rn = r + nwarps;
+        int64_t nbeg = 0, nend = 0;
+        if (rn < row_end) {
+            nbeg = ptr[ptr_base + rn];
+            nend = ptr[ptr_base + rn + 1];
+        }
+        if (beg != end) {
+            float a[4], b[4];
+            warp_row_dot_wide(pairs + beg, (int)(end - beg), grp, tA, tB, a, b);
+            if (grp == 0) {  // group 0 is even: a = first half (factors 4*sub ..), b = second half (16 + 4*sub ..)
+                float* o = out + (out_row_base + r) * ldo + sub * 4;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (sub * 4 + u < k && a[u] != 0.f) atomicAdd(o + u, a[u]);
+                    if (16 + sub * 4 + u < k && b[u] != 0.f) atomicAdd(o + 16 + u, b[u]);
+                }
+            }
+        }
+        r = rn;
+        beg = nbeg;
+        end = nend;
+    }
+    if (gram_seg >= 0 && gram_out != nullptr)
+        tile_gram_accumulate<float>(tile, KP, tile_rows, k, gram_out + (size_t)gram_seg * k * k, 1.0);
+}

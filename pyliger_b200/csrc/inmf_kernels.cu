@@ -1217,6 +1217,26 @@ extern "C" int32_t inmf_blocked_split_f32(const int64_t* work, int32_t nwork, co
     return blocked_split_one<4>(work, nwork, ptr, pairs, dense, kp, out, ldo, k, max_tile_rows, gram_out, stream);
 }
 
+extern "C" int32_t inmf_blocked_wide_f32(const int64_t* work, int32_t nwork, const int64_t* ptr, const void* pairs,
+                                         const float* dense, int32_t kp, float* out, int64_t ldo, int32_t k,
+                                         int32_t max_tile_rows, double* gram_out, void* stream) {
+    INMF_REQUIRE(kp == 32 && k >= 1 && k <= 32, "the wide kernel is for kp == 32");
+    INMF_REQUIRE(ldo >= k, "ldo must be >= k");
+    if (nwork <= 0) return 0;
+    const size_t smem = 128 + (size_t)max_tile_rows * 32 * sizeof(float);
+    INMF_REQUIRE(smem <= 227 * 1024, "dense tile does not fit in shared memory");
+    static bool attr_done = false;
+    if (!attr_done) {
+        INMF_CUDA_CHECK(cudaFuncSetAttribute(blocked_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             227 * 1024));
+        attr_done = true;
+    }
+    blocked_wide_kernel<<<(unsigned)nwork, 1024, smem, (cudaStream_t)stream>>>(
+        work, ptr, reinterpret_cast<const int2*>(pairs), dense, out, ldo, k, gram_out);
+    INMF_LAUNCH_CHECK();
+    return 0;
+}
+
 // =================================================================================================
 // tcgen05 diagnostics
 // =================================================================================================

@@ -300,6 +300,8 @@ class InmfEngine(object):
     def _blocked(self, p, work, nwork, dense, out, ldo, gram):
         """One tiled pass (out += X_blocked * dense tile): plain or split-tile kernel, as the format was built."""
         name, sfx = ("inmf_blocked_split_f32", "") if p.split else ("inmf_blocked_spmm", self.sfx)
+        if blocked.WIDE_TILE and not p.split and self.sfx == "f32" and self.ldm == 32:
+            name, sfx = "inmf_blocked_wide_f32", ""  # same formats, 8 factors per lane
         _lib.call(name, sfx, work, nwork, p.ptr, p.pairs, dense, self.ldm, out, ldo, self.k, p.max_tile_rows, gram,
                   _stream())
 

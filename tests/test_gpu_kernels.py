@@ -325,3 +325,41 @@ def test_split_tile_passes_match_plain_passes(dev, k):
     assert float(R[:, k:].abs().max().item() if R.shape[1] > k else 0.0) == 0.0  # pad columns stay zero
     np.testing.assert_allclose(objs, res[False][3], rtol=2e-6)
     assert relerr(Hf.cpu().numpy(), res[False][4].cpu().numpy()) < 1e-3
+
+
+@pytest.mark.parametrize("k", [29, 30, 32])
+def test_wide_tile_passes_match_plain_passes(dev, k):
+    """inmf_blocked_wide_f32 (KP = 32: 8 factors per lane, bank-swizzled halves) against numpy and the plain kernel."""
+    from pyliger_b200 import blocked
+    lam = 2.0
+    mats, W, V, H = _rand_problem(100 + k, ns=(333, 170), g=120, k=k, density=0.3)
+    old = (blocked.SMEM_BUDGET, blocked.WIDE_TILE)
+    blocked.SMEM_BUDGET = 50 * 128  # 50 tile rows: several gene and cell blocks
+    res = {}
+    try:
+        for wide in (False, True):
+            blocked.WIDE_TILE = wide
+            eng = _engine(mats, k, lam, "float32")
+            assert eng.ldm == 32
+            eng.set_als_state(W, V, H)
+            eng.prep()
+            eng.stats()
+            St, HtH = eng.St.clone(), eng.HtH.clone()
+            eng.rhs_H()
+            R = eng.H.clone()
+            eng.set_als_state(W, V, H)
+            objs = [float(eng.initial_objective())] + [float(eng.als_iteration(warm=i > 0).item()) for i in range(3)]
+            res[wide] = (St, HtH, R, objs, eng.H.clone())
+    finally:
+        blocked.SMEM_BUDGET, blocked.WIDE_TILE = old
+    St, HtH, R, objs, Hf = res[True]
+    off = 0
+    for i in range(len(mats)):
+        n = mats[i].shape[0]
+        assert relerr(St[i].cpu().numpy(), np.asarray(mats[i].T.dot(H[i]))) < 5e-6
+        assert relerr(HtH[i].cpu().numpy(), H[i].T @ H[i]) < 5e-6
+        assert relerr(R[off:off + n, :k].cpu().numpy(), np.asarray(mats[i].dot((W + V[i]).T))) < 5e-6
+        off += n
+    assert float(R[:, k:].abs().max().item() if R.shape[1] > k else 0.0) == 0.0
+    np.testing.assert_allclose(objs, res[False][3], rtol=2e-6)
+    assert relerr(Hf.cpu().numpy(), res[False][4].cpu().numpy()) < 1e-3
