@@ -11,7 +11,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT, PROF = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
-OURS = re.compile(r"blocked_spmm_kernel|bpp_kernel|ginv_kernel|rhs_[vw]_kernel|prep_kernel|objective_kernel|"
+OURS = re.compile(r"blocked_(spmm|split|wide)_kernel|bpp_kernel|ginv_kernel|rhs_[vw]_kernel|prep_kernel|objective_kernel|"
                   r"sqnorm_kernel|combine_g_kernel|blockfmt[12]_kernel|mt19937_uniform_kernel|gram_rows_kernel|"
                   r"stats_scatter_kernel|spmm_rows_kernel|hals_(inc_)?kernel|update_ab_kernel|normalize_rows_kernel|"
                   r"select_(count|scale)_kernel|tc_(pass|relayout)_kernel")
@@ -58,7 +58,7 @@ def launches():
 def full():
     body = subprocess.run([sys.executable, os.path.join(ROOT, "benchmarks", "ncu_summary.py"),
                            os.path.join(OUT, "prof_final.ncu-rep")], capture_output=True, text=True).stdout
-    hdr = ("# Round 1 (final build): ncu --set full --clock-control none --import-source on -k regex:blocked_spmm|bpp_kernel "
+    hdr = ("# Round 1 (final build): ncu --set full --clock-control none --import-source on -k regex:blocked_|bpp_kernel "
            "-s 20 -c 5 -- python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e\n"
            "# launches in order: bpp(W) of the previous iteration, blocked pass 1, bpp(H) [complement-set build <float, 1>], "
            "blocked pass 2, bpp(V)\n"
@@ -67,9 +67,9 @@ def full():
            "# reading: the blocked passes sit on the L1/shared-memory data pipe (l1tex 89-93 %, DRAM 14-15 %); bpp(H) is "
            "issue bound\n")
     open(os.path.join(PROF, "r1_ncu_full_summary.txt"), "w").write(hdr + body)
-    vals = re.findall(r"== void (\S+?)<.*?\n\s+time=.*?dram_rd=([\d.]+)Mbyte\s+dram_wr=([\d.]+)Mbyte", body)
-    label = {"spmm": "blocked_spmm_kernel<float,8> (pass 1)", "bpp_H": "bpp_kernel<float,true> (H solve)",
-             "stats": "blocked_spmm_kernel<float,8> (pass 2)"}
+    vals = re.findall(r"== (?:void )?(\w+).*?\n\s+time=.*?dram_rd=([\d.]+)Mbyte\s+dram_wr=([\d.]+)Mbyte", body)
+    label = {"spmm": "blocked_wide_kernel (pass 1)", "bpp_H": "bpp_kernel<float,true> (H solve)",
+             "stats": "blocked_wide_kernel (pass 2)"}
     d = {"source": "ncu --set full --clock-control none, gpurun_out/prof_final.ncu-rep (summarised in "
                    "profiles/r1_ncu_full_summary.txt); C2 workload, fp32, one B200; dram__bytes_read.sum + "
                    "dram__bytes_write.sum per launch", "kernels": {}}
