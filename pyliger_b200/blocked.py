@@ -379,32 +379,53 @@ def build_pass1_resident(X, kp, esize):
 
 
 def window_work(X, NB, gbs, plan, pieces):
-    """Work lists [steps][items][8] for the row windows of ``plan`` (the seg_desc array of online_windows):
-    window q -> row (win_start + q) % n of dataset s lands in output row out_off + q."""
+    """Work lists [steps][items][8] (+ valid items per step) for the row windows of ``plan`` (the seg_desc array of
+    online_windows): window position q -> row (win_start + q) % n of dataset s lands in output row out_off + q.
+    Every window is cut into ``pieces`` row ranges (x 2 where it wraps around the end of the dataset) per gene block;
+    built with array operations for all steps at once (it sits on the critical path of online_iNMF's set-up)."""
     g, N = X.g, X.N
     steps = plan.shape[0]
-    items = N * NB * pieces * 2  # every window piece may wrap once
-    work = np.zeros((steps, items, WORK_FIELDS), dtype=np.int64)
-    work[:, :, 6] = -1
-    counts = np.zeros(steps, dtype=np.int64)
-    for t in range(steps):
-        it = 0
-        for s in range(N):
-            out_off, win_start, n = int(plan[t, s, 0]), int(plan[t, s, 2]), int(plan[t, s, 3])
-            count = int(plan[t, s + 1, 0]) - out_off
-            per = -(-count // pieces) if count else 0
-            for b in range(NB):
-                rows_b = min(gbs, g - b * gbs)
-                pbase = NB * int(X.row_base[s]) + b * X.n_local[s]
-                for q0 in range(0, count, max(per, 1)):
-                    q1 = min(count, q0 + per)
-                    lo = (win_start + q0) % n
-                    hi = lo + (q1 - q0)
-                    # piece [lo, hi) possibly wrapping at n
-                    for a, e, obase in ((lo, min(hi, n), out_off + q0 - lo),
-                                        (0, max(hi - n, 0), out_off + q0 + (n - lo))):
-                        if e > a:
-                            work[t, it] = [pbase, s * g + b * gbs, rows_b, a, e, obase, -1, 0]
-                            it += 1
-        counts[t] = it
+    P = max(1, int(pieces))
+    out_off = plan[:, :N, 0].astype(np.int64)                       # [T, N]
+    win_start = plan[:, :N, 2].astype(np.int64)
+    n = np.maximum(plan[:, :N, 3].astype(np.int64), 1)
+    count = plan[:, 1:N + 1, 0].astype(np.int64) - out_off          # [T, N]
+    per = np.maximum(-(-count // P), 1)
+    j = np.arange(P, dtype=np.int64)[None, None, :]
+    q0 = j * per[:, :, None]                                        # [T, N, P]
+    q1 = np.minimum(count[:, :, None], q0 + per[:, :, None])
+    live = q0 < count[:, :, None]
+    lo = (win_start[:, :, None] + q0) % n[:, :, None]
+    hi = lo + (q1 - q0)
+    nn = n[:, :, None]
+    # part 0: [lo, min(hi, n)) ; part 1 (wrapped): [0, hi - n)
+    a = np.stack([lo, np.zeros_like(lo)], axis=-1)                  # [T, N, P, 2]
+    e = np.stack([np.minimum(hi, nn), np.maximum(hi - nn, 0)], axis=-1)
+    ob = np.stack([out_off[:, :, None] + q0 - lo, out_off[:, :, None] + q0 + (nn - lo)], axis=-1)
+    valid = (e > a) & live[..., None]
+    b = np.arange(NB, dtype=np.int64)
+    rows_b = np.minimum(gbs, g - b * gbs)                           # [NB]
+    row_base = np.asarray(X.row_base[:N], dtype=np.int64)
+    n_local = np.asarray(X.n_local, dtype=np.int64)
+    pbase = NB * row_base[:, None] + b[None, :] * n_local[:, None]  # [N, NB]
+    drow0 = np.arange(N, dtype=np.int64)[:, None] * g + b[None, :] * gbs
+    shape = (steps, N, NB, P, 2)
+    work = np.zeros(shape + (WORK_FIELDS,), dtype=np.int64)
+    work[..., 0] = pbase[None, :, :, None, None]
+    work[..., 1] = drow0[None, :, :, None, None]
+    work[..., 2] = rows_b[None, None, :, None, None]
+    work[..., 3] = a[:, :, None, :, :]
+    work[..., 4] = e[:, :, None, :, :]
+    work[..., 5] = ob[:, :, None, :, :]
+    work[..., 6] = -1
+    ok = np.broadcast_to(valid[:, :, None, :, :] & (rows_b > 0)[None, None, :, None, None], shape)
+    items = N * NB * P * 2
+    work = work.reshape(steps, items, WORK_FIELDS)
+    ok = ok.reshape(steps, items)
+    order = np.argsort(~ok, axis=1, kind="stable")                  # valid items first, original order kept
+    work = np.take_along_axis(work, order[:, :, None], axis=1)
+    counts = ok.sum(axis=1).astype(np.int64)
+    pad = np.arange(items)[None, :] >= counts[:, None]
+    work[pad] = 0
+    work[pad, 6] = -1
     return work, counts

@@ -413,3 +413,44 @@ def test_anndata_like_slicing_and_raw():
     assert c.shape == (6, 7) and c.obsm["H"].shape == (6, 2) and len(c.obs) == 6
     lig = liger_from_raw([X, X[:5]], ["a", "b"])
     assert lig.num_samples == 2 and lig.adata_list[1].shape == (5, 7) and lig.adata_list[0].layers == {}
+
+
+def _window_work_loop(X, NB, gbs, plan, pieces):
+    """Straightforward statement of blocked.window_work (one Python iteration per work item)."""
+    g, N = X.g, X.N
+    out = []
+    for t in range(plan.shape[0]):
+        items = []
+        for s in range(N):
+            out_off, win_start, n = int(plan[t, s, 0]), int(plan[t, s, 2]), int(plan[t, s, 3])
+            count = int(plan[t, s + 1, 0]) - out_off
+            per = max(-(-count // pieces), 1)
+            for b in range(NB):
+                rows_b = min(gbs, g - b * gbs)
+                pbase = NB * int(X.row_base[s]) + b * X.n_local[s]
+                for q0 in range(0, count, per):
+                    q1 = min(count, q0 + per)
+                    lo = (win_start + q0) % n
+                    hi = lo + (q1 - q0)
+                    for a, e, obase in ((lo, min(hi, n), out_off + q0 - lo), (0, max(hi - n, 0), out_off + q0 + (n - lo))):
+                        if e > a:
+                            items.append([pbase, s * g + b * gbs, rows_b, a, e, obase, -1, 0])
+        out.append(items)
+    return out
+
+
+@pytest.mark.parametrize("pieces", [1, 3, 4])
+def test_window_work_vectorised_equals_loop(pieces):
+    from pyliger_b200 import blocked
+    from pyliger_b200.engine import DeviceCSR, online_windows
+    mats = [sps.random(n, 61, density=0.2, random_state=5 + i, format="csr") for i, n in enumerate((131, 58, 17))]
+    X = DeviceCSR(mats, torch.float64, torch.device("cpu"), replicate=True)
+    mbs = [40, 18, 5]
+    for sub in ([(0, 40), (0, 18), (0, 5)], [(13, 27), (6, 12), (2, 4)], [(0, 40), (18, 18), (0, 5)]):
+        plan = online_windows(11, mbs, sub, X.n_global, X.row_base)
+        work, counts = blocked.window_work(X, 3, 21, plan, pieces)
+        ref = _window_work_loop(X, 3, 21, plan, pieces)
+        for t in range(plan.shape[0]):
+            assert counts[t] == len(ref[t])
+            assert work[t, :counts[t]].tolist() == ref[t]
+            assert (work[t, counts[t]:, 3] == work[t, counts[t]:, 4]).all()  # padding items are empty
