@@ -122,7 +122,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     from pyliger_b200.synth import make_datasets
-    cfg = C2
+    cfg = C2 if getattr(args, "config", "C2") == "C2" else C4
     t0 = time.time()
     sample = make_datasets([CPU_SAMPLE_CELLS] * cfg["datasets"], cfg["genes"], cfg["k"], cfg["density"],
                            structured=False, seed0=1000)
@@ -134,8 +134,9 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "optimize_ALS cell-iterations/s", "value": value, "unit": "cell-iters/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * s_per_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "C2 optimize_ALS 4 datasets x 50k cells x 3k genes, k=30, lambda=5 (CPU: bounded sample)",
-                   "sample": desc},
+        "config": {"workload": "%s optimize_ALS %d datasets x %dk cells x %dk genes, k=%d, lambda=%g (CPU: bounded sample)" % (
+            getattr(args, "config", "C2"), cfg["datasets"], cfg["cells_per_dataset"] // 1000, cfg["genes"] // 1000, cfg["k"],
+            cfg["value_lambda"]), "sample": desc},
         "cpu_baseline": {"value": value, "unit": "cell-iters/s", "cores": cpu_threads(), "kind": "port", "sample": desc},
         "e2e": {"value": value, "unit": "cell-iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
