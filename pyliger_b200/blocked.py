@@ -6,8 +6,6 @@ arithmetic passes over these structures are libinmf_b200.so kernels).
 pass 1  "gene-blocked CSR":  pairs ordered by (dataset, gene block, cell, gene);  tile = rows of Mt
 pass 2  "cell-blocked CSC":  pairs ordered by (dataset, cell block, gene, cell);  tile = rows of H
 """
-import os
-
 import numpy as np
 import torch
 
@@ -77,15 +75,13 @@ def _device_format2(X, kp, esize, nb, cbs, blk_off):
     return ptr, pairs
 
 
-# Split-tile kernel (csrc/blocked.cuh, inmf_blocked_split_f32) for fp32 and 32 < KP <= 64: [rows x 32] + [rows x rs]
-# tile, pairs carry row * 128.  Measured at C4 (k = 40): pass 1 2.43 -> 1.98 ms, pass 2 2.75 -> 2.23 ms per 480k cells;
-# INMF_SPLIT_TILE=0 selects the plain kernel.
-SPLIT_TILE = os.environ.get("INMF_SPLIT_TILE", "1") == "1"
-
-
-# Wide kernel for fp32, KP == 32 (inmf_blocked_wide_f32): same formats as the plain kernel, chosen at call time.
-# Measured at C2: pass 1 0.366 -> 0.340 ms, pass 2 0.364 -> 0.348 ms; INMF_WIDE_TILE=0 selects the plain kernel.
-WIDE_TILE = os.environ.get("INMF_WIDE_TILE", "1") == "1"
+# Kernel variants of the row-ordered format (module attributes, not environment switches; tests flip them to compare
+# the variants).  Split-tile kernel (csrc/blocked.cuh, inmf_blocked_split_f32) for fp32 and 32 < KP <= 64: [rows x 32] +
+# [rows x rs] tile, pairs carry row * 128.  Wide kernel for fp32, KP == 32 (inmf_blocked_wide_f32): same formats as the
+# plain kernel, chosen at call time.  The full passes of fp32 runs use the sliced format below (build_sell) instead.
+SPLIT_TILE = True
+WIDE_TILE = True
+SELL = True  # sliced (SELL-8) passes for fp32 full passes (csrc/sell.cuh)
 
 
 def split_applies(kp, esize):
@@ -122,7 +118,73 @@ def _pack_pairs(idx_local, vals):
 
 
 class BlockedPass(object):
-    __slots__ = ("work", "nwork", "ptr", "pairs", "max_tile_rows", "split")
+    __slots__ = ("work", "nwork", "ptr", "pairs", "max_tile_rows", "split", "work_host")
+
+
+class SellPass(object):
+    """Sliced form of a BlockedPass (csrc/sell.cuh): rows of every work item sorted by length, 8 per slice."""
+    __slots__ = ("work", "nwork", "slice_ptr", "rowid", "pairs4", "max_tile_rows", "nnz", "padded")
+
+
+def build_sell(bp, kp):
+    """Sliced copy of the row-ordered blocked format ``bp`` (fp32).  Index plumbing (sort of the rows of every work item
+    by length, slice table, prefix sums) is torch; the data movement is inmf_sell_fill_f32."""
+    dev = bp.ptr.device
+    W = bp.work_host[:bp.nwork]
+    sp = SellPass()
+    sp.max_tile_rows = bp.max_tile_rows
+    sp.nwork = bp.nwork
+    sp.nnz = int(bp.pairs.shape[0])
+    if bp.nwork == 0:
+        sp.work = torch.zeros(1, WORK_FIELDS, dtype=torch.int64, device=dev)
+        sp.slice_ptr = torch.zeros(1, dtype=torch.int64, device=dev)
+        sp.rowid = torch.zeros(8, dtype=torch.int32, device=dev)
+        sp.pairs4 = torch.zeros(1, 4, dtype=torch.int32, device=dev)
+        sp.padded = 0
+        return sp
+    lo = W[:, 0] + W[:, 3]
+    nrows = W[:, 4] - W[:, 3]
+    ns = (nrows + 7) // 8
+    start = np.concatenate([[0], np.cumsum(nrows)])
+    slice_off = np.concatenate([[0], np.cumsum(ns)])
+    total_rows, total_slices = int(start[-1]), int(slice_off[-1])
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int64)).to(dev)
+    wid = torch.repeat_interleave(torch.arange(bp.nwork, device=dev), t(nrows))
+    q = torch.arange(total_rows, device=dev) - t(start[:-1])[wid]          # position inside the work item
+    ridx = q + t(lo)[wid]                                                   # row of the blocked format (ptr index)
+    length = bp.ptr[ridx + 1] - bp.ptr[ridx]
+    big = 1 << 22
+    if total_rows and int(length.max().item()) >= big:
+        raise ValueError("sparse row too long for the sliced format")
+    order = torch.sort(wid * big + (big - 1 - length), stable=True)[1]     # by work item, longest row first
+    slot = t(slice_off[:-1])[wid] * 8 + q
+    slice_rows = torch.full((total_slices * 8,), -1, dtype=torch.int64, device=dev)
+    slice_rows[slot] = ridx[order]
+    slice_len = torch.zeros(total_slices * 8, dtype=torch.int64, device=dev)
+    slice_len[slot] = length[order]
+    L2 = (slice_len.view(total_slices, 8).max(dim=1)[0] + 1) // 2           # 128-bit units (two steps) per row
+    sp.slice_ptr = torch.zeros(total_slices + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(8 * L2, 0, out=sp.slice_ptr[1:])
+    n4 = int(sp.slice_ptr[-1].item())
+    sp.padded = 2 * n4
+    swid = torch.repeat_interleave(torch.arange(bp.nwork, device=dev), t(ns))
+    rel = slice_rows.view(total_slices, 8) - t(W[:, 0])[swid][:, None]
+    sp.rowid = torch.where(slice_rows.view(total_slices, 8) >= 0, rel, torch.full_like(rel, -1)).to(torch.int32).contiguous()
+    sp.pairs4 = torch.empty(max(n4, 1), 4, dtype=torch.int32, device=dev)
+    _lib.call("inmf_sell_fill_f32", "", bp.ptr, bp.pairs, slice_rows, sp.slice_ptr, total_slices, sp.pairs4, _stream(dev))
+    work = np.zeros((bp.nwork, WORK_FIELDS), dtype=np.int64)
+    work[:, 0] = slice_off[:-1]
+    work[:, 1] = slice_off[1:]
+    work[:, 2] = W[:, 1]
+    work[:, 3] = W[:, 2]
+    work[:, 4] = W[:, 5]
+    work[:, 5] = W[:, 6]
+    sp.work = torch.from_numpy(work).to(dev)
+    return sp
+
+
+def sell_applies(kp, esize):
+    return SELL and esize == 4 and 32 <= kp <= 64
 
 
 def _own_nnz(X):
@@ -189,7 +251,8 @@ def build_pass1(X, kp, esize, n_sms):
                 work.append([NB * int(X.own_off[s]) + b * n, s * g + b * gbs, rows_b, lo, min(n, lo + per),
                              int(X.own_off[s]), -1, 0])
     bp.nwork = len(work)
-    bp.work = torch.tensor(work if work else [[0] * WORK_FIELDS], dtype=torch.int64, device=dev)
+    bp.work_host = np.asarray(work if work else [[0] * WORK_FIELDS], dtype=np.int64)
+    bp.work = torch.from_numpy(bp.work_host).to(dev)
     bp.max_tile_rows = min(gbs, g)
     return bp
 
@@ -238,7 +301,8 @@ def build_pass2(X, kp, esize, n_sms):
                 work.append([g * (int(blk_off[s]) + b), int(X.own_off[s]) + b * cbs[s], rows_b, lo, min(g, lo + per),
                              s * g, s if ci == 0 else -1, 0])
     bp.nwork = len(work)
-    bp.work = torch.tensor(work if work else [[0] * WORK_FIELDS], dtype=torch.int64, device=dev)
+    bp.work_host = np.asarray(work if work else [[0] * WORK_FIELDS], dtype=np.int64)
+    bp.work = torch.from_numpy(bp.work_host).to(dev)
     bp.max_tile_rows = max(cbs) if cbs else 1
     return bp
 
@@ -373,7 +437,7 @@ def build_pass1_resident(X, kp, esize):
     bp.split = split_applies(kp, esize)
     bp.pairs = _pack_pairs((col - gb * gbs)[order] * row_bytes(kp, esize), val[order])
     bp.ptr = ptr
-    bp.work, bp.nwork = None, 0
+    bp.work, bp.nwork, bp.work_host = None, 0, None
     bp.max_tile_rows = min(gbs, g)
     return bp, NB, gbs
 

@@ -36,16 +36,35 @@ extern long long g_inmf_launches;  // kernels launched by this library (host-sid
         INMF_CUDA_CHECK(cudaGetLastError());     \
     } while (0)
 
-static inline int inmf_num_sms() {
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess ||
-            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
-            sms = 148;
-    }
-    return sms;
+#define INMF_MAX_DEVICES 64
+static inline int inmf_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= INMF_MAX_DEVICES) dev = 0;
+    return dev;
 }
+
+// SM count of the CURRENT device (a process may drive several GPUs through the Python API's device= argument).
+static inline int inmf_num_sms() {
+    static int sms[INMF_MAX_DEVICES];
+    const int dev = inmf_device();
+    if (sms[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        sms[dev] = n;
+    }
+    return sms[dev];
+}
+
+// Opt in to more than 48 KB of dynamic shared memory, once per (kernel instantiation, device).
+#define INMF_OPTIN_SMEM(kernel, bytes)                                                                     \
+    do {                                                                                                   \
+        static bool done_[INMF_MAX_DEVICES];                                                               \
+        const int d_ = inmf_device();                                                                      \
+        if (!done_[d_]) {                                                                                  \
+            INMF_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)); \
+            done_[d_] = true;                                                                              \
+        }                                                                                                  \
+    } while (0)
 
 template <typename T>
 __device__ __forceinline__ T inmf_rsqrt(T x);

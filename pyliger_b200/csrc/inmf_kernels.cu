@@ -3,6 +3,7 @@
 #include "inmf_common.cuh"
 #include "bpp.cuh"
 #include "blocked.cuh"
+#include "sell.cuh"
 #include "tc_common.cuh"
 #include "tc_pass.cuh"
 
@@ -173,15 +174,8 @@ static int32_t bpp_launch(const double* G, const T* R, int64_t ldr, T* X, int64_
     while (nwarps > 1 && goff * sizeof(T) + nwarps * per_warp > 64 * 1024) nwarps >>= 1;
     const size_t smem = goff * sizeof(T) + nwarps * per_warp;
     INMF_REQUIRE(smem <= 227 * 1024, "shared memory budget exceeded");
-    static bool attr_done[2] = {false, false};
-    const int ti = sizeof(T) == 8;
-    if (!attr_done[ti]) {
-        INMF_CUDA_CHECK(cudaFuncSetAttribute(bpp_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             227 * 1024));
-        INMF_CUDA_CHECK(cudaFuncSetAttribute(bpp_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             227 * 1024));
-        attr_done[ti] = true;
-    }
+    INMF_OPTIN_SMEM((bpp_kernel<T, false>), 227 * 1024);
+    INMF_OPTIN_SMEM((bpp_kernel<T, true>), 227 * 1024);
     // Grid: about two waves of resident CTAs over ALL segments, each warp striding over its share of the columns,
     // so that the per-CTA staging of G (and G^-1) into shared memory is amortised over many columns.
     int64_t blocks = (max_seg_cols + nwarps - 1) / nwarps;
@@ -273,13 +267,7 @@ static int32_t prep_launch(const T* Wt, const T* Vt, T* Mt, int64_t ldm, double*
     int64_t tiles = (g + GRAM_TILE_ROWS - 1) / GRAM_TILE_ROWS;
     if (tiles > 1024) tiles = 1024;
     const size_t smem = 2 * (size_t)GRAM_TILE_ROWS * ldm * sizeof(T);
-    static bool attr_done[2] = {false, false};
-    const int ti = sizeof(T) == 8;
-    if (!attr_done[ti]) {
-        INMF_CUDA_CHECK(cudaFuncSetAttribute(prep_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             100 * 1024));
-        attr_done[ti] = true;
-    }
+    INMF_OPTIN_SMEM((prep_kernel<T>), 100 * 1024);
     prep_kernel<T><<<dim3((unsigned)tiles, (unsigned)nseg), 256, smem, st>>>(Wt, Vt, Mt, ldm, Gwv, Gvv, g, k);
     INMF_LAUNCH_CHECK();
     const int n = nseg * k * k;
@@ -1016,13 +1004,7 @@ static int32_t hals_launch(const double* A, const T* B, T* Wt, T* Vt, double lam
             while (nw > 1 && shared_bytes + nw * per_warp > 220 * 1024) nw >>= 1;
             const size_t smem_inc = shared_bytes + nw * per_warp;
             if (smem_inc <= 227 * 1024) {
-                static bool inc_attr[2] = {false, false};
-                const int tix = sizeof(T) == 8;
-                if (!inc_attr[tix]) {
-                    INMF_CUDA_CHECK(cudaFuncSetAttribute(hals_inc_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                         227 * 1024));
-                    inc_attr[tix] = true;
-                }
+                INMF_OPTIN_SMEM((hals_inc_kernel<T>), 227 * 1024);
                 int64_t blocks = (g + nw - 1) / nw;
                 int per_sm = (int)((220 * 1024) / smem_inc);  // persistent: the A_i staging is paid once per CTA
                 if (per_sm < 1) per_sm = 1;
@@ -1042,17 +1024,8 @@ static int32_t hals_launch(const double* A, const T* B, T* Wt, T* Vt, double lam
     while (nwarps > 1 && nwarps * per_warp > budget) nwarps >>= 1;
     const size_t smem = (a_smem ? a_bytes : 0) + nwarps * per_warp;
     INMF_REQUIRE(smem <= 227 * 1024, "too many datasets for the HALS shared-memory staging");
-    static bool attr_done[2][2] = {{false, false}, {false, false}};
-    const int ti = sizeof(T) == 8;
-    if (!attr_done[ti][a_smem]) {
-        if (a_smem)
-            INMF_CUDA_CHECK(cudaFuncSetAttribute(hals_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 227 * 1024));
-        else
-            INMF_CUDA_CHECK(cudaFuncSetAttribute(hals_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 227 * 1024));
-        attr_done[ti][a_smem] = true;
-    }
+    INMF_OPTIN_SMEM((hals_kernel<T, true>), 227 * 1024);
+    INMF_OPTIN_SMEM((hals_kernel<T, false>), 227 * 1024);
     int64_t blocks = (g + nwarps - 1) / nwarps;
     if (blocks > inmf_num_sms() * 8) blocks = inmf_num_sms() * 8;
     if (a_smem)
@@ -1136,12 +1109,7 @@ template <typename T, int LPN_T>
 static int32_t blocked_launch_one(const int64_t* work, int32_t nwork, const int64_t* ptr, const void* pairs,
                                   const T* dense, int32_t kp, T* out, int64_t ldo, int32_t k, size_t smem,
                                   double* gram_out, void* stream) {
-    static bool attr_done = false;
-    if (!attr_done) {
-        INMF_CUDA_CHECK(cudaFuncSetAttribute(blocked_spmm_kernel<T, LPN_T>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_done = true;
-    }
+    INMF_OPTIN_SMEM((blocked_spmm_kernel<T, LPN_T>), 227 * 1024);
     blocked_spmm_kernel<T, LPN_T><<<(unsigned)nwork, 1024, smem, (cudaStream_t)stream>>>(
         work, ptr, reinterpret_cast<const typename PairTraits<T>::Pair*>(pairs), dense, kp, out, ldo, k, gram_out);
     INMF_LAUNCH_CHECK();
@@ -1193,12 +1161,7 @@ static int32_t blocked_split_one(const int64_t* work, int32_t nwork, const int64
                                  int32_t max_tile_rows, double* gram_out, void* stream) {
     const size_t smem = 128 + (size_t)max_tile_rows * (32 + 8 * RL) * sizeof(float);
     INMF_REQUIRE(smem <= 227 * 1024, "dense tile does not fit in shared memory");
-    static bool attr_done = false;
-    if (!attr_done) {
-        INMF_CUDA_CHECK(cudaFuncSetAttribute(blocked_split_kernel<RL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             227 * 1024));
-        attr_done = true;
-    }
+    INMF_OPTIN_SMEM((blocked_split_kernel<RL>), 227 * 1024);
     blocked_split_kernel<RL><<<(unsigned)nwork, 1024, smem, (cudaStream_t)stream>>>(
         work, ptr, reinterpret_cast<const int2*>(pairs), dense, kp, out, ldo, k, max_tile_rows, gram_out);
     INMF_LAUNCH_CHECK();
@@ -1225,14 +1188,55 @@ extern "C" int32_t inmf_blocked_wide_f32(const int64_t* work, int32_t nwork, con
     if (nwork <= 0) return 0;
     const size_t smem = 128 + (size_t)max_tile_rows * 32 * sizeof(float);
     INMF_REQUIRE(smem <= 227 * 1024, "dense tile does not fit in shared memory");
-    static bool attr_done = false;
-    if (!attr_done) {
-        INMF_CUDA_CHECK(cudaFuncSetAttribute(blocked_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             227 * 1024));
-        attr_done = true;
-    }
+    INMF_OPTIN_SMEM((blocked_wide_kernel), 227 * 1024);
     blocked_wide_kernel<<<(unsigned)nwork, 1024, smem, (cudaStream_t)stream>>>(
         work, ptr, reinterpret_cast<const int2*>(pairs), dense, out, ldo, k, gram_out);
+    INMF_LAUNCH_CHECK();
+    return 0;
+}
+
+// =================================================================================================
+// Sliced (SELL-8) passes (sell.cuh)
+// =================================================================================================
+template <int REM>
+static int32_t sell_pass_one(const int64_t* work, int32_t nwork, const int64_t* slice_ptr, const int32_t* rowid,
+                             const void* pairs4, const float* dense, int32_t kp, float* out, int64_t ldo, int32_t k,
+                             int32_t max_tile_rows, double* gram_out, void* stream) {
+    const size_t smem = 128 + (size_t)max_tile_rows * (32 + REM) * sizeof(float);
+    INMF_REQUIRE(smem <= 227 * 1024, "dense tile does not fit in shared memory");
+    INMF_OPTIN_SMEM((sell_pass_kernel<REM>), 227 * 1024);
+    sell_pass_kernel<REM><<<(unsigned)nwork, 1024, smem, (cudaStream_t)stream>>>(
+        work, slice_ptr, rowid, reinterpret_cast<const int4*>(pairs4), dense, kp, out, ldo, k, max_tile_rows, gram_out);
+    INMF_LAUNCH_CHECK();
+    return 0;
+}
+extern "C" int32_t inmf_sell_pass_f32(const int64_t* work, int32_t nwork, const int64_t* slice_ptr,
+                                      const int32_t* rowid, const void* pairs4, const float* dense, int32_t kp,
+                                      float* out, int64_t ldo, int32_t k, int32_t max_tile_rows, double* gram_out,
+                                      void* stream) {
+    INMF_REQUIRE(k >= 1 && k <= INMF_MAX_K, "k must be in [1, 64]");
+    INMF_REQUIRE(kp >= 32 && kp >= k && kp % 4 == 0 && kp <= 64, "kp must be a multiple of 4 in [max(k, 32), 64]");
+    INMF_REQUIRE(ldo >= k, "ldo must be >= k");
+    INMF_REQUIRE((reinterpret_cast<uintptr_t>(pairs4) & 15) == 0, "pairs4 must be 16-byte aligned");
+    if (nwork <= 0) return 0;
+    const int rem = kp - 32;
+#define INMF_SELL_ARGS work, nwork, slice_ptr, rowid, pairs4, dense, kp, out, ldo, k, max_tile_rows, gram_out, stream
+    if (rem == 0) return sell_pass_one<0>(INMF_SELL_ARGS);
+    if (rem <= 8) return sell_pass_one<8>(INMF_SELL_ARGS);
+    if (rem <= 16) return sell_pass_one<16>(INMF_SELL_ARGS);
+    return sell_pass_one<32>(INMF_SELL_ARGS);
+#undef INMF_SELL_ARGS
+}
+
+extern "C" int32_t inmf_sell_fill_f32(const int64_t* ptr, const void* pairs, const int64_t* slice_rows,
+                                      const int64_t* slice_ptr, int64_t nslices, void* pairs4, void* stream) {
+    if (nslices <= 0) return 0;
+    INMF_REQUIRE((reinterpret_cast<uintptr_t>(pairs4) & 15) == 0, "pairs4 must be 16-byte aligned");
+    int64_t blocks = (nslices + 7) / 8;
+    const int64_t cap = (int64_t)inmf_num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    sell_fill_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        ptr, reinterpret_cast<const int2*>(pairs), slice_rows, slice_ptr, nslices, reinterpret_cast<int4*>(pairs4));
     INMF_LAUNCH_CHECK();
     return 0;
 }
@@ -1244,11 +1248,7 @@ extern "C" int32_t inmf_tc_selftest(const float* A, const float* B, float* C, in
                                     void* stream) {
     INMF_REQUIRE(n >= 16 && n <= 64 && n % 16 == 0, "n must be 16, 32, 48 or 64");
     const size_t smem = 2 * TC_A_BYTES + 2 * TC_KC * 64 * 4 + 64;
-    static bool attr_done = false;
-    if (!attr_done) {
-        INMF_CUDA_CHECK(cudaFuncSetAttribute(tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_done = true;
-    }
+    INMF_OPTIN_SMEM((tc_selftest_kernel), 227 * 1024);
     tc_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(A, B, C, n, three_pass);
     INMF_LAUNCH_CHECK();
     return 0;
@@ -1282,11 +1282,7 @@ extern "C" int32_t inmf_tc_pass_f32(const int64_t* work, int32_t nwork, const in
     if (nwork <= 0) return 0;
     const TcSmemLayout L = tc_smem_layout(npad);
     INMF_REQUIRE(L.total + 1024 <= 227 * 1024, "shared memory budget exceeded");
-    static bool attr_done = false;
-    if (!attr_done) {
-        INMF_CUDA_CHECK(cudaFuncSetAttribute(tc_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_done = true;
-    }
+    INMF_OPTIN_SMEM((tc_pass_kernel), 227 * 1024);
     int grid = inmf_num_sms();
     if (max_ctas > 0 && max_ctas < grid) grid = max_ctas;
     if (grid > nwork) grid = nwork;
@@ -1482,17 +1478,8 @@ static int32_t blockfmt2_launch(int32_t fill, const int64_t* rowptr, const int32
     INMF_REQUIRE(smem <= 200 * 1024, "format-2 builder: W * genes counters exceed shared memory");
     if (nblocks <= 0) return 0;
     typedef typename PairTraits<T>::Pair Pair;
-    static bool attr_done[2][2] = {{false, false}, {false, false}};
-    const int ti = sizeof(T) == 8;
-    if (!attr_done[ti][fill != 0]) {
-        if (fill)
-            INMF_CUDA_CHECK(cudaFuncSetAttribute(blockfmt2_kernel<true, T>,
-                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        else
-            INMF_CUDA_CHECK(cudaFuncSetAttribute(blockfmt2_kernel<false, T>,
-                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_done[ti][fill != 0] = true;
-    }
+    INMF_OPTIN_SMEM((blockfmt2_kernel<true, T>), 200 * 1024);
+    INMF_OPTIN_SMEM((blockfmt2_kernel<false, T>), 200 * 1024);
     if (fill)
         blockfmt2_kernel<true, T><<<(unsigned)nblocks, W * 32, smem, (cudaStream_t)stream>>>(
             rowptr, colidx, vals, blk2, g, row_bytes, cnt, ptr, offs, (Pair*)pairs);

@@ -1,0 +1,282 @@
+// Sliced (SELL-8) form of the two X-streaming passes for fp32 (k <= 64): the default of an ALS iteration.
+//
+//   pass 1:  R[cell,:]  += X[cell, gene block] * Mt[gene block, :]      "row" = (cell, gene block) segment
+//   pass 2:  St[gene,:] += X[cell block, gene]' * H[cell block, :]      "row" = (gene, cell block) segment
+//
+// Same tiles and the same work split as blocked.cuh (one persistent CTA per SM holds one dense tile in shared
+// memory, brought in by TMA bulk copies), but the sparse rows of a CTA are sorted by length and packed in slices of
+// 8 rows stored step-interleaved:
+//
+//     slice = [step pair jj = 0 .. L2)[row i = 0 .. 8) { off(2jj), val(2jj), off(2jj+1), val(2jj+1) }   (int4)
+//
+// A warp owns a slice, a group of 4 lanes owns ONE ROW of it and each lane 8 factors (+ its share of the factors
+// beyond 32), so that
+//   * one coalesced 128-bit load per lane (8 distinct 16-byte pieces = one 128-byte line per warp instruction)
+//     delivers 16 non-zeros: 1/16 L1 wavefront per non-zero for the pair stream instead of ~1/4;
+//   * there is no cross-lane fold at the end of a row (the old kernels spend 24 shuffles per ~120 non-zeros on it),
+//     no per-row pointer chasing and no ragged row tails: rows of a slice have (almost) the same length;
+//   * the gathered operand is read with two 128-bit loads per lane whose 8-lane phases are conflict free (even
+//     groups read the first 64 bytes of their tile row first, odd groups the second 64 bytes).
+// What remains is the operand traffic itself: 4 * KP bytes of shared memory per non-zero.
+//
+// Pairs: {int32 off, float val}, off = (tile row) * 128 = byte offset of the row in the [rows x 32] main part of the
+// tile; factors beyond 32 live in a [rows x REM] remainder part (REM = 8, 16, 32 floats) addressed by a shift of it.
+// Padding pairs are {0, 0.0f}.  Slices are handed out dynamically, longest first.
+#pragma once
+#include "blocked.cuh"
+
+#define SELL_WORK_FIELDS 8
+// work[w] = { slice_begin, slice_end, dense_row0, tile_rows, out_row_base, gram_seg (-1: none), unused, unused }
+#define SELL_U 2  // 128-bit pair loads per pipeline stage
+
+__device__ __forceinline__ int4 sell_ld(const int4* p) {
+    int4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void lds128(uint32_t addr, float (&m)[4]) {
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(m[0]), "=f"(m[1]), "=f"(m[2]), "=f"(m[3]) : "r"(addr));
+}
+__device__ __forceinline__ void lds64(uint32_t addr, float (&m)[2]) {
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(m[0]), "=f"(m[1]) : "r"(addr));
+}
+__device__ __forceinline__ void red_add(float* p, float v) {
+    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+__device__ __forceinline__ void red_add4(float* p, const float (&v)[4]) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3])
+                 : "memory");
+}
+
+// Per-lane accumulators of one row: a/b = the two 4-factor chunks of the main part, r = remainder share.
+template <int REM>
+struct SellAcc {
+    static constexpr int NR = REM == 0 ? 1 : REM / 4;  // (REM == 32: two chunks of 4)
+    float a[4], b[4], r[NR];
+    __device__ __forceinline__ void clear() {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) a[u] = b[u] = 0.f;
+#pragma unroll
+        for (int u = 0; u < NR; ++u) r[u] = 0.f;
+    }
+};
+
+template <int REM>
+__device__ __forceinline__ void sell_fma(int off, int valbits, uint32_t tA, uint32_t tB, uint32_t tR, uint32_t tR2,
+                                         SellAcc<REM>& c) {
+    float m[4], n[4];
+    lds128(tA + (uint32_t)off, m);
+    lds128(tB + (uint32_t)off, n);
+    const float v = __int_as_float(valbits);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) c.a[u] = fmaf(v, m[u], c.a[u]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) c.b[u] = fmaf(v, n[u], c.b[u]);
+    if constexpr (REM == 8) {
+        float q[2];
+        lds64(tR + ((uint32_t)off >> 2), q);
+        c.r[0] = fmaf(v, q[0], c.r[0]);
+        c.r[1] = fmaf(v, q[1], c.r[1]);
+    } else if constexpr (REM == 16) {
+        float q[4];
+        lds128(tR + ((uint32_t)off >> 1), q);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) c.r[u] = fmaf(v, q[u], c.r[u]);
+    } else if constexpr (REM == 32) {
+        float q[4], s[4];
+        lds128(tR + (uint32_t)off, q);
+        lds128(tR2 + (uint32_t)off, s);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) c.r[u] = fmaf(v, q[u], c.r[u]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) c.r[4 + u] = fmaf(v, s[u], c.r[4 + u]);
+    }
+}
+
+template <int REM>
+__device__ __forceinline__ void sell_consume(const int4& q, uint32_t tA, uint32_t tB, uint32_t tR, uint32_t tR2,
+                                             SellAcc<REM>& c) {
+    sell_fma<REM>(q.x, q.y, tA, tB, tR, tR2, c);
+    sell_fma<REM>(q.z, q.w, tA, tB, tR, tR2, c);
+}
+
+// out[col0 .. col0+3] += v[0..3] for the columns < k
+__device__ __forceinline__ void sell_out4(float* __restrict__ o, int col0, int k, const float (&v)[4], bool vec_ok) {
+    if (vec_ok && col0 + 4 <= k) {
+        if (v[0] != 0.f || v[1] != 0.f || v[2] != 0.f || v[3] != 0.f) red_add4(o + col0, v);
+    } else {
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (col0 + u < k && v[u] != 0.f) red_add(o + col0 + u, v[u]);
+    }
+}
+
+template <int REM>
+__global__ void __launch_bounds__(1024, 1)
+sell_pass_kernel(const int64_t* __restrict__ work, const int64_t* __restrict__ slice_ptr,
+                 const int32_t* __restrict__ rowid, const int4* __restrict__ pairs, const float* __restrict__ dense,
+                 int KP, float* __restrict__ out, int64_t ldo, int k, int max_tile_rows,
+                 double* __restrict__ gram_out) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+    int* next_slice = reinterpret_cast<int*>(smem_raw + 16);
+    float* tmain = reinterpret_cast<float*>(smem_raw + 128);
+    float* trem = tmain + (size_t)max_tile_rows * 32;
+    const int64_t* wd = work + (size_t)blockIdx.x * SELL_WORK_FIELDS;
+    const int slice_begin = (int)wd[0], slice_end = (int)wd[1];
+    const int64_t dense_row0 = wd[2];
+    const int tile_rows = (int)wd[3];
+    const int64_t out_row_base = wd[4];
+    const int gram_seg = (int)wd[5];
+    const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        mbar_expect_tx(bar, (uint32_t)((size_t)tile_rows * KP * sizeof(float)));
+        *next_slice = slice_begin + nwarps;
+    }
+    __syncthreads();
+    {
+        const float* src = dense + (size_t)dense_row0 * KP;
+        if constexpr (REM == 0) {  // KP == 32: the tile is one contiguous block
+            if (threadIdx.x == 0) {
+                const size_t total = (size_t)tile_rows * 128;
+                const unsigned char* s = reinterpret_cast<const unsigned char*>(src);
+                unsigned char* d = reinterpret_cast<unsigned char*>(tmain);
+                for (size_t off = 0; off < total; off += 32768) {
+                    const size_t n = (total - off < 32768) ? (total - off) : 32768;
+                    bulk_g2s(d + off, s + off, (uint32_t)n, bar);
+                }
+            }
+        } else {
+            const int R = KP - 32;  // remainder floats per row in global memory (multiple of 4)
+            for (int r = threadIdx.x; r < tile_rows; r += blockDim.x) {
+                bulk_g2s(tmain + (size_t)r * 32, src + (size_t)r * KP, 128u, bar);
+                bulk_g2s(trem + (size_t)r * REM, src + (size_t)r * KP + 32, (uint32_t)(R * sizeof(float)), bar);
+            }
+        }
+    }
+    const int grp = lane >> 2, sub = lane & 3, par = grp & 1;
+    const uint32_t tA = smem_u32(tmain) + (uint32_t)((sub + 4 * par) * 16);
+    const uint32_t tB = smem_u32(tmain) + (uint32_t)((sub + 4 * (1 - par)) * 16);
+    uint32_t tR = 0, tR2 = 0;
+    if constexpr (REM == 8) tR = smem_u32(trem) + (uint32_t)(sub * 8);
+    if constexpr (REM == 16) tR = smem_u32(trem) + (uint32_t)(sub * 16);
+    if constexpr (REM == 32) {
+        tR = smem_u32(trem) + (uint32_t)((sub + 4 * par) * 16);
+        tR2 = smem_u32(trem) + (uint32_t)((sub + 4 * (1 - par)) * 16);
+    }
+    const bool vec_ok = ((ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+
+    int s = slice_begin + warp;
+    int64_t base = 0, lim = 0;
+    if (s < slice_end) {  // overlaps the tile copy
+        base = slice_ptr[s];
+        lim = slice_ptr[s + 1];
+    }
+    mbar_wait(bar, 0);
+
+    while (s < slice_end) {
+        const int L2 = (int)((lim - base) >> 3);
+        const int4* __restrict__ p = pairs + base + grp;
+        const int rid = rowid[(size_t)s * 8 + grp];
+        SellAcc<REM> c;
+        c.clear();
+        const int4 z4 = make_int4(0, 0, 0, 0);
+        int4 A[SELL_U], B[SELL_U];
+#pragma unroll
+        for (int t = 0; t < SELL_U; ++t) A[t] = (t < L2) ? sell_ld(p + t * 8) : z4;
+        int j = 0;
+        while (j < L2) {
+#pragma unroll
+            for (int t = 0; t < SELL_U; ++t) B[t] = (j + SELL_U + t < L2) ? sell_ld(p + (size_t)(j + SELL_U + t) * 8) : z4;
+#pragma unroll
+            for (int t = 0; t < SELL_U; ++t)
+                if (j + t < L2) sell_consume<REM>(A[t], tA, tB, tR, tR2, c);
+            j += SELL_U;
+            if (j >= L2) break;
+#pragma unroll
+            for (int t = 0; t < SELL_U; ++t) A[t] = (j + SELL_U + t < L2) ? sell_ld(p + (size_t)(j + SELL_U + t) * 8) : z4;
+#pragma unroll
+            for (int t = 0; t < SELL_U; ++t)
+                if (j + t < L2) sell_consume<REM>(B[t], tA, tB, tR, tR2, c);
+            j += SELL_U;
+        }
+        // next slice (dynamic, longest first): fetch before the output so the latencies overlap
+        int sn = 0;
+        if (lane == 0) sn = atomicAdd(next_slice, 1);
+        sn = __shfl_sync(INMF_FULL_MASK, sn, 0);
+        int64_t nbase = 0, nlim = 0;
+        if (sn < slice_end) {
+            nbase = slice_ptr[sn];
+            nlim = slice_ptr[sn + 1];
+        }
+        if (rid >= 0) {
+            float* o = out + (out_row_base + rid) * ldo;
+            // even groups: a = factors 4*sub.., b = 16 + 4*sub..; odd groups the other way round
+            sell_out4(o, 4 * sub + 16 * par, k, c.a, vec_ok);
+            sell_out4(o, 4 * sub + 16 * (1 - par), k, c.b, vec_ok);
+            if constexpr (REM == 8) {
+#pragma unroll
+                for (int u = 0; u < 2; ++u)
+                    if (32 + 2 * sub + u < k && c.r[u] != 0.f) red_add(o + 32 + 2 * sub + u, c.r[u]);
+            } else if constexpr (REM == 16) {
+                float q[4] = {c.r[0], c.r[1], c.r[2], c.r[3]};
+                sell_out4(o, 32 + 4 * sub, k, q, vec_ok);
+            } else if constexpr (REM == 32) {
+                float q[4] = {c.r[0], c.r[1], c.r[2], c.r[3]};
+                float t4[4] = {c.r[4], c.r[5], c.r[6], c.r[7]};
+                sell_out4(o, 32 + 4 * sub + 16 * par, k, q, vec_ok);
+                sell_out4(o, 32 + 4 * sub + 16 * (1 - par), k, t4, vec_ok);
+            }
+        }
+        s = sn;
+        base = nbase;
+        lim = nlim;
+    }
+    if (gram_seg >= 0 && gram_out != nullptr) {
+        if constexpr (REM == 0)
+            tile_gram_accumulate<float>(tmain, 32, tile_rows, k, gram_out + (size_t)gram_seg * k * k, 1.0);
+        else
+            split_gram_accumulate(tmain, trem, REM, tile_rows, k, gram_out + (size_t)gram_seg * k * k);
+    }
+}
+
+// Builder: copies the rows listed in slice_rows (ptr indices of the row-ordered blocked format, -1 = no row) into
+// the step-interleaved slices.  One warp per slice; lane = (row i = lane / 4, step-pair phase c = lane % 4).
+__global__ void __launch_bounds__(256) sell_fill_kernel(const int64_t* __restrict__ ptr, const int2* __restrict__ src,
+                                                        const int64_t* __restrict__ slice_rows,
+                                                        const int64_t* __restrict__ slice_ptr, int64_t nslices,
+                                                        int4* __restrict__ dst) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int i = lane >> 2, c = lane & 3;
+    for (int64_t s = warp0; s < nslices; s += nwarp) {
+        const int64_t base = slice_ptr[s];
+        const int L2 = (int)((slice_ptr[s + 1] - base) >> 3);
+        const int64_t row = slice_rows[s * 8 + i];
+        int64_t beg = 0;
+        int len = 0;
+        if (row >= 0) {
+            beg = ptr[row];
+            len = (int)(ptr[row + 1] - beg);
+        }
+        for (int jj = c; jj < L2; jj += 4) {
+            int4 q = make_int4(0, 0, 0, 0);
+            if (2 * jj < len) {
+                const int2 a = src[beg + 2 * jj];
+                q.x = a.x;
+                q.y = a.y;
+            }
+            if (2 * jj + 1 < len) {
+                const int2 b = src[beg + 2 * jj + 1];
+                q.z = b.x;
+                q.w = b.y;
+            }
+            dst[base + (int64_t)jj * 8 + i] = q;
+        }
+    }
+}

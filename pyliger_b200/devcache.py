@@ -4,8 +4,14 @@ pyliger's API hands scipy matrices from stage to stage (``layers["norm_data"]`` 
 optimize_ALS).  When a stage here has just computed such a matrix on the GPU it registers the device arrays
 under the identity of the host matrix it returned; the next stage finds them and skips the host->device copy
 ("X uploaded once ... never round-trips").  Entries die with the host matrix
-(weakref) or on ``clear()``; a sampled fingerprint of the host matrix is re-checked on every lookup, so a matrix
-edited in place after registration falls back to a normal upload (``forget`` drops an entry explicitly).
+(weakref) or on ``clear()``.
+
+Reuse is safe by construction: the ``data`` / ``indices`` / ``indptr`` arrays of a registered host matrix are made
+READ-ONLY (``flags.writeable = False``), so an in-place edit raises instead of silently diverging from the device
+copy; whoever wants to edit takes a copy (no twin) or re-enables ``writeable`` -- which ``lookup`` detects and
+treats as "edited": the twin is dropped and the matrix is uploaded like any other.  A cheap sampled fingerprint
+is kept as a second line of defence against arrays swapped for others of the same size (``forget`` drops an
+entry explicitly).
 """
 import weakref
 
@@ -22,8 +28,19 @@ def _fingerprint(m):
             int(np.asarray(m.indices[::step], dtype=np.int64).sum()), int(m.indptr[-1]))
 
 
+def _arrays(m):
+    return [a for a in (getattr(m, "data", None), getattr(m, "indices", None), getattr(m, "indptr", None))
+            if isinstance(a, np.ndarray)]
+
+
+def _frozen(m):
+    return all(not a.flags.writeable for a in _arrays(m))
+
+
 def register(host_matrix, device, rowptr, colidx, vals):
     key = id(host_matrix)
+    for a in _arrays(host_matrix):
+        a.flags.writeable = False
     try:
         ref = weakref.ref(host_matrix, lambda _r, key=key: _cache.pop(key, None))
     except TypeError:  # pragma: no cover - scipy matrices are weak-referenceable
@@ -39,7 +56,7 @@ def lookup(host_matrix, device):
     ref, dev, rowptr, colidx, vals, fp = ent
     if ref() is not host_matrix or dev != str(device):
         return None
-    if fp != _fingerprint(host_matrix):  # edited in place since: the twin is stale
+    if not _frozen(host_matrix) or fp != _fingerprint(host_matrix):  # made writable / arrays swapped: stale
         _cache.pop(id(host_matrix), None)
         return None
     return rowptr, colidx, vals

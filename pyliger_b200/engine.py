@@ -200,7 +200,11 @@ class InmfEngine(object):
         X, k, dev, dt = self.X, self.k, self.device, self.dtype
         N, g = X.N, X.g
         self.N, self.g = N, g
+        # leading dimension of H / Mt: k rounded up to 4, and at least 32 in fp32 (128-byte tile rows: the wide /
+        # sliced kernels of csrc/blocked.cuh, sell.cuh); pad columns stay zero
         self.ldm = max(4, (k + 3) // 4 * 4)
+        if dt == torch.float32 and self.use_blocked:
+            self.ldm = max(32, self.ldm)
         f64 = torch.float64
         z = lambda *shape, dtype=dt: torch.zeros(*shape, dtype=dtype, device=dev)
         self.Wt = z(g, k)
@@ -248,9 +252,14 @@ class InmfEngine(object):
             esize = 4 if dt == torch.float32 else 8
             sms = torch.cuda.get_device_properties(dev).multi_processor_count
             if not self.use_tc:
+                sell = blocked.sell_applies(self.ldm, esize)
                 self.pass1 = blocked.build_pass1(X, self.ldm, esize, sms)
+                if sell:
+                    self.pass1 = blocked.build_sell(self.pass1, self.ldm)
                 if self.need_stats:
                     self.pass2 = blocked.build_pass2(X, self.ldm, esize, sms)
+                    if sell:
+                        self.pass2 = blocked.build_sell(self.pass2, self.ldm)
         self.tc1 = self.tc2 = None
         if self.use_tc and X.n_own_total > 0:
             sms = torch.cuda.get_device_properties(dev).multi_processor_count
@@ -298,7 +307,11 @@ class InmfEngine(object):
                       seg_desc, nseg, max_rows, k, _stream())
 
     def _blocked(self, p, work, nwork, dense, out, ldo, gram):
-        """One tiled pass (out += X_blocked * dense tile): plain or split-tile kernel, as the format was built."""
+        """One tiled pass (out += X_blocked * dense tile): sliced, plain or split-tile kernel, as the format was built."""
+        if isinstance(p, blocked.SellPass):
+            _lib.call("inmf_sell_pass_f32", "", work, nwork, p.slice_ptr, p.rowid, p.pairs4, dense, self.ldm, out, ldo,
+                      self.k, p.max_tile_rows, gram, _stream())
+            return
         name, sfx = ("inmf_blocked_split_f32", "") if p.split else ("inmf_blocked_spmm", self.sfx)
         if blocked.WIDE_TILE and not p.split and self.sfx == "f32" and self.ldm == 32:
             name, sfx = "inmf_blocked_wide_f32", ""  # same formats, 8 factors per lane
@@ -553,6 +566,8 @@ class InmfEngine(object):
             sms = torch.cuda.get_device_properties(self.device).multi_processor_count
             bp, NB, gbs = blocked.build_pass1_resident(self.X, self.ldm, esize)
             pieces = max(1, sms // max(1, self.N * NB))
+            # window_work splits a piece into at most two row ranges (one wrap): no piece longer than its dataset
+            pieces = max([pieces] + [-(-(hi - lo) // max(1, n)) for (lo, hi), n in zip(self.sub, self.X.n_global)])
             work, counts = blocked.window_work(self.X, NB, gbs, plan, pieces)
             self.win = (bp, torch.from_numpy(work).to(self.device), counts)
         return torch.from_numpy(plan).to(self.device)

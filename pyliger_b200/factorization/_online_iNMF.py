@@ -61,7 +61,8 @@ def _cal_W_V(Xs, num_genes, num_cells, prev_info, W_init, V_init, A_init, B_init
     Vs = ([_init_V_online(num_cells[i], k, Xs[i], h5_chunk_size, rand_seed) for i in range(num_files)]
           if V_init is None else V_init)
     n_prev = 0 if prev_info is None else len(prev_info["A_prev"])
-    engine = InmfEngine(Xs, k, value_lambda, dtype=dtype, device=device, replicate=True, n_prev=n_prev)
+    engine = InmfEngine(Xs, k, value_lambda, dtype=dtype, device=device, replicate=True, n_prev=n_prev,
+                        need_stats=False)  # mini-batch statistics go through the window kernels, not pass 2
 
     miniBatch_sizes = np.asarray(
         [np.round((num_cells[i] / np.sum(num_cells)) * miniBatch_size).astype(int) for i in range(num_files)])
@@ -176,7 +177,7 @@ def online_iNMF(
             print("Metagene projection")
         W = liger_object.W if W_init is None else W_init
         for adata in X_new:
-            engine = InmfEngine([_scale_data(adata)], k, 0.0, dtype=dt, device=device)
+            engine = InmfEngine([_scale_data(adata)], k, 0.0, dtype=dt, device=device, need_stats=False)
             engine.Wt.copy_(_to_dev(engine, W))
             engine.Vt.zero_()
             engine.final_H(with_V=False)
@@ -212,7 +213,7 @@ def online_iNMF(
         adata.uns["A"] = A[0]
     # refresh H of the existing datasets with the refined W and their own V
     for adata in liger_object.adata_list:
-        engine = InmfEngine([_scale_data(adata)], k, value_lambda, dtype=dt, device=device)
+        engine = InmfEngine([_scale_data(adata)], k, value_lambda, dtype=dt, device=device, need_stats=False)
         engine.Wt.copy_(_to_dev(engine, W))
         engine.Vt[0].copy_(_to_dev(engine, adata.varm["V"]))
         engine.final_H()

@@ -294,8 +294,9 @@ def test_split_tile_passes_match_plain_passes(dev, k):
     from pyliger_b200 import blocked
     lam = 2.0
     mats, W, V, H = _rand_problem(k, k=k)
-    old = (blocked.SMEM_BUDGET, blocked.SPLIT_TILE)
+    old = (blocked.SMEM_BUDGET, blocked.SPLIT_TILE, blocked.SELL)
     blocked.SMEM_BUDGET = 40 * 256  # 40-64 tile rows: several gene and cell blocks at this toy size
+    blocked.SELL = False            # the row-ordered kernels themselves (the sliced ones: test_sell_passes_...)
     res = {}
     try:
         for split in (False, True):
@@ -312,7 +313,7 @@ def test_split_tile_passes_match_plain_passes(dev, k):
             objs = [float(eng.initial_objective())] + [float(eng.als_iteration(warm=i > 0).item()) for i in range(3)]
             res[split] = (St, HtH, R, objs, eng.H.clone())
     finally:
-        blocked.SMEM_BUDGET, blocked.SPLIT_TILE = old
+        blocked.SMEM_BUDGET, blocked.SPLIT_TILE, blocked.SELL = old
     N = len(mats)
     St, HtH, R, objs, Hf = res[True]
     off = 0
@@ -333,8 +334,9 @@ def test_wide_tile_passes_match_plain_passes(dev, k):
     from pyliger_b200 import blocked
     lam = 2.0
     mats, W, V, H = _rand_problem(100 + k, ns=(333, 170), g=120, k=k, density=0.3)
-    old = (blocked.SMEM_BUDGET, blocked.WIDE_TILE)
+    old = (blocked.SMEM_BUDGET, blocked.WIDE_TILE, blocked.SELL)
     blocked.SMEM_BUDGET = 50 * 128  # 50 tile rows: several gene and cell blocks
+    blocked.SELL = False
     res = {}
     try:
         for wide in (False, True):
@@ -351,7 +353,7 @@ def test_wide_tile_passes_match_plain_passes(dev, k):
             objs = [float(eng.initial_objective())] + [float(eng.als_iteration(warm=i > 0).item()) for i in range(3)]
             res[wide] = (St, HtH, R, objs, eng.H.clone())
     finally:
-        blocked.SMEM_BUDGET, blocked.WIDE_TILE = old
+        blocked.SMEM_BUDGET, blocked.WIDE_TILE, blocked.SELL = old
     St, HtH, R, objs, Hf = res[True]
     off = 0
     for i in range(len(mats)):
@@ -363,3 +365,52 @@ def test_wide_tile_passes_match_plain_passes(dev, k):
     assert float(R[:, k:].abs().max().item() if R.shape[1] > k else 0.0) == 0.0
     np.testing.assert_allclose(objs, res[False][3], rtol=2e-6)
     assert relerr(Hf.cpu().numpy(), res[False][4].cpu().numpy()) < 1e-3
+
+
+@pytest.mark.parametrize("k", [3, 20, 30, 32, 33, 40, 44, 48, 50, 64])
+@pytest.mark.parametrize("budget_rows", [37, 100000])
+def test_sell_passes_match_numpy_and_row_ordered_passes(dev, k, budget_rows):
+    """inmf_sell_pass_f32 (rows sorted by length, slices of 8 rows, 4 lanes per row) against numpy and against the
+    row-ordered tiled kernels: pass 1, pass 2 + H'H, with several gene / cell blocks and with one, ragged row lengths
+    (empty rows and columns included), and a short ALS run."""
+    from pyliger_b200 import blocked
+    lam = 2.0
+    mats, W, V, H = _rand_problem(200 + k, ns=(333, 171, 9), g=130, k=k, density=0.25)
+    mats[0] = sps.csr_matrix(mats[0].multiply(np.arange(mats[0].shape[0])[:, None] % 7 != 0))  # empty rows
+    mats[1] = sps.csr_matrix(mats[1].multiply(np.arange(130)[None, :] % 5 != 0))               # empty columns
+    kp = max(32, (k + 3) // 4 * 4)
+    old = (blocked.SMEM_BUDGET, blocked.SELL)
+    blocked.SMEM_BUDGET = min(old[0], budget_rows * blocked.smem_row_bytes(kp, 4))
+    res = {}
+    try:
+        for sell in (False, True):
+            blocked.SELL = sell
+            eng = _engine(mats, k, lam, "float32")
+            assert isinstance(eng.pass1, blocked.SellPass) == sell and isinstance(eng.pass2, blocked.SellPass) == sell
+            if sell:
+                assert eng.pass1.padded >= eng.pass1.nnz and eng.pass2.padded >= eng.pass2.nnz
+                assert eng.pass1.nnz == eng.pass2.nnz == sum(m.nnz for m in mats)
+            eng.set_als_state(W, V, H)
+            eng.prep()
+            eng.stats()
+            St, HtH = eng.St.clone(), eng.HtH.clone()
+            eng.rhs_H()
+            R = eng.H.clone()
+            eng.set_als_state(W, V, H)
+            objs = [float(eng.initial_objective())] + [float(eng.als_iteration(warm=i > 0).item()) for i in range(3)]
+            res[sell] = (St, HtH, R, objs, eng.H.clone())
+    finally:
+        blocked.SMEM_BUDGET, blocked.SELL = old
+    St, HtH, R, objs, Hf = res[True]
+    off = 0
+    for i in range(len(mats)):
+        n = mats[i].shape[0]
+        assert relerr(St[i].cpu().numpy(), np.asarray(mats[i].T.dot(H[i]))) < 5e-6
+        assert relerr(HtH[i].cpu().numpy(), H[i].T @ H[i]) < 5e-6
+        assert relerr(R[off:off + n, :k].cpu().numpy(), np.asarray(mats[i].dot((W + V[i]).T))) < 5e-6
+        off += n
+    assert float(R[:, k:].abs().max().item() if R.shape[1] > k else 0.0) == 0.0  # pad columns stay zero
+    # different summation order than the row-ordered kernels: the fp32 objective of this toy problem (4e7 -> 6e4,
+    # i.e. three digits of cancellation) agrees to the north star's fp32 tolerance
+    np.testing.assert_allclose(objs, res[False][3], rtol=1e-3)
+    assert relerr(Hf.cpu().numpy(), res[False][4].cpu().numpy()) < 2e-2

@@ -386,8 +386,22 @@ def test_device_twin_cache_detects_edits_and_dies_with_the_matrix():
     assert devcache.lookup(m, dev) is not None
     assert devcache.lookup(m, torch.device("meta")) is None       # other device
     assert devcache.lookup(m.copy(), dev) is None                 # identity, not equality
-    m.data *= 2.0                                                 # in-place edit -> stale twin is dropped
+    # registered matrices are frozen: an in-place edit (even of a single entry no sampled fingerprint would see)
+    # raises instead of silently diverging from the device copy
+    with pytest.raises(ValueError):
+        m.data[1] = 123.0
+    with pytest.raises(ValueError):
+        m.data *= 2.0
+    assert devcache.lookup(m, dev) is not None
+    # whoever re-enables writing gets the upload path: the twin is dropped on the next lookup
+    m.data.flags.writeable = True
+    m.data[1] = 123.0                                             # one (non-sampled) entry
     assert devcache.lookup(m, dev) is None and devcache.lookup(m, dev) is None
+    big = sps.random(400, 300, density=0.3, random_state=3, format="csr")   # > 4096 non-zeros: strided sampling
+    devcache.register(big, dev, *t)
+    big.data.flags.writeable = True
+    big.data[1] += 1.0
+    assert devcache.lookup(big, dev) is None
     m2 = sps.random(20, 30, density=0.3, random_state=2, format="csr")
     devcache.register(m2, dev, *t)
     n_before = len(devcache._cache)
