@@ -45,7 +45,7 @@ def main():
     ap.add_argument("--cells", type=int, default=0)
     ap.add_argument("--k", type=int, default=0)
     ap.add_argument("--reps", type=int, default=10)
-    ap.add_argument("--variants", default="sell,rows")
+    ap.add_argument("--variants", default="sell,sell8,rows")
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])
     if args.cells:
@@ -67,7 +67,8 @@ def main():
         pass
     ref = None
     for variant in args.variants.split(","):
-        blocked.SELL = variant == "sell"
+        blocked.SELL = variant.startswith("sell")
+        blocked.SELL_HEIGHT_KP32 = 8 if variant == "sell8" else 32
         eng = InmfEngine(mats, k, 5.0, dtype=torch.float32, device=dev)
         eng.set_als_state(W0, V0, H0)
         eng.initial_objective()

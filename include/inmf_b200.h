@@ -126,22 +126,25 @@ int32_t inmf_blocked_wide_f32(const int64_t* work, int32_t nwork, const int64_t*
 /* Sliced (SELL-8) form of the tiled product above, fp32, k <= 64: the default of the two X-streaming passes of an ALS
  * iteration (R = X (W+V_s)' of _iNMF_ANLS.py:135-139; X' H, H' H of :142-152).  The sparse rows of every work item
  * (the rows of the row-ordered blocked format: (cell, gene block) segments in pass 1, (gene, cell block) segments in
- * pass 2) are sorted by length and stored in slices of 8 rows, step-interleaved, two steps per 16 bytes:
- *   pairs4[slice_ptr[s] + jj*8 + i] = { off(2jj), val(2jj), off(2jj+1), val(2jj+1) } of row i of slice s,
+ * pass 2) are sorted by length and stored in slices of `height` rows, step-interleaved, two steps per 16 bytes:
+ *   pairs4[slice_ptr[s] + jj*height + i] = { off(2jj), val(2jj), off(2jj+1), val(2jj+1) } of row i of slice s,
  *   off = (row of the dense tile) * 128, padding = {0, 0.0f};  slice_ptr int64[nslices+1] in 16-byte units;
- *   rowid int32[nslices*8]: output row of slice row i relative to the work item's out_row_base, -1 = no row.
+ *   rowid int32[nslices*height]: output row of slice row i relative to the work item's out_row_base, -1 = no row.
+ *   height = 8: four lanes per row (any kp);  height = 32 (kp == 32 only): one lane per row, the pair stream is not
+ *   replicated across lanes and every lane walks the 16-byte chunks of its tile row in a rotated, bank-conflict-free
+ *   order.
  *   work int64[nwork][8] = { slice_begin, slice_end, dense_row0, tile_rows, out_row_base, gram_seg, 0, 0 }
  * dense has kp floats per row (kp = 32 for k <= 32, else k rounded up to 4); the tile is held in shared memory as
  * [rows x 32] + [rows x rs], rs = 0 / 8 / 16 / 32 for kp - 32 = 0 / <= 8 / <= 16 / <= 32, so max_tile_rows is bounded by
  * (227 KB - 128) / ((32 + rs) * 4).  out rows are accumulated (caller zeroes). */
 int32_t inmf_sell_pass_f32(const int64_t* work, int32_t nwork, const int64_t* slice_ptr, const int32_t* rowid,
-                           const void* pairs4, const float* dense, int32_t kp, float* out, int64_t ldo, int32_t k,
-                           int32_t max_tile_rows, double* gram_out, void* stream);
+                           const void* pairs4, int32_t height, const float* dense, int32_t kp, float* out, int64_t ldo,
+                           int32_t k, int32_t max_tile_rows, double* gram_out, void* stream);
 
-/* Builder of pairs4: copies the rows slice_rows[s*8 + i] (indices into ptr of the row-ordered blocked format built by
- * inmf_blockfmt1/2_f32, -1 = no row) into the slices laid out by slice_ptr, zero padded. */
+/* Builder of pairs4: copies the rows slice_rows[s*height + i] (indices into ptr of the row-ordered blocked format built
+ * by inmf_blockfmt1/2_f32, -1 = no row) into the slices laid out by slice_ptr, zero padded. */
 int32_t inmf_sell_fill_f32(const int64_t* ptr, const void* pairs, const int64_t* slice_rows, const int64_t* slice_ptr,
-                           int64_t nslices, void* pairs4, void* stream);
+                           int64_t nslices, int32_t height, void* pairs4, void* stream);
 
 /* Sufficient statistics of one pass over the cells (accumulating; caller zeroes):
  *   St[s] (g x k) += sum_q X[row(q), :]' H[q, :],   HtH[s] (k x k, double) += sum_q H[q,:]' H[q,:]

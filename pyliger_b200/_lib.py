@@ -74,9 +74,9 @@ def load():
         getattr(lib, name).restype = _I32
         getattr(lib, name).argtypes = _TYPED["inmf_blocked_spmm"]
     lib.inmf_sell_pass_f32.restype = _I32
-    lib.inmf_sell_pass_f32.argtypes = [_PTR, _I32, _PTR, _PTR, _PTR, _PTR, _I32, _PTR, _I64, _I32, _I32, _PTR, _PTR]
+    lib.inmf_sell_pass_f32.argtypes = [_PTR, _I32, _PTR, _PTR, _PTR, _I32, _PTR, _I32, _PTR, _I64, _I32, _I32, _PTR, _PTR]
     lib.inmf_sell_fill_f32.restype = _I32
-    lib.inmf_sell_fill_f32.argtypes = [_PTR, _PTR, _PTR, _PTR, _I64, _PTR, _PTR]
+    lib.inmf_sell_fill_f32.argtypes = [_PTR, _PTR, _PTR, _PTR, _I64, _I32, _PTR, _PTR]
     lib.inmf_select_count.restype = _I32
     lib.inmf_select_count.argtypes = [_PTR, _PTR, _I64, _PTR, _PTR, _PTR]
     for name, argtypes in _TYPED.items():

@@ -123,28 +123,32 @@ class BlockedPass(object):
 
 class SellPass(object):
     """Sliced form of a BlockedPass (csrc/sell.cuh): rows of every work item sorted by length, 8 per slice."""
-    __slots__ = ("work", "nwork", "slice_ptr", "rowid", "pairs4", "max_tile_rows", "nnz", "padded")
+    __slots__ = ("work", "nwork", "slice_ptr", "rowid", "pairs4", "max_tile_rows", "nnz", "padded", "height")
 
 
-def build_sell(bp, kp):
+SELL_HEIGHT_KP32 = 32  # slice height at kp == 32: 32 (one lane per row) or 8 (four lanes per row)
+
+
+def build_sell(bp, kp, height=None):
     """Sliced copy of the row-ordered blocked format ``bp`` (fp32).  Index plumbing (sort of the rows of every work item
     by length, slice table, prefix sums) is torch; the data movement is inmf_sell_fill_f32."""
     dev = bp.ptr.device
     W = bp.work_host[:bp.nwork]
     sp = SellPass()
+    S = sp.height = int(height or (SELL_HEIGHT_KP32 if kp == 32 else 8))
     sp.max_tile_rows = bp.max_tile_rows
     sp.nwork = bp.nwork
     sp.nnz = int(bp.pairs.shape[0])
     if bp.nwork == 0:
         sp.work = torch.zeros(1, WORK_FIELDS, dtype=torch.int64, device=dev)
         sp.slice_ptr = torch.zeros(1, dtype=torch.int64, device=dev)
-        sp.rowid = torch.zeros(8, dtype=torch.int32, device=dev)
+        sp.rowid = torch.zeros(S, dtype=torch.int32, device=dev)
         sp.pairs4 = torch.zeros(1, 4, dtype=torch.int32, device=dev)
         sp.padded = 0
         return sp
     lo = W[:, 0] + W[:, 3]
     nrows = W[:, 4] - W[:, 3]
-    ns = (nrows + 7) // 8
+    ns = (nrows + S - 1) // S
     start = np.concatenate([[0], np.cumsum(nrows)])
     slice_off = np.concatenate([[0], np.cumsum(ns)])
     total_rows, total_slices = int(start[-1]), int(slice_off[-1])
@@ -157,21 +161,21 @@ def build_sell(bp, kp):
     if total_rows and int(length.max().item()) >= big:
         raise ValueError("sparse row too long for the sliced format")
     order = torch.sort(wid * big + (big - 1 - length), stable=True)[1]     # by work item, longest row first
-    slot = t(slice_off[:-1])[wid] * 8 + q
-    slice_rows = torch.full((total_slices * 8,), -1, dtype=torch.int64, device=dev)
+    slot = t(slice_off[:-1])[wid] * S + q
+    slice_rows = torch.full((total_slices * S,), -1, dtype=torch.int64, device=dev)
     slice_rows[slot] = ridx[order]
-    slice_len = torch.zeros(total_slices * 8, dtype=torch.int64, device=dev)
+    slice_len = torch.zeros(total_slices * S, dtype=torch.int64, device=dev)
     slice_len[slot] = length[order]
-    L2 = (slice_len.view(total_slices, 8).max(dim=1)[0] + 1) // 2           # 128-bit units (two steps) per row
+    L2 = (slice_len.view(total_slices, S).max(dim=1)[0] + 1) // 2           # 128-bit units (two steps) per row
     sp.slice_ptr = torch.zeros(total_slices + 1, dtype=torch.int64, device=dev)
-    torch.cumsum(8 * L2, 0, out=sp.slice_ptr[1:])
+    torch.cumsum(S * L2, 0, out=sp.slice_ptr[1:])
     n4 = int(sp.slice_ptr[-1].item())
     sp.padded = 2 * n4
     swid = torch.repeat_interleave(torch.arange(bp.nwork, device=dev), t(ns))
-    rel = slice_rows.view(total_slices, 8) - t(W[:, 0])[swid][:, None]
-    sp.rowid = torch.where(slice_rows.view(total_slices, 8) >= 0, rel, torch.full_like(rel, -1)).to(torch.int32).contiguous()
+    rel = slice_rows.view(total_slices, S) - t(W[:, 0])[swid][:, None]
+    sp.rowid = torch.where(slice_rows.view(total_slices, S) >= 0, rel, torch.full_like(rel, -1)).to(torch.int32).contiguous()
     sp.pairs4 = torch.empty(max(n4, 1), 4, dtype=torch.int32, device=dev)
-    _lib.call("inmf_sell_fill_f32", "", bp.ptr, bp.pairs, slice_rows, sp.slice_ptr, total_slices, sp.pairs4, _stream(dev))
+    _lib.call("inmf_sell_fill_f32", "", bp.ptr, bp.pairs, slice_rows, sp.slice_ptr, total_slices, S, sp.pairs4, _stream(dev))
     work = np.zeros((bp.nwork, WORK_FIELDS), dtype=np.int64)
     work[:, 0] = slice_off[:-1]
     work[:, 1] = slice_off[1:]

@@ -1211,14 +1211,24 @@ static int32_t sell_pass_one(const int64_t* work, int32_t nwork, const int64_t* 
     return 0;
 }
 extern "C" int32_t inmf_sell_pass_f32(const int64_t* work, int32_t nwork, const int64_t* slice_ptr,
-                                      const int32_t* rowid, const void* pairs4, const float* dense, int32_t kp,
-                                      float* out, int64_t ldo, int32_t k, int32_t max_tile_rows, double* gram_out,
-                                      void* stream) {
+                                      const int32_t* rowid, const void* pairs4, int32_t height, const float* dense,
+                                      int32_t kp, float* out, int64_t ldo, int32_t k, int32_t max_tile_rows,
+                                      double* gram_out, void* stream) {
     INMF_REQUIRE(k >= 1 && k <= INMF_MAX_K, "k must be in [1, 64]");
     INMF_REQUIRE(kp >= 32 && kp >= k && kp % 4 == 0 && kp <= 64, "kp must be a multiple of 4 in [max(k, 32), 64]");
     INMF_REQUIRE(ldo >= k, "ldo must be >= k");
     INMF_REQUIRE((reinterpret_cast<uintptr_t>(pairs4) & 15) == 0, "pairs4 must be 16-byte aligned");
+    INMF_REQUIRE(height == 8 || (height == 32 && kp == 32), "slice height must be 8, or 32 with kp == 32");
     if (nwork <= 0) return 0;
+    if (height == 32) {
+        const size_t smem = 128 + (size_t)max_tile_rows * 128;
+        INMF_REQUIRE(smem <= 227 * 1024, "dense tile does not fit in shared memory");
+        INMF_OPTIN_SMEM((sell32_pass_kernel), 227 * 1024);
+        sell32_pass_kernel<<<(unsigned)nwork, SELL32_THREADS, smem, (cudaStream_t)stream>>>(
+            work, slice_ptr, rowid, reinterpret_cast<const int4*>(pairs4), dense, out, ldo, k, gram_out);
+        INMF_LAUNCH_CHECK();
+        return 0;
+    }
     const int rem = kp - 32;
 #define INMF_SELL_ARGS work, nwork, slice_ptr, rowid, pairs4, dense, kp, out, ldo, k, max_tile_rows, gram_out, stream
     if (rem == 0) return sell_pass_one<0>(INMF_SELL_ARGS);
@@ -1229,14 +1239,20 @@ extern "C" int32_t inmf_sell_pass_f32(const int64_t* work, int32_t nwork, const 
 }
 
 extern "C" int32_t inmf_sell_fill_f32(const int64_t* ptr, const void* pairs, const int64_t* slice_rows,
-                                      const int64_t* slice_ptr, int64_t nslices, void* pairs4, void* stream) {
+                                      const int64_t* slice_ptr, int64_t nslices, int32_t height, void* pairs4,
+                                      void* stream) {
     if (nslices <= 0) return 0;
+    INMF_REQUIRE(height == 8 || height == 32, "slice height must be 8 or 32");
     INMF_REQUIRE((reinterpret_cast<uintptr_t>(pairs4) & 15) == 0, "pairs4 must be 16-byte aligned");
     int64_t blocks = (nslices + 7) / 8;
     const int64_t cap = (int64_t)inmf_num_sms() * 16;
     if (blocks > cap) blocks = cap;
-    sell_fill_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
-        ptr, reinterpret_cast<const int2*>(pairs), slice_rows, slice_ptr, nslices, reinterpret_cast<int4*>(pairs4));
+    if (height == 8)
+        sell_fill_kernel<8><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+            ptr, reinterpret_cast<const int2*>(pairs), slice_rows, slice_ptr, nslices, reinterpret_cast<int4*>(pairs4));
+    else
+        sell_fill_kernel<32><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+            ptr, reinterpret_cast<const int2*>(pairs), slice_rows, slice_ptr, nslices, reinterpret_cast<int4*>(pairs4));
     INMF_LAUNCH_CHECK();
     return 0;
 }

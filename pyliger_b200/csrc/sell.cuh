@@ -102,10 +102,17 @@ __device__ __forceinline__ void sell_consume(const int4& q, uint32_t tA, uint32_
     sell_fma<REM>(q.z, q.w, tA, tB, tR, tR2, c);
 }
 
-// out[col0 .. col0+3] += v[0..3] for the columns < k
-__device__ __forceinline__ void sell_out4(float* __restrict__ o, int col0, int k, const float (&v)[4], bool vec_ok) {
-    if (vec_ok && col0 + 4 <= k) {
+__device__ __forceinline__ void red_add2(float* p, float a, float b) {
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+}
+
+// out[col0 .. col0+3] += v[0..3] for the columns < k.  vec = 4: rows are 16-byte aligned, 2: 8-byte aligned, else 1.
+__device__ __forceinline__ void sell_out4(float* __restrict__ o, int col0, int k, const float (&v)[4], int vec) {
+    if (vec == 4 && col0 + 4 <= k) {
         if (v[0] != 0.f || v[1] != 0.f || v[2] != 0.f || v[3] != 0.f) red_add4(o + col0, v);
+    } else if (vec >= 2 && col0 + 4 <= k) {
+        if (v[0] != 0.f || v[1] != 0.f) red_add2(o + col0, v[0], v[1]);
+        if (v[2] != 0.f || v[3] != 0.f) red_add2(o + col0 + 2, v[2], v[3]);
     } else {
 #pragma unroll
         for (int u = 0; u < 4; ++u)
@@ -135,7 +142,7 @@ sell_pass_kernel(const int64_t* __restrict__ work, const int64_t* __restrict__ s
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);
         mbar_expect_tx(bar, (uint32_t)((size_t)tile_rows * KP * sizeof(float)));
-        *next_slice = slice_begin + nwarps;
+        *next_slice = slice_begin;
     }
     __syncthreads();
     {
@@ -168,15 +175,27 @@ sell_pass_kernel(const int64_t* __restrict__ work, const int64_t* __restrict__ s
         tR = smem_u32(trem) + (uint32_t)((sub + 4 * par) * 16);
         tR2 = smem_u32(trem) + (uint32_t)((sub + 4 * (1 - par)) * 16);
     }
-    const bool vec_ok = ((ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    const int vec_ok = (((ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0)) ? 4
+                       : (((ldo & 1) == 0) && ((reinterpret_cast<uintptr_t>(out) & 7) == 0)) ? 2 : 1;
 
-    int s = slice_begin + warp;
+    mbar_wait(bar, 0);
+    // H'H of the resident tile (pass 2): done FIRST by the few warps whose threads own an output block, while all
+    // other warps already stream slices -- the slices are handed out dynamically, so those warps simply join later
+    // and the latency-bound Gram loop costs no tail.
+    if (gram_seg >= 0 && gram_out != nullptr) {
+        if constexpr (REM == 0)
+            tile_gram_accumulate<float>(tmain, 32, tile_rows, k, gram_out + (size_t)gram_seg * k * k, 1.0);
+        else
+            split_gram_accumulate(tmain, trem, REM, tile_rows, k, gram_out + (size_t)gram_seg * k * k);
+    }
+    int s = 0;
+    if (lane == 0) s = atomicAdd(next_slice, 1);
+    s = __shfl_sync(INMF_FULL_MASK, s, 0);
     int64_t base = 0, lim = 0;
-    if (s < slice_end) {  // overlaps the tile copy
+    if (s < slice_end) {
         base = slice_ptr[s];
         lim = slice_ptr[s + 1];
     }
-    mbar_wait(bar, 0);
 
     while (s < slice_end) {
         const int L2 = (int)((lim - base) >> 3);
@@ -236,35 +255,146 @@ sell_pass_kernel(const int64_t* __restrict__ work, const int64_t* __restrict__ s
         base = nbase;
         lim = nlim;
     }
-    if (gram_seg >= 0 && gram_out != nullptr) {
-        if constexpr (REM == 0)
-            tile_gram_accumulate<float>(tmain, 32, tile_rows, k, gram_out + (size_t)gram_seg * k * k, 1.0);
-        else
-            split_gram_accumulate(tmain, trem, REM, tile_rows, k, gram_out + (size_t)gram_seg * k * k);
+}
+
+// =====================================================================================================
+// One lane per row, 32 rows per slice, KP == 32 (k <= 32): the pair stream is not replicated across lanes at all.
+//
+// ncu on the 4-lanes-per-row kernel above (C2, k = 30): 1.03 shared-memory wavefronts per non-zero for the operand --
+// the floor -- but another 0.30 for the pairs, because a 128-bit load returns 512 bytes to the register file even when
+// groups of 4 lanes ask for the same 16 bytes; the L1 data pipe is 91-98 % busy, so that is 23 % of the kernel.
+// Here a lane owns a whole row: one 128-bit load per lane brings two non-zeros of ITS row (512 distinct bytes per
+// warp instruction, 1/16 wavefront per non-zero) and the lane reads all eight 16-byte chunks of the gathered tile
+// row itself.  Lanes of a phase (8 lanes) would all hit the same 4 banks, so lane l walks the chunks in the rotated
+// order (l + j) mod 8: its j-th load always goes to accumulator chunk j (static register index), and the 8 lanes of a
+// phase always touch 8 different bank groups, whatever rows they gather.  32 accumulators per lane: 512 threads per
+// CTA with up to 128 registers.
+// Slices: [step pair jj][row i = 0 .. 32) int4; rowid int32[nslices * 32].
+// =====================================================================================================
+#define SELL32_THREADS 512
+
+__global__ void __launch_bounds__(SELL32_THREADS, 1)
+sell32_pass_kernel(const int64_t* __restrict__ work, const int64_t* __restrict__ slice_ptr,
+                   const int32_t* __restrict__ rowid, const int4* __restrict__ pairs, const float* __restrict__ dense,
+                   float* __restrict__ out, int64_t ldo, int k, double* __restrict__ gram_out) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+    int* next_slice = reinterpret_cast<int*>(smem_raw + 16);
+    float* tile = reinterpret_cast<float*>(smem_raw + 128);
+    const int64_t* wd = work + (size_t)blockIdx.x * SELL_WORK_FIELDS;
+    const int slice_begin = (int)wd[0], slice_end = (int)wd[1];
+    const int64_t dense_row0 = wd[2];
+    const int tile_rows = (int)wd[3];
+    const int64_t out_row_base = wd[4];
+    const int gram_seg = (int)wd[5];
+    const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        *next_slice = slice_begin;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const size_t total = (size_t)tile_rows * 128;
+        mbar_expect_tx(bar, (uint32_t)total);
+        const unsigned char* sp = reinterpret_cast<const unsigned char*>(dense + (size_t)dense_row0 * 32);
+        unsigned char* d = reinterpret_cast<unsigned char*>(tile);
+        for (size_t off = 0; off < total; off += 32768) {
+            const size_t n = (total - off < 32768) ? (total - off) : 32768;
+            bulk_g2s(d + off, sp + off, (uint32_t)n, bar);
+        }
+    }
+    uint32_t tb[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) tb[j] = smem_u32(tile) + (uint32_t)(((lane + j) & 7) * 16);
+    const int vec_ok = (((ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0)) ? 4
+                       : (((ldo & 1) == 0) && ((reinterpret_cast<uintptr_t>(out) & 7) == 0)) ? 2 : 1;
+
+    mbar_wait(bar, 0);
+    if (gram_seg >= 0 && gram_out != nullptr)  // first, by the warps that own output blocks (see sell_pass_kernel)
+        tile_gram_accumulate<float>(tile, 32, tile_rows, k, gram_out + (size_t)gram_seg * k * k, 1.0);
+    int s = 0;
+    if (lane == 0) s = atomicAdd(next_slice, 1);
+    s = __shfl_sync(INMF_FULL_MASK, s, 0);
+    int64_t base = 0, lim = 0;
+    if (s < slice_end) {
+        base = slice_ptr[s];
+        lim = slice_ptr[s + 1];
+    }
+
+    while (s < slice_end) {
+        const int L2 = (int)((lim - base) >> 5);
+        const int4* __restrict__ p = pairs + base + lane;
+        const int rid = rowid[(size_t)s * 32 + lane];
+        float acc[8][4];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int u = 0; u < 4; ++u) acc[j][u] = 0.f;
+        const int4 z4 = make_int4(0, 0, 0, 0);
+        int4 A = (0 < L2) ? sell_ld(p) : z4;
+        int4 B = (1 < L2) ? sell_ld(p + 32) : z4;
+        for (int j = 0; j < L2; j += 2) {
+            const int4 A2 = (j + 2 < L2) ? sell_ld(p + (size_t)(j + 2) * 32) : z4;
+            const int4 B2 = (j + 3 < L2) ? sell_ld(p + (size_t)(j + 3) * 32) : z4;
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+                const int off = h == 0 ? A.x : h == 1 ? A.z : h == 2 ? B.x : B.z;
+                const float v = __int_as_float(h == 0 ? A.y : h == 1 ? A.w : h == 2 ? B.y : B.w);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    float m[4];
+                    lds128(tb[c] + (uint32_t)off, m);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) acc[c][u] = fmaf(v, m[u], acc[c][u]);
+                }
+            }
+            A = A2;
+            B = B2;
+        }
+        int sn = 0;
+        if (lane == 0) sn = atomicAdd(next_slice, 1);
+        sn = __shfl_sync(INMF_FULL_MASK, sn, 0);
+        int64_t nbase = 0, nlim = 0;
+        if (sn < slice_end) {
+            nbase = slice_ptr[sn];
+            nlim = slice_ptr[sn + 1];
+        }
+        if (rid >= 0) {
+            float* o = out + (out_row_base + rid) * ldo;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) sell_out4(o, ((lane + c) & 7) * 4, k, acc[c], vec_ok);
+        }
+        s = sn;
+        base = nbase;
+        lim = nlim;
     }
 }
 
 // Builder: copies the rows listed in slice_rows (ptr indices of the row-ordered blocked format, -1 = no row) into
-// the step-interleaved slices.  One warp per slice; lane = (row i = lane / 4, step-pair phase c = lane % 4).
+// the step-interleaved slices of HEIGHT rows.  One warp per slice; HEIGHT = 8: lane = (row i = lane / 4, step-pair
+// phase c = lane % 4); HEIGHT = 32: lane = row.
+template <int HEIGHT>
 __global__ void __launch_bounds__(256) sell_fill_kernel(const int64_t* __restrict__ ptr, const int2* __restrict__ src,
                                                         const int64_t* __restrict__ slice_rows,
                                                         const int64_t* __restrict__ slice_ptr, int64_t nslices,
                                                         int4* __restrict__ dst) {
+    constexpr int LPR = 32 / HEIGHT;  // lanes per row
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    const int i = lane >> 2, c = lane & 3;
+    const int i = lane / LPR, c = lane % LPR;
     for (int64_t s = warp0; s < nslices; s += nwarp) {
         const int64_t base = slice_ptr[s];
-        const int L2 = (int)((slice_ptr[s + 1] - base) >> 3);
-        const int64_t row = slice_rows[s * 8 + i];
+        const int L2 = (int)((slice_ptr[s + 1] - base) / HEIGHT);
+        const int64_t row = slice_rows[s * HEIGHT + i];
         int64_t beg = 0;
         int len = 0;
         if (row >= 0) {
             beg = ptr[row];
             len = (int)(ptr[row + 1] - beg);
         }
-        for (int jj = c; jj < L2; jj += 4) {
+        for (int jj = c; jj < L2; jj += LPR) {
             int4 q = make_int4(0, 0, 0, 0);
             if (2 * jj < len) {
                 const int2 a = src[beg + 2 * jj];
@@ -276,7 +406,7 @@ __global__ void __launch_bounds__(256) sell_fill_kernel(const int64_t* __restric
                 q.z = b.x;
                 q.w = b.y;
             }
-            dst[base + (int64_t)jj * 8 + i] = q;
+            dst[base + (int64_t)jj * HEIGHT + i] = q;
         }
     }
 }

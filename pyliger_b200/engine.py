@@ -75,6 +75,23 @@ def online_windows(total_iters, mbs, sub, n_global, row_base):
     return plan
 
 
+class DeviceMatrix(object):
+    """One dataset's scale_data already resident on the device as CSR (rowptr int64[n+1], colidx int32[nnz] sorted
+    within rows, vals): accepted wherever a scipy CSR matrix is (InmfEngine, DeviceCSR) and never uploaded."""
+
+    def __init__(self, rowptr, colidx, vals, shape):
+        self.rowptr, self.colidx, self.vals = rowptr, colidx, vals
+        self.shape = (int(shape[0]), int(shape[1]))
+        self.nnz = int(colidx.numel())
+        self._indptr_host = None
+
+    @property
+    def indptr(self):
+        if self._indptr_host is None:
+            self._indptr_host = self.rowptr.cpu().numpy()
+        return self._indptr_host
+
+
 class DeviceCSR(object):
     """All datasets' (local row slices of) scale_data concatenated by rows on the device."""
 
@@ -104,11 +121,14 @@ class DeviceCSR(object):
         for m, (lo, hi) in zip(mats, self.bounds):
             if m.shape[1] != self.g:
                 raise ValueError("all datasets must share the same genes (columns)")
-            twin = devcache.lookup(m, device)  # left on the device by scale_not_center: no upload
-            if not sps.isspmatrix_csr(m):
-                m = sps.csr_matrix(m)
-            if not m.has_sorted_indices:
-                m = m.sorted_indices()
+            if isinstance(m, DeviceMatrix):
+                twin = (m.rowptr, m.colidx, m.vals)
+            else:
+                twin = devcache.lookup(m, device)  # left on the device by scale_not_center: no upload
+                if not sps.isspmatrix_csr(m):
+                    m = sps.csr_matrix(m)
+                if not m.has_sorted_indices:
+                    m = m.sorted_indices()
             p0, p1 = int(m.indptr[lo]), int(m.indptr[hi])
             indptr.append(m.indptr[lo + 1:hi + 1].astype(np.int64) - p0 + off)
             if twin is not None:
@@ -309,7 +329,7 @@ class InmfEngine(object):
     def _blocked(self, p, work, nwork, dense, out, ldo, gram):
         """One tiled pass (out += X_blocked * dense tile): sliced, plain or split-tile kernel, as the format was built."""
         if isinstance(p, blocked.SellPass):
-            _lib.call("inmf_sell_pass_f32", "", work, nwork, p.slice_ptr, p.rowid, p.pairs4, dense, self.ldm, out, ldo,
+            _lib.call("inmf_sell_pass_f32", "", work, nwork, p.slice_ptr, p.rowid, p.pairs4, p.height, dense, self.ldm, out, ldo,
                       self.k, p.max_tile_rows, gram, _stream())
             return
         name, sfx = ("inmf_blocked_split_f32", "") if p.split else ("inmf_blocked_spmm", self.sfx)

@@ -14,9 +14,23 @@ import torch
 
 import os
 
-CHUNK_BYTES = int(os.environ.get("INMF_STAGE_CHUNK_MB", "8")) << 20
-# = host threads copying into the pinned ring (measured at C2 on a 16-core host: 8 -> 14-19 ms, 16 -> 12.7 ms)
-NBUF = int(os.environ.get("INMF_STAGE_BUFFERS", str(max(4, min(16, os.cpu_count() or 8)))))
+CHUNK_BYTES = 8 << 20
+
+
+def _default_threads():
+    """Host threads copying into the pinned ring (measured at C2 on a 16-core host: 8 -> 14-19 ms, 16 -> 12.7 ms):
+    one per core up to 16, shared fairly between the processes of a multi-GPU launch (torchrun's LOCAL_WORLD_SIZE) so
+    that 8 ranks do not run 128 copy threads on 32 cores."""
+    cores = os.cpu_count() or 8
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        pass
+    local_world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1))
+    return max(2, min(16, cores // local_world))
+
+
+NBUF = _default_threads()
 _TORCH_TO_NP = {torch.float32: np.float32, torch.float64: np.float64, torch.int32: np.int32, torch.int64: np.int64}
 
 _stagers = {}

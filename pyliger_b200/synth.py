@@ -128,3 +128,51 @@ def make_datasets_device(ns, g, k_true, density=0.08, seed0=1000, device="cuda",
         counts.append(sps.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))),
                                      shape=(int(n), g)))
     return scale_like_pyliger(counts)
+
+
+def make_datasets_resident(ns, g, k_true, density=0.08, seed0=1000, device="cuda", dtype=None, chunk=32768):
+    """The structured generator of ``make_datasets_device`` with everything left on the GPU: counts, the row-L1
+    normalisation, the per-gene RMS scaling (same maths as ``scale_like_pyliger``) and the CSR arrays.  Returns a list
+    of ``engine.DeviceMatrix`` (what the device-timed legs of bench.py feed to InmfEngine for the workloads that are too
+    large to round-trip through host scipy matrices in a bench run, e.g. configs[3]: 2 M cells x 5 k genes).
+    Cells without counts keep an empty row; a gene that is all zero in a dataset keeps an empty column."""
+    import torch
+    from .engine import DeviceMatrix
+
+    dev = torch.device(device)
+    dtype = dtype or torch.float32
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(int(seed0) - 1)
+
+    def gamma_half(shape):
+        return torch.randn(shape, device=dev, dtype=torch.float32, generator=gen).square_().mul_(0.5)
+
+    W_star = gamma_half((k_true, g))
+    out = []
+    for i, n in enumerate(ns):
+        n = int(n)
+        gen.manual_seed(int(seed0) + i)
+        M = W_star + 0.3 * gamma_half((k_true, g))
+        Hs = gamma_half((2048, k_true))
+        s = _depth_for_density((Hs @ M).double().cpu().numpy(), density)
+        counts_per_row = torch.zeros(n, dtype=torch.int64, device=dev)
+        cols, vals = [], []
+        ss = torch.zeros(g, dtype=torch.float64, device=dev)
+        for lo in range(0, n, chunk):
+            m = min(chunk, n - lo)
+            C = torch.poisson((gamma_half((m, k_true)) @ M).mul_(float(s)), generator=gen)
+            rs = C.sum(dim=1, keepdim=True).clamp_(min=1.0)
+            Nm = C / rs                                   # row-L1 normalised (_normalization.py:95)
+            ss += Nm.double().square().sum(dim=0)
+            nz = C.nonzero(as_tuple=True)
+            counts_per_row[lo:lo + m] = torch.bincount(nz[0], minlength=m)
+            cols.append(nz[1].to(torch.int32))
+            vals.append(Nm[nz])
+            del C, Nm, nz
+        scaler = torch.where(ss > 0, 1.0 / torch.sqrt(ss / (n - 1)), torch.zeros_like(ss))   # _scale.py:100-101
+        colidx = torch.cat(cols)
+        v = (torch.cat(vals).double() * scaler[colidx.long()]).to(dtype)
+        rowptr = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(counts_per_row, 0, out=rowptr[1:])
+        out.append(DeviceMatrix(rowptr, colidx, v, (n, g)))
+    return out
