@@ -38,7 +38,7 @@ extern "C" {
 #endif
 
 #define INMF_MAX_K 64
-#define INMF_BPP_NSTATS 8 /* not_converged, factorizations, backup_flips, pivot_failures, rounds_sum, rounds_max, columns, reserved */
+#define INMF_BPP_NSTATS 8 /* not_converged, factorizations, backup_flips, pivot_failures, rounds_sum, rounds_max, columns, deferred (half-warp -> full-warp solver) */
 
 int32_t inmf_version(void);
 const char* inmf_last_error(void);
@@ -57,19 +57,28 @@ int64_t inmf_launch_count(void);
  *   warm     bit 0: warm start from mask; bit 1 (needs ginv_ws): solve a partition on its active-set
  *            complement through G^-1 whenever that is the smaller system (same solution; meant for
  *            well-conditioned G such as the H-update's, whose solutions are mostly passive)
+ *            bit 2: Y is not an output but a buffer to CLEAR: the k entries of every solved column are set to 0
+ *            (the ALS loop ping-pongs two right-hand-side buffers; the one pass 1 accumulates into next is
+ *            cleared here instead of by a separate memset on the critical path)
  *   seg_off  device int64[nseg+1] column ranges;  max_seg_cols = max segment length (host value)
  *   stats    device int64[INMF_BPP_NSTATS], accumulated (caller zeroes)
- *   ginv_ws  device double[nseg][k][k] workspace or NULL.  If given, G^-1 is formed per segment first
- *            and the "all indices passive" solves (the first round of every cold start on non-negative
- *            right-hand sides) become one k x k mat-vec, and passive sets larger than 31 (k > 31) are
- *            solved on the complement; the result is the same NNLS solution.
+ *   ws, ws_bytes  device workspace or NULL, sized with inmf_bpp_workspace_bytes():
+ *            [nseg][k][k] doubles: G^-1 is formed per segment first, the "all indices passive" solves (the first
+ *            round of every cold start on non-negative right-hand sides) become one k x k mat-vec, and passive
+ *            sets larger than the register solver's limit are solved on the complement (same NNLS solution);
+ *            the rest (int32 counters and per-segment column lists) lets the HALF-WARP solver run first: two
+ *            columns per warp, 16 lanes each, partitions of <= 15 unknowns; a column with a larger partition is
+ *            put on its segment's list and solved by the full-warp kernel afterwards, from its original start
+ *            set.  A workspace of just nseg*k*k doubles is accepted (inverse only, full-warp solver).
+ *            warm bit 3 switches the half-warp solver off.
  */
+int64_t inmf_bpp_workspace_bytes(int64_t max_seg_cols, int32_t nseg, int32_t k);
 int32_t inmf_bpp_f32(const double* G, const float* R, int64_t ldr, float* X, int64_t ldx, float* Y,
                      int64_t ldy, uint64_t* mask, int32_t warm, const int64_t* seg_off, int32_t nseg,
-                     int64_t max_seg_cols, int32_t k, int64_t* stats, double* ginv_ws, void* stream);
+                     int64_t max_seg_cols, int32_t k, int64_t* stats, void* ws, int64_t ws_bytes, void* stream);
 int32_t inmf_bpp_f64(const double* G, const double* R, int64_t ldr, double* X, int64_t ldx, double* Y,
                      int64_t ldy, uint64_t* mask, int32_t warm, const int64_t* seg_off, int32_t nseg,
-                     int64_t max_seg_cols, int32_t k, int64_t* stats, double* ginv_ws, void* stream);
+                     int64_t max_seg_cols, int32_t k, int64_t* stats, void* ws, int64_t ws_bytes, void* stream);
 
 /* H-update preparation per segment s (replaces the hstack/AtA of _iNMF_ANLS.py:137 +
  * _utilities.py:212 and _online_iNMF.py:421): Mt[s] = Wt + Vt[s] (zero padded to ldm),

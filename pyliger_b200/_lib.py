@@ -14,7 +14,7 @@ _I32, _I64, _F64, _PTR = _c.c_int32, _c.c_int64, _c.c_double, _c.c_void_p
 
 # name -> argtypes (without the _f32/_f64 suffix; P = device pointer or stream)
 _TYPED = {
-    "inmf_bpp": [_PTR, _PTR, _I64, _PTR, _I64, _PTR, _I64, _PTR, _I32, _PTR, _I32, _I64, _I32, _PTR, _PTR, _PTR],
+    "inmf_bpp": [_PTR, _PTR, _I64, _PTR, _I64, _PTR, _I64, _PTR, _I32, _PTR, _I32, _I64, _I32, _PTR, _PTR, _I64, _PTR],
     "inmf_prep": [_PTR, _PTR, _PTR, _I64, _PTR, _PTR, _PTR, _F64, _I32, _I64, _I32, _PTR],
     "inmf_spmm": [_PTR, _PTR, _PTR, _PTR, _I64, _I64, _PTR, _I64, _PTR, _I32, _I64, _I32, _PTR],
     "inmf_stats": [_PTR, _PTR, _PTR, _PTR, _I64, _PTR, _PTR, _I64, _PTR, _I32, _I64, _I32, _PTR],
@@ -33,7 +33,7 @@ _TYPED = {
     "inmf_blockfmt2": [_I32, _PTR, _PTR, _PTR, _PTR, _I32, _I32, _I32, _I32, _PTR, _PTR, _PTR, _PTR, _PTR],
 }
 
-EXPORTED_SYMBOLS = ["inmf_version", "inmf_last_error", "inmf_launch_count", "inmf_tc_selftest",
+EXPORTED_SYMBOLS = ["inmf_version", "inmf_last_error", "inmf_launch_count", "inmf_bpp_workspace_bytes", "inmf_tc_selftest",
                     "inmf_tc_relayout_f32", "inmf_tc_pass_f32", "inmf_tc_debug_buffer", "inmf_select_count", "inmf_mt19937_uniform", "inmf_blocked_split_f32", "inmf_blocked_wide_f32",
                     "inmf_sell_pass_f32", "inmf_sell_fill_f32"] + [
     "%s_%s" % (n, t) for n in _TYPED for t in ("f32", "f64")
@@ -62,6 +62,8 @@ def load():
     lib.inmf_last_error.argtypes = []
     lib.inmf_launch_count.restype = _I64
     lib.inmf_launch_count.argtypes = []
+    lib.inmf_bpp_workspace_bytes.restype = _I64
+    lib.inmf_bpp_workspace_bytes.argtypes = [_I64, _I32, _I32]
     lib.inmf_tc_selftest.restype = _I32
     lib.inmf_tc_selftest.argtypes = [_PTR, _PTR, _PTR, _I32, _I32, _PTR]
     lib.inmf_tc_relayout_f32.restype = _I32
@@ -111,3 +113,19 @@ def call(name, suffix, *args):
 def launch_count():
     """Kernels launched by libinmf_b200.so so far in this process."""
     return int(load().inmf_launch_count())
+
+
+def bpp_workspace(max_seg_cols, nseg, k, device):
+    """Workspace tensor for inmf_bpp_* (G^-1 + the half-warp solver's deferral lists), sized by the library."""
+    import torch
+    nbytes = int(load().inmf_bpp_workspace_bytes(int(max_seg_cols), int(nseg), int(k)))
+    if nbytes < 0:
+        raise InmfError("inmf_bpp_workspace_bytes: bad arguments")
+    return torch.empty((nbytes + 7) // 8, dtype=torch.float64, device=device)
+
+
+def ws_args(ws):
+    """(pointer, byte count) pair of a workspace tensor (or (None, 0))."""
+    if ws is None:
+        return None, 0
+    return ws, ws.numel() * ws.element_size()

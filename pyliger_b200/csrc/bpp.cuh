@@ -119,6 +119,7 @@ __device__ __forceinline__ T warp_max(T v) {
 }
 
 #include "bpp_fast.cuh"
+#include "bpp16.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // General path: any |P| <= 64, L in the shared scratch.

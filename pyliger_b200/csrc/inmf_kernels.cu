@@ -81,12 +81,14 @@ __global__ void __launch_bounds__(1024) ginv_kernel(const double* __restrict__ G
 template <typename T, bool COMP>
 __global__ void __launch_bounds__(BPP_THREADS, COMP ? BPP_COMP_MIN_BLOCKS : BPP_MIN_BLOCKS) bpp_kernel(const double* __restrict__ G, const double* __restrict__ Ginv, const T* R, int64_t ldr, T* X, int64_t ldx,
                            T* __restrict__ Y, int64_t ldy, uint64_t* __restrict__ mask, int warm, const int64_t* __restrict__ seg_off, int k,
-                           long long* __restrict__ stats) {
+                           long long* __restrict__ stats, const int* __restrict__ list_count,
+                           const int32_t* __restrict__ list, int64_t list_cap) {
+    // list mode (list != nullptr): only the columns the half-warp solver deferred, list[seg * list_cap + i]
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* smem = reinterpret_cast<T*>(smem_raw);
     const int seg = blockIdx.y;
     const int64_t c_begin = seg_off[seg];
-    const int64_t ncols = seg_off[seg + 1] - c_begin;
+    const int64_t ncols = list ? (int64_t)list_count[seg] : seg_off[seg + 1] - c_begin;
     const int nwarps = blockDim.x >> 5;
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -112,7 +114,7 @@ __global__ void __launch_bounds__(BPP_THREADS, COMP ? BPP_COMP_MIN_BLOCKS : BPP_
 
     long long n_notconv = 0, n_fact = 0, n_backup = 0, n_fail = 0, n_rounds = 0, max_rounds = 0, n_cols = 0;
     for (int64_t c = (int64_t)blockIdx.x * nwarps + warp; c < ncols; c += (int64_t)gridDim.x * nwarps) {
-        const int64_t col = c_begin + c;
+        const int64_t col = c_begin + (list ? (int64_t)list[(size_t)seg * list_cap + c] : c);
         const T* r = R + col * ldr;
         const T r0 = (lane < k) ? r[lane] : T(0);
         const T r1 = (lane + 32 < k) ? r[lane + 32] : T(0);
@@ -123,10 +125,11 @@ __global__ void __launch_bounds__(BPP_THREADS, COMP ? BPP_COMP_MIN_BLOCKS : BPP_
         T* x = X + col * ldx;
         if (lane < k) x[lane] = x0;
         if (lane + 32 < k) x[lane + 32] = x1;
-        if (Y) {
+        if (Y) {  // warm bit 2: Y is a scratch buffer to clear (the H-update's spare right-hand-side buffer)
             T* y = Y + col * ldy;
-            if (lane < k) y[lane] = y0;
-            if (lane + 32 < k) y[lane + 32] = y1;
+            const bool clr = (warm & 4) != 0;
+            if (lane < k) y[lane] = clr ? T(0) : y0;
+            if (lane + 32 < k) y[lane + 32] = clr ? T(0) : y1;
         }
         if (mask && lane == 0) mask[col] = P;
         if (lane == 0) {
@@ -159,14 +162,140 @@ __global__ void __launch_bounds__(BPP_THREADS, COMP ? BPP_COMP_MIN_BLOCKS : BPP_
     }
 }
 
+// Half-warp solver (bpp16.cuh): 8 tiles of 16 lanes per CTA, one column per tile.
+#define BPP16_THREADS 128
+template <typename T, int NF>
+__global__ void __launch_bounds__(BPP16_THREADS, sizeof(T) == 8 ? 4 : (NF <= 2 ? 7 : 6))
+bpp16_kernel(const double* __restrict__ G, const double* __restrict__ Ginv, const T* R, int64_t ldr, T* X, int64_t ldx,
+             T* __restrict__ Y, int64_t ldy, uint64_t* __restrict__ mask, int warm,
+             const int64_t* __restrict__ seg_off, int k, long long* __restrict__ stats, int* __restrict__ defer_count,
+             int32_t* __restrict__ defer_list, int64_t list_cap) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* smem = reinterpret_cast<T*>(smem_raw);
+    const int seg = blockIdx.y;
+    const int64_t c_begin = seg_off[seg];
+    const int64_t ncols = seg_off[seg + 1] - c_begin;
+    constexpr int TILES = BPP16_THREADS / 16;
+    const int tile = threadIdx.x >> 4, t = threadIdx.x & 15;
+    const int half = (threadIdx.x >> 4) & 1;
+    const unsigned tmask = 0xffffu << (16 * half);
+    if ((int64_t)blockIdx.x * TILES >= ncols) return;
+
+    const int ldg = k | 1;
+    T* Gs = smem;
+    const double* Gseg = G + (size_t)seg * k * k;
+    for (int e = threadIdx.x; e < k * k; e += blockDim.x) Gs[(e / k) * ldg + (e % k)] = (T)Gseg[e];
+    size_t goff = ((size_t)k * ldg + 3) & ~(size_t)3;
+    const T* Gis = nullptr;
+    if (Ginv != nullptr) {
+        const double* Iseg = Ginv + (size_t)seg * k * k;
+        T* Gi = smem + goff;
+        for (int e = threadIdx.x; e < k * k; e += blockDim.x) Gi[(e / k) * ldg + (e % k)] = (T)Iseg[e];
+        if (Iseg[0] == Iseg[0]) Gis = Gi;
+        goff *= 2;
+    }
+    __syncthreads();
+    Bpp16Scratch<T> sc = bpp16_carve<T>(smem + goff + (size_t)tile * bpp16_tile_scratch_elems<T>(NF), NF);
+    if (t < 8) reinterpret_cast<uint32_t*>(sc.idx)[t] = 0u;  // padded index reads stay in range
+    if (t < 4) sc.z[16 + t] = T(0);
+    __syncwarp(tmask);
+
+    long long n_notconv = 0, n_fact = 0, n_backup = 0, n_fail = 0, n_rounds = 0, max_rounds = 0, n_cols = 0, n_defer = 0;
+    for (int64_t c = (int64_t)blockIdx.x * TILES + tile; c < ncols; c += (int64_t)gridDim.x * TILES) {
+        const int64_t col = c_begin + c;
+        const T* rp = R + col * ldr;
+        T r[NF], x[NF], y[NF];
+#pragma unroll
+        for (int f = 0; f < NF; ++f) r[f] = (t + 16 * f < k) ? rp[t + 16 * f] : T(0);
+        uint64_t P = ((warm & 1) && mask) ? mask[col] : 0ull;
+        BppCounters cnt = {0, 0, 0, 0, true, {0, 0, 0, 0, 0, 0}};
+        const bool done = bpp16_column<T, NF>(Gs, Gis, ldg, sc, k, r, P, (warm & 1) != 0, (warm & 2) != 0, x, y, cnt,
+                                              tmask, t, half);
+        if (!done) {  // too large for a tile: the full-warp kernel redoes this column from its original start set
+            if (t == 0) {
+                const int slot = atomicAdd(&defer_count[seg], 1);
+                defer_list[(size_t)seg * list_cap + slot] = (int32_t)c;
+                n_defer++;
+            }
+            continue;
+        }
+        T* xo = X + col * ldx;
+#pragma unroll
+        for (int f = 0; f < NF; ++f)
+            if (t + 16 * f < k) xo[t + 16 * f] = x[f];
+        if (Y) {
+            T* yo = Y + col * ldy;
+            const bool clr = (warm & 4) != 0;
+#pragma unroll
+            for (int f = 0; f < NF; ++f)
+                if (t + 16 * f < k) yo[t + 16 * f] = clr ? T(0) : y[f];
+        }
+        if (mask && t == 0) mask[col] = P;
+        if (t == 0) {
+            n_cols++;
+            n_notconv += cnt.ok ? 0 : 1;
+            n_fact += cnt.nfact;
+            n_backup += cnt.nbackup;
+            n_fail += cnt.nfail;
+            n_rounds += cnt.rounds;
+            max_rounds = max_rounds > cnt.rounds ? max_rounds : cnt.rounds;
+        }
+    }
+    if (stats && t == 0 && (n_cols || n_defer)) {
+        atomicAdd((unsigned long long*)&stats[0], (unsigned long long)n_notconv);
+        atomicAdd((unsigned long long*)&stats[1], (unsigned long long)n_fact);
+        atomicAdd((unsigned long long*)&stats[2], (unsigned long long)n_backup);
+        atomicAdd((unsigned long long*)&stats[3], (unsigned long long)n_fail);
+        atomicAdd((unsigned long long*)&stats[4], (unsigned long long)n_rounds);
+        atomicMax(&stats[5], max_rounds);
+        atomicAdd((unsigned long long*)&stats[6], (unsigned long long)n_cols);
+        atomicAdd((unsigned long long*)&stats[7], (unsigned long long)n_defer);
+    }
+}
+
+// Workspace layout of inmf_bpp_*: [G^-1: nseg*k*k doubles][deferral counters: nseg int32, padded to 16 bytes]
+// [deferral lists: nseg * max_seg_cols int32].
+static inline size_t bpp_ws_ginv_bytes(int nseg, int k) { return (size_t)nseg * k * k * sizeof(double); }
+static inline size_t bpp_ws_count_bytes(int nseg) { return (((size_t)nseg * sizeof(int)) + 15) & ~(size_t)15; }
+extern "C" int64_t inmf_bpp_workspace_bytes(int64_t max_seg_cols, int32_t nseg, int32_t k) {
+    if (max_seg_cols < 0 || nseg < 1 || k < 1) return -1;
+    return (int64_t)(bpp_ws_ginv_bytes(nseg, k) + bpp_ws_count_bytes(nseg) + (size_t)nseg * max_seg_cols * sizeof(int32_t));
+}
+
+template <typename T, int NF>
+static int32_t bpp16_launch_one(const double* G, const double* ginv, const T* R, int64_t ldr, T* X, int64_t ldx, T* Y,
+                                int64_t ldy, uint64_t* mask, int32_t warm, const int64_t* seg_off, int32_t nseg,
+                                int64_t max_seg_cols, int32_t k, int64_t* stats, int* defer_count, int32_t* defer_list,
+                                cudaStream_t st) {
+    const int ldg = k | 1;
+    const size_t goff = (((size_t)k * ldg + 3) & ~(size_t)3) * (ginv ? 2 : 1);
+    const size_t smem = (goff + (BPP16_THREADS / 16) * bpp16_tile_scratch_elems<T>(NF)) * sizeof(T);
+    INMF_OPTIN_SMEM((bpp16_kernel<T, NF>), 227 * 1024);
+    constexpr int TILES = BPP16_THREADS / 16;
+    int64_t blocks = (max_seg_cols + TILES - 1) / TILES;
+    int64_t cap = ((int64_t)inmf_num_sms() * 2 * 8 + nseg - 1) / nseg;
+    if (cap < 1) cap = 1;
+    if (blocks > cap) blocks = cap;
+    bpp16_kernel<T, NF><<<dim3((unsigned)blocks, (unsigned)nseg), BPP16_THREADS, smem, st>>>(
+        G, ginv, R, ldr, X, ldx, Y, ldy, mask, warm, seg_off, k, (long long*)stats, defer_count, defer_list, max_seg_cols);
+    INMF_LAUNCH_CHECK();
+    return 0;
+}
+
 template <typename T>
 static int32_t bpp_launch(const double* G, const T* R, int64_t ldr, T* X, int64_t ldx, T* Y, int64_t ldy,
                           uint64_t* mask, int32_t warm, const int64_t* seg_off, int32_t nseg,
-                          int64_t max_seg_cols, int32_t k, int64_t* stats, double* ginv_ws, void* stream) {
+                          int64_t max_seg_cols, int32_t k, int64_t* stats, void* ws, int64_t ws_bytes, void* stream) {
     INMF_REQUIRE(k >= 1 && k <= INMF_MAX_K, "k must be in [1, 64]");
     INMF_REQUIRE(nseg >= 1 && nseg <= 65535, "nseg out of range");
     INMF_REQUIRE(ldr >= k && ldx >= k && (Y == nullptr || ldy >= k), "leading dimensions must be >= k");
     if (max_seg_cols <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    // workspace: the inverse needs the first part, the half-warp solver's deferral lists the rest
+    double* ginv_ws = (ws != nullptr && ws_bytes >= (int64_t)bpp_ws_ginv_bytes(nseg, k)) ? (double*)ws : nullptr;
+    INMF_REQUIRE(ws == nullptr || ginv_ws != nullptr, "workspace smaller than nseg * k * k doubles");
+    const bool have_lists = ws != nullptr && ws_bytes >= inmf_bpp_workspace_bytes(max_seg_cols, nseg, k) &&
+                            max_seg_cols < ((int64_t)1 << 31);
     const int ldg = k | 1;
     const size_t goff = (((size_t)k * ldg + 3) & ~(size_t)3) * (ginv_ws ? 2 : 1);
     const size_t per_warp = bpp_warp_scratch_elems<T>(k) * sizeof(T);
@@ -185,34 +314,56 @@ static int32_t bpp_launch(const double* G, const T* R, int64_t ldr, T* X, int64_
     if (ginv_ws != nullptr) {
         // the inverse is used in T arithmetic: accept it only while cond(G) * eps(T) stays small
         const double rcond_min = sizeof(T) == 4 ? 1e-4 : 1e-10;
-        ginv_kernel<<<(unsigned)nseg, 1024, (size_t)k * k * sizeof(double), (cudaStream_t)stream>>>(G, ginv_ws, k,
-                                                                                                rcond_min);
+        ginv_kernel<<<(unsigned)nseg, 1024, (size_t)k * k * sizeof(double), st>>>(G, ginv_ws, k, rcond_min);
         INMF_LAUNCH_CHECK();
     }
+    const bool comp_kernel = k > BPP_FAST_MAX_P || ((warm & 2) && ginv_ws != nullptr);
+    // Half-warp solver first (two columns per warp) when its partitions can be expected to fit 15 unknowns: always
+    // for k <= 32 (one side of every partition has <= 16), for larger k only with the inverse (complement solves).
+    // warm bit 3 switches it off.  What it defers is solved by the full-warp kernel in list mode.
+    const bool use16 = have_lists && !(warm & 8) && (k <= 32 || ginv_ws != nullptr);
+    int* defer_count = nullptr;
+    int32_t* defer_list = nullptr;
+    if (use16) {
+        defer_count = reinterpret_cast<int*>((unsigned char*)ws + bpp_ws_ginv_bytes(nseg, k));
+        defer_list = reinterpret_cast<int32_t*>((unsigned char*)defer_count + bpp_ws_count_bytes(nseg));
+        INMF_CUDA_CHECK(cudaMemsetAsync(defer_count, 0, bpp_ws_count_bytes(nseg), st));
+#define INMF_BPP16_ARGS G, ginv_ws, R, ldr, X, ldx, Y, ldy, mask, warm, seg_off, nseg, max_seg_cols, k, stats, defer_count, defer_list, st
+        int32_t rc;
+        if (k <= 32) rc = bpp16_launch_one<T, 2>(INMF_BPP16_ARGS);
+        else if (k <= 48) rc = bpp16_launch_one<T, 3>(INMF_BPP16_ARGS);
+        else rc = bpp16_launch_one<T, 4>(INMF_BPP16_ARGS);
+#undef INMF_BPP16_ARGS
+        if (rc != 0) return rc;
+        // the deferred columns: a small grid is enough (usually none); CTAs without work leave at once
+        int64_t lblocks = blocks;
+        const int64_t lcap = ((int64_t)inmf_num_sms() * 2 + nseg - 1) / nseg;
+        if (lblocks > lcap) lblocks = lcap;
+        blocks = lblocks;
+    }
     dim3 grid((unsigned)blocks, (unsigned)nseg);
-    if (k > BPP_FAST_MAX_P || ((warm & 2) && ginv_ws != nullptr))  // complement path needed / asked for
-        bpp_kernel<T, true><<<grid, nwarps * 32, smem, (cudaStream_t)stream>>>(
-            G, ginv_ws, R, ldr, X, ldx, Y, ldy, mask, warm, seg_off, k, (long long*)stats);
+    if (comp_kernel)
+        bpp_kernel<T, true><<<grid, nwarps * 32, smem, st>>>(G, ginv_ws, R, ldr, X, ldx, Y, ldy, mask, warm, seg_off, k,
+                                                            (long long*)stats, defer_count, defer_list, max_seg_cols);
     else
-        bpp_kernel<T, false><<<grid, nwarps * 32, smem, (cudaStream_t)stream>>>(
-            G, ginv_ws, R, ldr, X, ldx, Y, ldy, mask, warm, seg_off, k, (long long*)stats);
+        bpp_kernel<T, false><<<grid, nwarps * 32, smem, st>>>(G, ginv_ws, R, ldr, X, ldx, Y, ldy, mask, warm, seg_off, k,
+                                                             (long long*)stats, defer_count, defer_list, max_seg_cols);
     INMF_LAUNCH_CHECK();
     return 0;
 }
-
 extern "C" int32_t inmf_bpp_f32(const double* G, const float* R, int64_t ldr, float* X, int64_t ldx, float* Y,
                                 int64_t ldy, uint64_t* mask, int32_t warm, const int64_t* seg_off,
-                                int32_t nseg, int64_t max_seg_cols, int32_t k, int64_t* stats, double* ginv_ws,
-                                void* stream) {
-    return bpp_launch<float>(G, R, ldr, X, ldx, Y, ldy, mask, warm, seg_off, nseg, max_seg_cols, k, stats,
-                             ginv_ws, stream);
+                                int32_t nseg, int64_t max_seg_cols, int32_t k, int64_t* stats, void* ws,
+                                int64_t ws_bytes, void* stream) {
+    return bpp_launch<float>(G, R, ldr, X, ldx, Y, ldy, mask, warm, seg_off, nseg, max_seg_cols, k, stats, ws,
+                             ws_bytes, stream);
 }
 extern "C" int32_t inmf_bpp_f64(const double* G, const double* R, int64_t ldr, double* X, int64_t ldx,
                                 double* Y, int64_t ldy, uint64_t* mask, int32_t warm, const int64_t* seg_off,
-                                int32_t nseg, int64_t max_seg_cols, int32_t k, int64_t* stats, double* ginv_ws,
-                                void* stream) {
-    return bpp_launch<double>(G, R, ldr, X, ldx, Y, ldy, mask, warm, seg_off, nseg, max_seg_cols, k, stats,
-                              ginv_ws, stream);
+                                int32_t nseg, int64_t max_seg_cols, int32_t k, int64_t* stats, void* ws,
+                                int64_t ws_bytes, void* stream) {
+    return bpp_launch<double>(G, R, ldr, X, ldx, Y, ldy, mask, warm, seg_off, nseg, max_seg_cols, k, stats, ws,
+                              ws_bytes, stream);
 }
 
 // =================================================================================================

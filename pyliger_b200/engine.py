@@ -242,7 +242,10 @@ class InmfEngine(object):
         self.Rw = z(g, k)
         self.Gv = z(N, k, k, dtype=f64)
         self.Gw = z(1, k, k, dtype=f64)
-        self.ginv_ws = z(max(N, 1), k, k, dtype=f64)  # G^-1 workspace of the cold-start BPP solves
+        # BPP workspaces (G^-1 + the half-warp solver's deferral lists), one per solve shape
+        self.ws_H = _lib.bpp_workspace(max(max(X.n_own) if N else 0, 1), max(N, 1), k, dev)
+        self.ws_V = _lib.bpp_workspace(g, max(N, 1), k, dev)
+        self.ws_W = _lib.bpp_workspace(g, 1, k, dev)
         self.xnorm2 = z(N, dtype=f64)
         self.obj = z(1, dtype=f64)
         self.bpp_stats = torch.zeros(3, 8, dtype=torch.int64, device=dev)  # rows: H, V, W solves
@@ -319,7 +322,9 @@ class InmfEngine(object):
             _lib.call("inmf_tc_pass_f32", "", t.work, t.nwork, t.ptr, t.pairs, self.dc1_hi, self.dc1_lo, out, self.ldm,
                       k, t.npad, 1 if self.tc_three_pass else 0, 0, _stream())
         elif full and out is self.H and self.pass1 is not None:
-            out.zero_()
+            if out.data_ptr() != self._clean_ptr:  # not cleared by the previous H solve (bpp_H(clear=...)): do it now
+                out.zero_()
+            self._clean_ptr = None
             p = self.pass1
             self._blocked(p, p.work, p.nwork, self.Mt, out, self.ldm, None)
         else:
@@ -338,20 +343,15 @@ class InmfEngine(object):
         _lib.call(name, sfx, work, nwork, p.ptr, p.pairs, dense, self.ldm, out, ldo, self.k, p.max_tile_rows, gram,
                   _stream())
 
-    def _ginv(self, warm):
-        """Workspace for G^-1: cold starts use it for the all-passive first round, k > 31 for passive sets
-        larger than the 31-row register solver (solved on the complement instead)."""
-        return self.ginv_ws if (not warm or self.k > 31) else None
-
     # V / W solves: 2 = complement preference as for H.  Measured slower (C2: V 0.081 -> 0.116 ms, W 0.048 ->
     # 0.081 ms): gene loadings are sparse, so their passive sets are the small side already.
     vw_flags = 0
 
-    def _ginv_vw(self, warm):
-        return self.ginv_ws if self.vw_flags else self._ginv(warm)
+    _clean_ptr = None  # data_ptr of the H-shaped buffer known to be all zero (cleared by the last bpp_H(clear=...))
 
-    def bpp_H(self, seg_desc=None, max_rows=None, out=None, mask=None, warm=False, nseg=None):
-        """In-place batched BPP on the right-hand sides produced by rhs_H."""
+    def bpp_H(self, seg_desc=None, max_rows=None, out=None, mask=None, warm=False, nseg=None, clear=None):
+        """In-place batched BPP on the right-hand sides produced by rhs_H.  ``clear``: an H-shaped buffer whose
+        solved columns are zeroed by the same kernel (the spare buffer the next pass 1 accumulates into)."""
         if seg_desc is None:
             seg_off = self.seg_full_off
         else:
@@ -363,8 +363,14 @@ class InmfEngine(object):
             return
         k = self.k
         # bit 1: G = (W+V)(W+V)' + lambda VV' is well conditioned and H is mostly passive -> complement solves
-        _lib.call("inmf_bpp", self.sfx, self.G, out, self.ldm, out, self.ldm, None, 0, mask, (1 if warm else 0) | 2,
-                  seg_off, nseg, max_rows, k, self.bpp_stats[0], self.ginv_ws, _stream())
+        ws = self.ws_H
+        if max_rows > self.max_rows_full or nseg > self.N:  # windows larger than the sized workspace (never in practice)
+            ws = _lib.bpp_workspace(max_rows, nseg, k, self.device)
+        _lib.call("inmf_bpp", self.sfx, self.G, out, self.ldm, out, self.ldm, clear, self.ldm if clear is not None else 0,
+                  mask, (1 if warm else 0) | 2 | (4 if clear is not None else 0), seg_off, nseg, max_rows, k,
+                  self.bpp_stats[0], *_lib.ws_args(ws), _stream())
+        if clear is not None:
+            self._clean_ptr = clear.data_ptr()
 
     def solve_H(self, seg_desc=None, max_rows=None, out=None, mask=None, warm=False, nseg=None):
         """out[q,:] = argmin_{h>=0} for every row of the windows in seg_desc (default: all owned cells)."""
@@ -404,15 +410,15 @@ class InmfEngine(object):
         _lib.call("inmf_rhs_v", self.sfx, self.St, self.Wt, self.HtH, self.Rv, self.Gv, self.lam, N, g, k,
                   _stream())
         _lib.call("inmf_bpp", self.sfx, self.Gv, self.Rv, k, self.Vt, k, None, 0, self.mask_V,
-                  (1 if warm else 0) | self.vw_flags, self.seg_genes, N, g, k, self.bpp_stats[1], self._ginv_vw(warm),
-                  _stream())
+                  (1 if warm else 0) | self.vw_flags, self.seg_genes, N, g, k, self.bpp_stats[1],
+                  *_lib.ws_args(self.ws_V), _stream())
 
     def solve_W(self, warm=False):
         k, g, N = self.k, self.g, self.N
         _lib.call("inmf_rhs_w", self.sfx, self.St, self.Vt, self.HtH, self.Rw, self.Gw, N, g, k, _stream())
         _lib.call("inmf_bpp", self.sfx, self.Gw, self.Rw, k, self.Wt, k, None, 0, self.mask_W,
-                  (1 if warm else 0) | self.vw_flags, self.seg_w, 1, g, k, self.bpp_stats[2], self._ginv_vw(warm),
-                  _stream())
+                  (1 if warm else 0) | self.vw_flags, self.seg_w, 1, g, k, self.bpp_stats[2],
+                  *_lib.ws_args(self.ws_W), _stream())
 
     def objective(self):
         """Objective from the current St/HtH and the Mt/Gwv/Gvv of the last prep(). Device scalar."""
@@ -471,9 +477,10 @@ class InmfEngine(object):
 
         Requires prep() of the current W, V (done by initial_objective() / the previous iteration)."""
         if not self._begun:
-            self.rhs_H()
+            self.als_begin()
         self._begun = False
-        self.bpp_H(mask=self.mask_H, warm=warm)
+        # the buffer that held the previous iteration's H is dead from here on: the solve clears it for the next pass 1
+        self.bpp_H(mask=self.mask_H, warm=warm, clear=self.H_alt)
         self.stats()
         self.solve_V(warm=warm)
         self.solve_W(warm=warm)
@@ -490,11 +497,13 @@ class InmfEngine(object):
     _obj_event = None
 
     def als_begin(self):
-        """Enqueue pass 1 of the next iteration into the spare H buffer (the current H stays intact in H_alt)."""
+        """Enqueue pass 1 of the next iteration into the spare H buffer (the current H stays intact in H_alt).
+        The two buffers ping-pong: pass 1 accumulates into the one the previous H solve cleared."""
         if self._begun:
             return
         if self.H_alt is None:
             self.H_alt = torch.zeros_like(self.H)
+            self._clean_ptr = self.H_alt.data_ptr()
         self.H, self.H_alt = self.H_alt, self.H
         self.rhs_H()
         self._begun = True
@@ -552,7 +561,7 @@ class InmfEngine(object):
     def bpp_report(self):
         s = self.bpp_stats.cpu().numpy()
         names = ("not_converged", "factorizations", "backup_flips", "pivot_failures", "rounds_sum",
-                 "rounds_max", "columns")
+                 "rounds_max", "columns", "deferred")
         return {which: dict(zip(names, map(int, s[r]))) for r, which in enumerate(("H", "V", "W"))}
 
     # ------------------------------------------------------------------ online iNMF

@@ -4,8 +4,11 @@
 Keyword-only extensions (defaults preserve reference behaviour):
   dtype       "float64" (default, parity mode) or "float32" (throughput mode)
   device      torch device (default: current CUDA device)
-  warm_start  start each BPP solve from the previous iteration's passive sets (same unique NNLS
-              solution, fewer pivoting rounds); default False = the reference's cold start
+  warm_start  start each BPP solve from the previous iteration's passive sets -- the reference solver's own
+              ``init`` argument (_utilities.py:222-225); NNLS with an SPD Gram matrix has a unique solution, so the
+              iterates are the same (tests: trajectories equal to 4e-16 in fp64 with and without) while the
+              solver needs ~2 instead of 4-5 factorisations per column.  Default True; False = the reference's
+              literal cold start (init=None) in every iteration
   return_info if True, return a dict with the per-iteration objectives and solver counters
               (the reference returns None; the default stays None)
   tensor_core None (default) = CUDA-core passes; "tf32x3" / "tf32" = experimental dense-tile tcgen05 form
@@ -53,7 +56,7 @@ def optimize_ALS(
     *,
     dtype="float64",
     device=None,
-    warm_start=False,
+    warm_start=True,
     return_info=False,
     progress=True,
     presharded=False,

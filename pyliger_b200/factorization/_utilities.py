@@ -28,8 +28,9 @@ def _solve_on_device(G, Rt, init_mask, k, dtype, device, want_Y=True):
         mask.copy_(init_mask)
         warm = 1
     # G^-1 workspace: all-passive first round of a cold start; complement solves for passive sets > 31
-    ginv = None if (warm and k <= 31) else torch.empty(k, k, dtype=torch.float64, device=device)
-    _lib.call("inmf_bpp", sfx, G, Rt, k, X, k, Y, k, mask, warm, seg_off, 1, cols, k, stats, ginv, _stream())
+    # and the deferral list of the half-warp solver
+    ws = _lib.bpp_workspace(cols, 1, k, device)
+    _lib.call("inmf_bpp", sfx, G, Rt, k, X, k, Y, k, mask, warm, seg_off, 1, cols, k, stats, *_lib.ws_args(ws), _stream())
     return X, Y, mask, stats
 
 

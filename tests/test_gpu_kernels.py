@@ -187,7 +187,7 @@ def test_hals_sweep_golden(dev, golden_online, dtype, tol):
 def test_error_reporting(dev):
     from pyliger_b200 import _lib
     with pytest.raises(_lib.InmfError, match="k must be"):
-        _lib.call("inmf_bpp", "f32", 0, 0, 1, 0, 1, 0, 1, 0, 0, 0, 1, 1, 65, 0, 0, 0)
+        _lib.call("inmf_bpp", "f32", 0, 0, 1, 0, 1, 0, 1, 0, 0, 0, 1, 1, 65, 0, 0, 0, 0)
 
 
 def test_tcgen05_selftest_tile(dev):

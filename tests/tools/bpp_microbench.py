@@ -62,7 +62,7 @@ def main():
         Xo = torch.empty_like(Rt)
         mask = torch.zeros(args.cols, dtype=torch.int64, device=dev)
         seg = torch.tensor([0, args.cols], dtype=torch.int64, device=dev)
-        ginv = torch.empty(k, k, dtype=torch.float64, device=dev)
+        ginv = _lib.bpp_workspace(args.cols, 1, k, dev)
         res = {"k": k, "cols": args.cols, "dtype": args.dtype}
         for mode, warm in (("cold", 0), ("warm", 1)):
             times = []
@@ -71,7 +71,7 @@ def main():
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
                 _lib.call("inmf_bpp", args.dtype, Gd, Rt, k, Xo, k, None, 0, mask, warm, seg, 1, args.cols, k, stats,
-                          None if ((warm and k <= 31) or args.no_ginv) else ginv, _stream())
+                          *_lib.ws_args(None if args.no_ginv else ginv), _stream())
                 e1.record()
                 torch.cuda.synchronize()
                 if rep > 0:
