@@ -70,7 +70,8 @@ int64_t inmf_launch_count(void);
  *            columns per warp, 16 lanes each, partitions of <= 15 unknowns; a column with a larger partition is
  *            put on its segment's list and solved by the full-warp kernel afterwards, from its original start
  *            set.  A workspace of just nseg*k*k doubles is accepted (inverse only, full-warp solver).
- *            warm bit 3 switches the half-warp solver off.
+ *            warm bit 3 switches the half-warp solver off; warm bit 4 skips forming G^-1 although the workspace
+ *            would hold it (small warm-started solves where the k^3 inverse costs more than it saves).
  */
 int64_t inmf_bpp_workspace_bytes(int64_t max_seg_cols, int32_t nseg, int32_t k);
 int32_t inmf_bpp_f32(const double* G, const float* R, int64_t ldr, float* X, int64_t ldx, float* Y,
@@ -131,6 +132,15 @@ int32_t inmf_blocked_split_f32(const int64_t* work, int32_t nwork, const int64_t
 int32_t inmf_blocked_wide_f32(const int64_t* work, int32_t nwork, const int64_t* ptr, const void* pairs,
                               const float* dense, int32_t kp, float* out, int64_t ldo, int32_t k,
                               int32_t max_tile_rows, double* gram_out, void* stream);
+
+/* HALS update of H, one Gauss-Seidel sweep over the k factors of every cell, in place (iNMF_HALS's _update_H_HALS,
+ * _utilities.py:132-148; the W / V sweeps of _iNMF_HALS.py:118-121 are inmf_hals_* with A = H'H, B = X'H):
+ *   h_j <- max(1e-16, h_j + (R[c, j] - G[s][j, :] h) / G[s][j, j])     for j = 0 .. k-1,
+ * with R = X (W + V_s)' from the pass-1 kernels and G[s] from inmf_prep_*.  Columns as in inmf_bpp_*. */
+int32_t inmf_hals_h_f32(const double* G, const float* R, int64_t ldr, float* H, int64_t ldh, const int64_t* seg_off,
+                        int32_t nseg, int64_t max_seg_cols, int32_t k, void* stream);
+int32_t inmf_hals_h_f64(const double* G, const double* R, int64_t ldr, double* H, int64_t ldh, const int64_t* seg_off,
+                        int32_t nseg, int64_t max_seg_cols, int32_t k, void* stream);
 
 /* Sliced (SELL-8) form of the tiled product above, fp32, k <= 64: the default of the two X-streaming passes of an ALS
  * iteration (R = X (W+V_s)' of _iNMF_ANLS.py:135-139; X' H, H' H of :142-152).  The sparse rows of every work item

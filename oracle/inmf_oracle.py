@@ -14,6 +14,7 @@ What is restated (reference file:line, relative to /root/reference/src/pyliger/f
 * ``online_cal_W_V`` / ``online_cal_H`` / ``online`` / ``projection`` / ``online_refine``
                                       -- _online_iNMF.py:125-508
 * ``init_W`` / ``init_V_online``      -- _utilities.py:16-26, 69-88
+* ``hals_H`` / ``inmf_hals``          -- _utilities.py:132-148, _iNMF_HALS.py:60-163 (batch HALS factorisation)
 
 The restatement works on *products* (G = AᵀA, R = AᵀB built from scipy CSR) instead of the
 reference's dense stacked matrices, so it also runs at shapes where the reference's ``.toarray()``
@@ -482,3 +483,66 @@ def online_refine(X_old, prev, X_new, k=20, value_lambda=5.0, max_epochs=5, mini
     H_old = [online_cal_H([X], W, [V], value_lambda, miniBatch_size)[0].T
              for X, V in zip(X_old, prev["V"])]
     return dict(new=news, H_old=H_old, W=W)
+
+
+# ----------------------------------------------------------------------------------------------
+# iNMF_HALS (batch HALS factorisation)
+# ----------------------------------------------------------------------------------------------
+def hals_H(H, V, W, Xs, lam):
+    """_utilities.py:132-148 in product form; in place on every H_i (k x n_i).  W, V_i are g x k, Xs[i] cells x genes:
+    H[j,:] = nonneg(H[j,:] + ((W+V)[:,j]' X' - G1[j,:] H - lam G2[j,:] H) / (G1[j,j] + lam G2[j,j]))."""
+    for Hi, Vi, X in zip(H, V, Xs):
+        M = W + Vi
+        G1 = M.T @ M
+        G2 = Vi.T @ Vi
+        R = np.asarray(X.dot(M)).T  # k x n
+        for j in range(W.shape[1]):
+            row = Hi[j, :] + (R[j, :] - G1[j, :] @ Hi - lam * (G2[j, :] @ Hi)) / (G1[j, j] + lam * G2[j, j])
+            row[row < EPS_NONNEG] = EPS_NONNEG
+            Hi[j, :] = row
+    return H
+
+
+def inmf_hals(Xs, k=20, value_lambda=5.0, thresh=1e-4, max_iters=25, nrep=1, rand_seed=1):
+    """_iNMF_HALS.py:60-161 (without the failing attribute assignment at :156).  Xs: cells x genes CSR."""
+    N = len(Xs)
+    ns = [X.shape[0] for X in Xs]
+    g = Xs[0].shape[1]
+    np.random.seed(seed=rand_seed)
+    final = None
+    all_objs = []
+    for _ in range(nrep):
+        V = [np.asarray(Xs[i][np.random.choice(list(range(ns[i])), k), :].todense()).T for i in range(N)]
+        V = [v / np.sqrt(np.sum(np.square(v), axis=0)) for v in V]
+        W = init_W(g, k, rand_seed)
+        H = [np.random.uniform(0, 2, (k, ns[i])) for i in range(N)]
+        xn = [float(X.multiply(X).sum()) for X in Xs]
+
+        def objective():
+            tot = 0.0
+            for i in range(N):
+                M = W + V[i]
+                S = np.asarray(Xs[i].T.dot(H[i].T))  # g x k
+                HHt = H[i] @ H[i].T
+                tot += xn[i] - 2.0 * np.sum(S * M) + np.sum(HHt * (M.T @ M)) + value_lambda * np.sum(HHt * (V[i].T @ V[i]))
+            return tot
+
+        obj = objective()
+        objs = [obj]
+        it = 1
+        delta = np.inf
+        while delta > thresh and it <= max_iters:
+            H = hals_H(H, V, W, Xs, value_lambda)
+            XHt = [np.asarray(Xs[i].T.dot(H[i].T)) for i in range(N)]
+            HHt = [H[i] @ H[i].T for i in range(N)]
+            W = hals_W(HHt, XHt, W, V)
+            V = hals_V(HHt, XHt, W, V, value_lambda)
+            prev = obj
+            obj = objective()
+            objs.append(obj)
+            delta = np.absolute(prev - obj) / ((prev + obj) / 2)
+            if obj <= prev:
+                final = ([h.copy() for h in H], W.copy(), [v.copy() for v in V])
+            it += 1
+        all_objs.append(objs)
+    return {"H": [h.T for h in final[0]], "W": final[1], "V": final[2], "objectives": all_objs}

@@ -29,6 +29,7 @@ _TYPED = {
     "inmf_blocked_spmm": [_PTR, _I32, _PTR, _PTR, _PTR, _I32, _PTR, _I64, _I32, _I32, _PTR, _PTR],
     "inmf_normalize_rows": [_PTR, _PTR, _PTR, _I64, _PTR, _PTR, _PTR, _PTR, _PTR],
     "inmf_select_scale": [_PTR, _PTR, _PTR, _I64, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR],
+    "inmf_hals_h": [_PTR, _PTR, _I64, _PTR, _I64, _PTR, _I32, _I64, _I32, _PTR],
     "inmf_blockfmt1": [_I32, _PTR, _PTR, _PTR, _PTR, _I32, _I64, _I32, _I32, _I32, _PTR, _PTR, _PTR],
     "inmf_blockfmt2": [_I32, _PTR, _PTR, _PTR, _PTR, _I32, _I32, _I32, _I32, _PTR, _PTR, _PTR, _PTR, _PTR],
 }

@@ -178,7 +178,6 @@ bpp16_kernel(const double* __restrict__ G, const double* __restrict__ Ginv, cons
     constexpr int TILES = BPP16_THREADS / 16;
     const int tile = threadIdx.x >> 4, t = threadIdx.x & 15;
     const int half = (threadIdx.x >> 4) & 1;
-    const unsigned tmask = 0xffffu << (16 * half);
     if ((int64_t)blockIdx.x * TILES >= ncols) return;
 
     const int ldg = k | 1;
@@ -198,47 +197,50 @@ bpp16_kernel(const double* __restrict__ G, const double* __restrict__ Ginv, cons
     Bpp16Scratch<T> sc = bpp16_carve<T>(smem + goff + (size_t)tile * bpp16_tile_scratch_elems<T>(NF), NF);
     if (t < 8) reinterpret_cast<uint32_t*>(sc.idx)[t] = 0u;  // padded index reads stay in range
     if (t < 4) sc.z[16 + t] = T(0);
-    __syncwarp(tmask);
+    __syncwarp();
 
     long long n_notconv = 0, n_fact = 0, n_backup = 0, n_fail = 0, n_rounds = 0, max_rounds = 0, n_cols = 0, n_defer = 0;
-    for (int64_t c = (int64_t)blockIdx.x * TILES + tile; c < ncols; c += (int64_t)gridDim.x * TILES) {
-        const int64_t col = c_begin + c;
+    // warp-uniform trip count: the two tiles of a warp work in lockstep, a tile past the end is predicated off
+    for (int64_t cb = (int64_t)blockIdx.x * TILES; cb < ncols; cb += (int64_t)gridDim.x * TILES) {
+        const int64_t c = cb + tile;
+        const bool valid = c < ncols;
+        const int64_t col = c_begin + (valid ? c : 0);
         const T* rp = R + col * ldr;
         T r[NF], x[NF], y[NF];
 #pragma unroll
-        for (int f = 0; f < NF; ++f) r[f] = (t + 16 * f < k) ? rp[t + 16 * f] : T(0);
-        uint64_t P = ((warm & 1) && mask) ? mask[col] : 0ull;
+        for (int f = 0; f < NF; ++f) r[f] = (valid && t + 16 * f < k) ? rp[t + 16 * f] : T(0);
+        uint64_t P = (valid && (warm & 1) && mask) ? mask[col] : 0ull;
         BppCounters cnt = {0, 0, 0, 0, true, {0, 0, 0, 0, 0, 0}};
-        const bool done = bpp16_column<T, NF>(Gs, Gis, ldg, sc, k, r, P, (warm & 1) != 0, (warm & 2) != 0, x, y, cnt,
-                                              tmask, t, half);
-        if (!done) {  // too large for a tile: the full-warp kernel redoes this column from its original start set
+        const int status = bpp16_column<T, NF>(Gs, Gis, ldg, sc, k, valid, r, P, (warm & 1) != 0, (warm & 2) != 0, x, y,
+                                               cnt, t, half);
+        if (status == 2) {  // too large for a tile: the full-warp kernel redoes this column from its original start set
             if (t == 0) {
                 const int slot = atomicAdd(&defer_count[seg], 1);
                 defer_list[(size_t)seg * list_cap + slot] = (int32_t)c;
                 n_defer++;
             }
-            continue;
-        }
-        T* xo = X + col * ldx;
-#pragma unroll
-        for (int f = 0; f < NF; ++f)
-            if (t + 16 * f < k) xo[t + 16 * f] = x[f];
-        if (Y) {
-            T* yo = Y + col * ldy;
-            const bool clr = (warm & 4) != 0;
+        } else if (status == 1) {
+            T* xo = X + col * ldx;
 #pragma unroll
             for (int f = 0; f < NF; ++f)
-                if (t + 16 * f < k) yo[t + 16 * f] = clr ? T(0) : y[f];
-        }
-        if (mask && t == 0) mask[col] = P;
-        if (t == 0) {
-            n_cols++;
-            n_notconv += cnt.ok ? 0 : 1;
-            n_fact += cnt.nfact;
-            n_backup += cnt.nbackup;
-            n_fail += cnt.nfail;
-            n_rounds += cnt.rounds;
-            max_rounds = max_rounds > cnt.rounds ? max_rounds : cnt.rounds;
+                if (t + 16 * f < k) xo[t + 16 * f] = x[f];
+            if (Y) {
+                T* yo = Y + col * ldy;
+                const bool clr = (warm & 4) != 0;
+#pragma unroll
+                for (int f = 0; f < NF; ++f)
+                    if (t + 16 * f < k) yo[t + 16 * f] = clr ? T(0) : y[f];
+            }
+            if (mask && t == 0) mask[col] = P;
+            if (t == 0) {
+                n_cols++;
+                n_notconv += cnt.ok ? 0 : 1;
+                n_fact += cnt.nfact;
+                n_backup += cnt.nbackup;
+                n_fail += cnt.nfail;
+                n_rounds += cnt.rounds;
+                max_rounds = max_rounds > cnt.rounds ? max_rounds : cnt.rounds;
+            }
         }
     }
     if (stats && t == 0 && (n_cols || n_defer)) {
@@ -294,6 +296,7 @@ static int32_t bpp_launch(const double* G, const T* R, int64_t ldr, T* X, int64_
     // workspace: the inverse needs the first part, the half-warp solver's deferral lists the rest
     double* ginv_ws = (ws != nullptr && ws_bytes >= (int64_t)bpp_ws_ginv_bytes(nseg, k)) ? (double*)ws : nullptr;
     INMF_REQUIRE(ws == nullptr || ginv_ws != nullptr, "workspace smaller than nseg * k * k doubles");
+    if (warm & 16) ginv_ws = nullptr;  // the caller does not want the inverse formed (small warm-started solves)
     const bool have_lists = ws != nullptr && ws_bytes >= inmf_bpp_workspace_bytes(max_seg_cols, nseg, k) &&
                             max_seg_cols < ((int64_t)1 << 31);
     const int ldg = k | 1;
@@ -319,9 +322,14 @@ static int32_t bpp_launch(const double* G, const T* R, int64_t ldr, T* X, int64_
     }
     const bool comp_kernel = k > BPP_FAST_MAX_P || ((warm & 2) && ginv_ws != nullptr);
     // Half-warp solver first (two columns per warp) when its partitions can be expected to fit 15 unknowns: always
-    // for k <= 32 (one side of every partition has <= 16), for larger k only with the inverse (complement solves).
+    // for k <= 32 (one side of every partition has <= 16), for larger k only warm-started and with the inverse
+    // (complement solves): measured at 10 M columns, a cold start at k = 40 / 60 defers 94 / 100 % of the columns
+    // (99.6 vs 167 M columns/s with the full-warp kernel alone), a warm start 0.2 / 1 % (1 281 vs 625, 828 vs 268).
     // warm bit 3 switches it off.  What it defers is solved by the full-warp kernel in list mode.
-    const bool use16 = have_lists && !(warm & 8) && (k <= 32 || ginv_ws != nullptr);
+    // Small batches (the gene-side V / W solves: 3 000 - 40 000 columns) are latency-bound either way and lose more to
+    // the extra launches than they gain (C2: V 0.075 -> 0.102 ms, W 0.057 -> 0.067 ms): full-warp kernel only.
+    const bool use16 = have_lists && !(warm & 8) && (k <= 32 || (ginv_ws != nullptr && (warm & 1))) &&
+                       (int64_t)nseg * max_seg_cols >= 65536;
     int* defer_count = nullptr;
     int32_t* defer_list = nullptr;
     if (use16) {
@@ -1251,6 +1259,69 @@ extern "C" int32_t inmf_normal_eq_f32(const float* A, const float* B, int64_t m,
 extern "C" int32_t inmf_normal_eq_f64(const double* A, const double* B, int64_t m, int32_t n, int64_t cols,
                                       double* G, double* Rt, void* stream) {
     return normal_eq_launch<double>(A, B, m, n, cols, G, Rt, stream);
+}
+
+// =================================================================================================
+// HALS update of H (iNMF_HALS): one Gauss-Seidel sweep over the k factors of every cell
+// =================================================================================================
+// Reference: _update_H_HALS (_utilities.py:132-148): for j = 0..k-1, in place,
+//   H[j,:] = nonneg(H[j,:] + ((W+V)[:,j]' X - (W+V)[:,j]'(W+V) H - lambda V'V[j,:] H) / ((W+V)'(W+V)[j,j] + lambda V'V[j,j]))
+// i.e. per cell c, with r = X[c,:](W+V) (pass 1) and G = (W+V)'(W+V) + lambda V'V (prep):
+//   h_j <- max(1e-16, h_j + (r_j - G[j,:] h) / G[j,j]),   h updated in place.
+// One THREAD per cell (cells are independent, the sweep over j is sequential): G is read as shared-memory broadcasts,
+// the cell's h lives in a [k][threads] shared array (conflict free), 2 k^2 / 32 warp instructions per cell.
+template <typename T>
+__global__ void __launch_bounds__(128) hals_h_kernel(const double* __restrict__ G, const T* __restrict__ R, int64_t ldr,
+                                                     T* __restrict__ H, int64_t ldh,
+                                                     const int64_t* __restrict__ seg_off, int k) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* Gs = reinterpret_cast<T*>(smem_raw);
+    T* hs = Gs + (((size_t)k * k + 3) & ~(size_t)3);
+    const int seg = blockIdx.y;
+    const int64_t c_begin = seg_off[seg], ncols = seg_off[seg + 1] - c_begin;
+    if ((int64_t)blockIdx.x * blockDim.x >= ncols) return;
+    const double* Gseg = G + (size_t)seg * k * k;
+    for (int e = threadIdx.x; e < k * k; e += blockDim.x) Gs[e] = (T)Gseg[e];
+    __syncthreads();
+    const int nt = blockDim.x, tid = threadIdx.x;
+    for (int64_t c = (int64_t)blockIdx.x * nt + tid; c < ncols; c += (int64_t)gridDim.x * nt) {
+        T* h = H + (c_begin + c) * ldh;
+        const T* r = R + (c_begin + c) * ldr;
+        for (int l = 0; l < k; ++l) hs[l * nt + tid] = h[l];
+        for (int j = 0; j < k; ++j) {
+            T s = r[j];
+            const T* g = Gs + j * k;
+            for (int l = 0; l < k; ++l) s = fma(-g[l], hs[l * nt + tid], s);
+            T hj = hs[j * nt + tid] + s / g[j];
+            hj = hj < T(1e-16) ? T(1e-16) : hj;  // nonneg(): x[x < eps] = eps (_utilities.py:10-13)
+            hs[j * nt + tid] = hj;
+        }
+        for (int l = 0; l < k; ++l) h[l] = hs[l * nt + tid];
+    }
+}
+template <typename T>
+static int32_t hals_h_launch(const double* G, const T* R, int64_t ldr, T* H, int64_t ldh, const int64_t* seg_off,
+                             int32_t nseg, int64_t max_seg_cols, int32_t k, void* stream) {
+    INMF_REQUIRE(k >= 1 && k <= INMF_MAX_K, "k must be in [1, 64]");
+    INMF_REQUIRE(nseg >= 1 && nseg <= 65535 && ldr >= k && ldh >= k, "bad shape");
+    if (max_seg_cols <= 0) return 0;
+    const size_t smem = ((((size_t)k * k + 3) & ~(size_t)3) + (size_t)k * 128) * sizeof(T);
+    INMF_OPTIN_SMEM((hals_h_kernel<T>), 100 * 1024);
+    int64_t blocks = (max_seg_cols + 127) / 128;
+    const int64_t cap = (int64_t)inmf_num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    hals_h_kernel<T><<<dim3((unsigned)blocks, (unsigned)nseg), 128, smem, (cudaStream_t)stream>>>(G, R, ldr, H, ldh,
+                                                                                                 seg_off, k);
+    INMF_LAUNCH_CHECK();
+    return 0;
+}
+extern "C" int32_t inmf_hals_h_f32(const double* G, const float* R, int64_t ldr, float* H, int64_t ldh,
+                                   const int64_t* seg_off, int32_t nseg, int64_t max_seg_cols, int32_t k, void* stream) {
+    return hals_h_launch<float>(G, R, ldr, H, ldh, seg_off, nseg, max_seg_cols, k, stream);
+}
+extern "C" int32_t inmf_hals_h_f64(const double* G, const double* R, int64_t ldr, double* H, int64_t ldh,
+                                   const int64_t* seg_off, int32_t nseg, int64_t max_seg_cols, int32_t k, void* stream) {
+    return hals_h_launch<double>(G, R, ldr, H, ldh, seg_off, nseg, max_seg_cols, k, stream);
 }
 
 // =================================================================================================

@@ -46,6 +46,21 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+class _Range(object):
+    """NVTX range (visible in nsys / ncu --nvtx timelines): ``with _Range("pass1"): ...``."""
+    __slots__ = ("name",)
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *exc):
+        torch.cuda.nvtx.range_pop()
+        return False
+
+
 def all_gather_rows(local, counts, group=None):
     """Concatenate per-rank row blocks of unequal height (all_gather needs equal shapes: pad)."""
     cap = max(counts)
@@ -321,10 +336,11 @@ class InmfEngine(object):
                       self.dc1_lo, k, t.npad, _stream())
             _lib.call("inmf_tc_pass_f32", "", t.work, t.nwork, t.ptr, t.pairs, self.dc1_hi, self.dc1_lo, out, self.ldm,
                       k, t.npad, 1 if self.tc_three_pass else 0, 0, _stream())
-        elif full and out is self.H and self.pass1 is not None:
+        elif full and self.pass1 is not None:
             if out.data_ptr() != self._clean_ptr:  # not cleared by the previous H solve (bpp_H(clear=...)): do it now
                 out.zero_()
-            self._clean_ptr = None
+            else:
+                self._clean_ptr = None
             p = self.pass1
             self._blocked(p, p.work, p.nwork, self.Mt, out, self.ldm, None)
         else:
@@ -346,6 +362,11 @@ class InmfEngine(object):
     # V / W solves: 2 = complement preference as for H.  Measured slower (C2: V 0.081 -> 0.116 ms, W 0.048 ->
     # 0.081 ms): gene loadings are sparse, so their passive sets are the small side already.
     vw_flags = 0
+
+    def _vw(self, warm):
+        """flags of the gene-side solves: warm-started ones at k <= 31 never need the inverse (|P| <= 31 is solved
+        directly; the all-passive shortcut only pays on cold starts)."""
+        return (1 if warm else 0) | self.vw_flags | (16 if (warm and self.k <= 31 and not self.vw_flags) else 0)
 
     _clean_ptr = None  # data_ptr of the H-shaped buffer known to be all zero (cleared by the last bpp_H(clear=...))
 
@@ -405,19 +426,34 @@ class InmfEngine(object):
         if reduce:
             self._allreduce(St, HtH)
 
+    def hals_H(self):
+        """One HALS sweep over H in place (iNMF_HALS, _utilities.py:132-148): right-hand sides by pass 1 into a scratch
+        buffer, then the per-cell Gauss-Seidel sweep.  Requires prep() of the current W, V."""
+        if getattr(self, "R_hals", None) is None:
+            self.R_hals = torch.zeros_like(self.H)
+        self.rhs_H(out=self.R_hals)
+        if self.max_rows_full > 0:
+            _lib.call("inmf_hals_h", self.sfx, self.G, self.R_hals, self.ldm, self.H, self.ldm, self.seg_full_off, self.N,
+                      self.max_rows_full, self.k, _stream())
+
+    def hals_WV(self, n_inner=1):
+        """HALS sweeps of W then V (_utilities.py:102-129) with A = H'H, B = X'H of the current statistics."""
+        _lib.call("inmf_hals", self.sfx, self.HtH, self.St, self.Wt, self.Vt_all, self.lam, self.n_prev,
+                  self.n_prev + self.N, self.g, self.k, int(n_inner), _stream())
+
     def solve_V(self, warm=False):
         k, g, N = self.k, self.g, self.N
         _lib.call("inmf_rhs_v", self.sfx, self.St, self.Wt, self.HtH, self.Rv, self.Gv, self.lam, N, g, k,
                   _stream())
         _lib.call("inmf_bpp", self.sfx, self.Gv, self.Rv, k, self.Vt, k, None, 0, self.mask_V,
-                  (1 if warm else 0) | self.vw_flags, self.seg_genes, N, g, k, self.bpp_stats[1],
+                  self._vw(warm), self.seg_genes, N, g, k, self.bpp_stats[1],
                   *_lib.ws_args(self.ws_V), _stream())
 
     def solve_W(self, warm=False):
         k, g, N = self.k, self.g, self.N
         _lib.call("inmf_rhs_w", self.sfx, self.St, self.Vt, self.HtH, self.Rw, self.Gw, N, g, k, _stream())
         _lib.call("inmf_bpp", self.sfx, self.Gw, self.Rw, k, self.Wt, k, None, 0, self.mask_W,
-                  (1 if warm else 0) | self.vw_flags, self.seg_w, 1, g, k, self.bpp_stats[2],
+                  self._vw(warm), self.seg_w, 1, g, k, self.bpp_stats[2],
                   *_lib.ws_args(self.ws_W), _stream())
 
     def objective(self):
@@ -480,12 +516,17 @@ class InmfEngine(object):
             self.als_begin()
         self._begun = False
         # the buffer that held the previous iteration's H is dead from here on: the solve clears it for the next pass 1
-        self.bpp_H(mask=self.mask_H, warm=warm, clear=self.H_alt)
-        self.stats()
-        self.solve_V(warm=warm)
-        self.solve_W(warm=warm)
-        self.prep()
-        return self.objective()
+        with _Range("inmf.bpp_H"):
+            self.bpp_H(mask=self.mask_H, warm=warm, clear=self.H_alt)
+        with _Range("inmf.pass2_stats"):
+            self.stats()
+        with _Range("inmf.solve_V"):
+            self.solve_V(warm=warm)
+        with _Range("inmf.solve_W"):
+            self.solve_W(warm=warm)
+        with _Range("inmf.prep_objective"):
+            self.prep()
+            return self.objective()
 
     # The reference decides after every iteration whether to go on (delta > thresh), which costs one host read-back
     # of the objective per iteration.  To keep the GPU busy across that read-back, the first kernel of the NEXT
@@ -505,7 +546,8 @@ class InmfEngine(object):
             self.H_alt = torch.zeros_like(self.H)
             self._clean_ptr = self.H_alt.data_ptr()
         self.H, self.H_alt = self.H_alt, self.H
-        self.rhs_H()
+        with _Range("inmf.pass1_rhs_H"):
+            self.rhs_H()
         self._begun = True
 
     def als_cancel(self):

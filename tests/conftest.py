@@ -54,3 +54,8 @@ def golden_online():
 @pytest.fixture(scope="session")
 def golden_pre():
     return load_golden("preprocess.npz")
+
+
+@pytest.fixture(scope="session")
+def golden_hals():
+    return load_golden("hals.npz")

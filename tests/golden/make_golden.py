@@ -276,10 +276,41 @@ def gen_preprocess():
     print("preprocess done; scale_data sums", [float(a.layers["scale_data"].sum()) for a in lig.adata_list])
 
 
+class _DuckLiger(object):
+    """iNMF_HALS only touches ``adata_list`` and assigns ``W``: the reference's own Liger class makes that assignment
+    fail (read-only property, _iNMF_HALS.py:156), so the unmodified function is run on a plain object instead."""
+
+
+def gen_hals():
+    from pyliger.factorization._iNMF_HALS import iNMF_HALS as ref_hals
+    d = {}
+    cases = {"a": dict(ns=[260, 210], g=120, k=5, lam=5.0, thresh=1e-4, max_iters=12, nrep=1, seed=1),
+             "b": dict(ns=[150, 170, 90], g=90, k=7, lam=2.0, thresh=1e-6, max_iters=6, nrep=2, seed=3)}
+    for tag, c in cases.items():
+        mats = make_datasets(c["ns"], c["g"], c["k"], density=0.15, structured=True, seed0=2300 + len(c["ns"]))
+        lig = _DuckLiger()
+        lig.adata_list = [AnnData(X=m, layers={"scale_data": m}) for m in mats]
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            ref_hals(lig, k=c["k"], value_lambda=c["lam"], thresh=c["thresh"], max_iters=c["max_iters"], nrep=c["nrep"],
+                     rand_seed=c["seed"])
+        objs = [float(line.split("Obj:")[-1]) for line in buf.getvalue().splitlines() if "Obj:" in line]
+        for i, m in enumerate(mats):
+            csr_pack("%s_X%d" % (tag, i), m, d)
+            d["%s_H%d" % (tag, i)] = np.array(lig.adata_list[i].obsm["H"])
+            d["%s_V%d" % (tag, i)] = np.array(lig.adata_list[i].varm["V"])
+        d[tag + "_W"] = np.array(lig.adata_list[0].varm["W"])
+        d[tag + "_objectives"] = np.array(objs)
+        d[tag + "_params"] = np.array([len(mats), c["k"], c["lam"], c["thresh"], c["max_iters"], c["nrep"], c["seed"]],
+                                      dtype=np.float64)
+        print("hals", tag, "objectives", objs[:3], "...", objs[-1], "n =", len(objs))
+    np.savez_compressed(os.path.join(OUT, "hals.npz"), **d)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["bpp", "als", "online", "preprocess"]
+    which = sys.argv[1:] or ["bpp", "als", "online", "preprocess", "hals"]
     for name in which:
-        {"bpp": gen_bpp, "als": gen_als, "online": gen_online, "preprocess": gen_preprocess}[name]()
+        {"bpp": gen_bpp, "als": gen_als, "online": gen_online, "preprocess": gen_preprocess, "hals": gen_hals}[name]()
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")

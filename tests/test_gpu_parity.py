@@ -451,3 +451,138 @@ def test_als_with_nearly_dead_factor_falls_back_from_inverse(dtype):
     got, ref = np.array(info["objectives"][0]), np.array(want["objectives"])
     assert np.max(np.abs(got - ref) / ref) < tol
     assert info["bpp"]["H"]["not_converged"] == 0
+
+
+# ----------------------------------------------------------------------------------- BASELINE.json configs
+def _trajectory_report(tag, lig, info, want, N):
+    objs = np.array(info["objectives"][0])
+    rel = np.abs(objs - np.array(want["objectives"])) / np.array(want["objectives"])
+    herr = [relerr(lig.H[i], want["H"][i]) for i in range(N)]
+    verr = [relerr(lig.V[i].T, want["V"][i]) for i in range(N)]
+    werr = relerr(lig.W.T, want["W"])
+    agree = [float(np.mean(np.all((lig.H[i] > 0) == (want["H"][i] > 0), axis=1))) for i in range(N)]
+    print("%s: max rel objective err %.2e, H %s, W %.2e, V %s, H active-set agreement per cell %s, bpp(H) %s" % (
+        tag, rel.max(), ["%.1e" % e for e in herr], werr, ["%.1e" % e for e in verr], ["%.4f" % a for a in agree],
+        info["bpp"]["H"]))
+    return rel.max(), max(herr), werr, max(verr), min(agree)
+
+
+@pytest.fixture(scope="module")
+def c1_problem():
+    """configs[0] of BASELINE.json: 2 datasets x 7 000 cells x 2 000 genes, k = 20, lambda = 5, 30 iterations,
+    rand_seed = 1 -- the oracle (the pinned restatement of the reference) runs it once for all C1 tests (~15 s)."""
+    from pyliger_b200.synth import make_datasets
+    mats = make_datasets([7000, 7000], 2000, 20, density=0.10, seed0=1000)
+    want = orc.als(mats, 20, 5.0, 1e-6, 30, rand_seed=1, dense_objective=False)
+    return mats, want
+
+
+@pytest.mark.parametrize("dtype,warm", [("float64", True), ("float64", False), ("float32", True), ("float32", False)])
+def test_c1_full_trajectory_vs_oracle(c1_problem, dtype, warm):
+    """C1 at full size: every one of the 30 objectives within the north star's tolerance (1e-5 fp64 / 1e-3 fp32;
+    measured 1e-15 / 1e-8), final H, W, V in relative Frobenius norm, per-cell active-set agreement of H."""
+    from pyliger_b200 import optimize_ALS
+    mats, want = c1_problem
+    lig = _liger(mats)
+    info = optimize_ALS(lig, 20, 5.0, 1e-6, 30, rand_seed=1, dtype=dtype, warm_start=warm, return_info=True,
+                        progress=False)
+    assert info["iters_run"] == [want["iters_run"]]
+    obj, h, w, v, agree = _trajectory_report("C1 %s warm=%s" % (dtype, warm), lig, info, want, 2)
+    if dtype == "float64":
+        assert obj < 1e-5 and obj < 1e-10    # north-star tolerance, and what the kernels actually deliver
+        assert h < 1e-7 and w < 1e-7 and v < 1e-7 and agree > 0.999
+    else:
+        assert obj < 1e-3 and obj < 1e-5
+        assert h < 2e-2 and w < 2e-2 and v < 2e-2 and agree > 0.98
+    assert info["bpp"]["H"]["not_converged"] == 0
+
+
+@pytest.mark.parametrize("name,ns,g,k,density", [
+    ("C2 reduced", [2500, 2500, 2500, 2500], 600, 30, 0.08),          # 4 datasets, k = 30: sliced passes, half-warp BPP
+    ("C4 reduced", [1300] * 8, 800, 40, 0.08),                         # 8 datasets, k = 40: split tile, complement BPP
+])
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_named_config_shapes_reduced_vs_oracle(name, ns, g, k, density, dtype):
+    """The k = 30 / k = 40 configurations of BASELINE.json at a size the oracle finishes in seconds: 8 iterations of
+    the whole trajectory against the oracle (same seeded init), default options."""
+    from pyliger_b200 import optimize_ALS
+    from pyliger_b200.synth import make_datasets
+    mats = make_datasets(ns, g, k, density=density, seed0=3300)
+    want = orc.als(mats, k, 5.0, 1e-6, 8, rand_seed=1, dense_objective=False)
+    lig = _liger(mats)
+    info = optimize_ALS(lig, k, 5.0, 1e-6, 8, rand_seed=1, dtype=dtype, return_info=True, progress=False)
+    obj, h, w, v, agree = _trajectory_report("%s %s" % (name, dtype), lig, info, want, len(ns))
+    if dtype == "float64":
+        assert obj < 1e-9 and h < 1e-6 and w < 1e-6 and v < 1e-6 and agree > 0.999
+    else:
+        assert obj < 1e-3 and h < 5e-2 and w < 5e-2 and v < 5e-2 and agree > 0.95
+    assert info["bpp"]["H"]["not_converged"] == 0
+
+
+@pytest.mark.parametrize("k", [12, 30, 40, 64])
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_half_warp_bpp_equals_full_warp_bpp(k, dtype):
+    """inmf_bpp with the full workspace (half-warp solver + deferral list) against the same call with warm bit 3 (full-
+    warp solver only): same X, same passive sets, same counters except `deferred`; every column is accounted for."""
+    from pyliger_b200 import _lib
+    from pyliger_b200.engine import _stream
+    dt = torch.float64 if dtype == "float64" else torch.float32
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(900 + k)
+    g, cols = 300, 70011   # (batches below 64k columns go to the full-warp kernel alone)
+    M = rng.uniform(0, 2, (k, g)) * (rng.random((k, g)) < 0.7)
+    V = rng.uniform(0, 1, (k, g)) * (rng.random((k, g)) < 0.5)
+    G = torch.from_numpy(M @ M.T + 5.0 * V @ V.T).to(dev)
+    Xs = rng.gamma(0.3, 1.0, (cols, g)) * (rng.random((cols, g)) < 0.1)
+    R = torch.from_numpy(Xs @ M.T - 0.5 * rng.random((cols, k))).to(dev, dt)   # mixed signs: partitions of all sizes
+    seg = torch.tensor([0, cols // 3, cols], dtype=torch.int64, device=dev)     # two segments sharing G twice
+    G2 = torch.stack([G, G * 1.5])
+    res = {}
+    for flags in (0, 8):
+        for prefer in (0, 2):
+            X = torch.empty_like(R)
+            mask = torch.zeros(cols, dtype=torch.int64, device=dev)
+            stats = torch.zeros(8, dtype=torch.int64, device=dev)
+            ws = _lib.bpp_workspace(cols, 2, k, dev)
+            for warm in (0, 1):  # cold, then warm from the cold run's sets
+                stats.zero_()
+                _lib.call("inmf_bpp", "f64" if dtype == "float64" else "f32", G2, R, k, X, k, None, 0, mask,
+                          warm | prefer | flags, seg, 2, cols, k, stats, *_lib.ws_args(ws), _stream())
+                res[(flags, prefer, warm)] = (X.clone(), mask.clone(), stats.cpu().numpy().copy())
+    for prefer in (0, 2):
+        for warm in (0, 1):
+            a, b = res[(0, prefer, warm)], res[(8, prefer, warm)]
+            assert b[2][7] == 0 and a[2][6] == cols and b[2][6] == cols and a[2][0] == 0 and b[2][0] == 0
+            assert relerr(a[0].cpu().numpy(), b[0].cpu().numpy()) < (1e-12 if dtype == "float64" else 1e-4)
+            same = float((a[1] == b[1]).double().mean().item())
+            print("k=%d %s prefer=%d warm=%d: deferred %d of %d, identical passive sets %.5f, factorisations %d vs %d" % (
+                k, dtype, prefer, warm, a[2][7], cols, same, a[2][1], b[2][1]))
+            assert same > (0.9999 if dtype == "float64" else 0.99)
+            if k <= 30 and prefer:
+                assert a[2][7] == 0   # min(|P|, |F|) <= 15 always: nothing to defer
+
+
+# ----------------------------------------------------------------------------------- iNMF_HALS
+@pytest.mark.parametrize("tag", ["a", "b"])
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_inmf_hals_vs_reference(golden_hals, tag, dtype, capsys):
+    """iNMF_HALS (pass 1 + per-cell HALS sweep + pass 2 + W/V HALS sweeps + statistics-form objective) against the
+    executed reference: every printed objective, the written-back H, W, V; restarts (case b: nrep = 2)."""
+    from pyliger_b200 import iNMF_HALS
+    d = golden_hals
+    N, k, lam, thresh, max_iters, nrep, seed = d[tag + "_params"]
+    N, k, max_iters, nrep, seed = int(N), int(k), int(max_iters), int(nrep), int(seed)
+    mats = [csr_unpack(d, "%s_X%d" % (tag, i)) for i in range(N)]
+    lig = _liger(mats)
+    info = iNMF_HALS(lig, k=k, value_lambda=lam, thresh=thresh, max_iters=max_iters, nrep=nrep, rand_seed=seed,
+                     dtype=dtype, return_info=True)
+    out = capsys.readouterr().out
+    assert out.count("Initial Training Obj:") == nrep and "Iter: 1, Total time:" in out   # the reference's prints
+    objs = np.concatenate(info["objectives"])
+    rel = np.abs(objs - d[tag + "_objectives"]) / d[tag + "_objectives"]
+    print("iNMF_HALS %s %s: max rel objective err %.2e" % (tag, dtype, rel.max()))
+    assert objs.shape == d[tag + "_objectives"].shape and rel.max() < OBJ_TOL[dtype]
+    for i in range(N):
+        assert relerr(lig.adata_list[i].obsm["H"], d["%s_H%d" % (tag, i)]) < FAC_TOL[dtype]
+        assert relerr(lig.adata_list[i].varm["V"], d["%s_V%d" % (tag, i)]) < FAC_TOL[dtype]
+        assert relerr(lig.adata_list[i].varm["W"], d[tag + "_W"]) < FAC_TOL[dtype]

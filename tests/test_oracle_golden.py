@@ -210,3 +210,20 @@ def test_preprocess_oracle_matches_reference(golden_pre):
         ms = np.asarray(sc.power(2).sum(axis=0)).ravel() / (sc.shape[0] - 1)
         expressed = np.asarray((sc != 0).sum(axis=0)).ravel() > 0
         np.testing.assert_allclose(ms[expressed], 1.0, rtol=1e-12)
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_inmf_hals_oracle_matches_reference(golden_hals, tag):
+    """oracle.inmf_hals against the executed reference iNMF_HALS (_iNMF_HALS.py:60-161, run on a duck-typed liger
+    object because the reference's own Liger class makes its final attribute assignment fail)."""
+    d = golden_hals
+    N, k, lam, thresh, max_iters, nrep, seed = d[tag + "_params"]
+    N, k, max_iters, nrep, seed = int(N), int(k), int(max_iters), int(nrep), int(seed)
+    mats = [csr_unpack(d, "%s_X%d" % (tag, i)) for i in range(N)]
+    got = orc.inmf_hals(mats, k, lam, thresh, max_iters, nrep, seed)
+    objs = np.concatenate(got["objectives"])
+    np.testing.assert_allclose(objs, d[tag + "_objectives"], rtol=1e-9)
+    for i in range(N):
+        assert relerr(got["H"][i], d["%s_H%d" % (tag, i)]) < 1e-8
+        assert relerr(got["V"][i], d["%s_V%d" % (tag, i)]) < 1e-8
+    assert relerr(got["W"], d[tag + "_W"]) < 1e-8
