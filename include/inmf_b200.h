@@ -323,6 +323,34 @@ int32_t inmf_blockfmt2_f64(int32_t fill, const int64_t* rowptr, const int32_t* c
  * (/root/reference/src/pyliger/factorization/_iNMF_ANLS.py:103-108). */
 int32_t inmf_mt19937_uniform(uint32_t seed, int64_t n, double scale, double* out, void* stream);
 
+/* ---- quantile_norm (tools/_quantile_norm.py:9-195, clustering/_utilities.py:11-95): the consumer of H ------------ */
+
+/* Max-factor assignment (_quantile_norm.py:110-125): the m selected columns dims[] of H (n x ld, double) are scaled by
+ * sqrt(sum(x^2) / (n-1)) (center = 0) or centred and divided by std(ddof = 1) (center = 1); cluster[c] = argmax over
+ * the selected columns (numpy semantics).  stats_ws: 2*m doubles of scratch. */
+int32_t inmf_qn_max_factor(const double* H, int64_t ld, int64_t n, const int32_t* dims, int32_t m, int32_t center,
+                           double* stats_ws, int32_t* cluster, void* stream);
+
+/* Exact K nearest neighbours (Euclidean, self included) of every cell in the space of the selected factors
+ * (run_knn, clustering/_utilities.py:11-17): knn int32[n][K], nearest first, ties by the smaller index. */
+int32_t inmf_qn_knn(const double* H, int64_t ld, int64_t n, const int32_t* dims, int32_t m, int32_t K, int32_t* knn,
+                    void* stream);
+
+/* cluster_vote (clustering/_utilities.py:57-79): for i = 0 .. n-1 in order, cluster[i] = the most frequent label among
+ * the K neighbours of cell i (ties: the largest label), in place, so later cells see the labels earlier cells of the
+ * same sweep received.  Labels must be < 64. */
+int32_t inmf_qn_vote(const int32_t* knn, int32_t K, int64_t n, int32_t* cluster, void* stream);
+
+/* Quantile alignment of one dataset's factor loadings against the reference dataset (_quantile_norm.py:133-183), one
+ * (cluster, factor) group per work item: group int64[ngroups][6] = { cluster j, column i, samp2_off, samp2_n, samp1_off,
+ * samp1_n }.  memb / off: the cells of a dataset sorted by cluster (off[j] .. off[j+1]).  samp*_n = 0: all members
+ * enter the quantiles; otherwise samp[off .. off+n) are positions in the cluster's member list (the first max_sample
+ * entries of the reference's np.random.permutation, drawn by the host).  Hk[members, i] is overwritten with the
+ * warped values (Hk may be Href: the reference dataset itself is aligned against itself). */
+int32_t inmf_qn_align(const int64_t* group, int32_t ngroups, double* Hk, int64_t ldk, const double* Href, int64_t ldr,
+                      const int32_t* memb2, const int32_t* off2, const int32_t* memb1, const int32_t* off1,
+                      const int32_t* samp, int32_t quantiles, int32_t max_sample, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -85,12 +85,30 @@ def install():
             except ImportError:
                 sys.modules[mod] = _MissingModule(mod)
 
+    # third-party modules that pyliger/clustering/_utilities.py imports at module level but quantile_norm's exact-kNN
+    # path never calls (annoy / pynndescent), plus numba, whose @njit on cluster_vote is an optimisation only
+    if "numba" not in sys.modules:
+        try:
+            importlib.import_module("numba")
+        except ImportError:
+            nb = types.ModuleType("numba")
+            nb.njit = lambda f=None, *a, **k: f if callable(f) else (lambda g: g)
+            sys.modules["numba"] = nb
+    for mod, attr in (("annoy", "AnnoyIndex"), ("pynndescent", "NNDescent")):
+        if mod not in sys.modules:
+            try:
+                importlib.import_module(mod)
+            except ImportError:
+                m = types.ModuleType(mod)
+                setattr(m, attr, type(attr, (), {}))
+                sys.modules[mod] = m
+
     root = os.path.join(REFERENCE_SRC, "pyliger")
     pkg = types.ModuleType("pyliger")
     pkg.__path__ = [root]
     pkg._b200_shim = True
     sys.modules["pyliger"] = pkg
-    for sub in ("factorization", "preprocessing"):
+    for sub in ("factorization", "preprocessing", "tools", "clustering"):
         m = types.ModuleType("pyliger." + sub)
         m.__path__ = [os.path.join(root, sub)]
         sys.modules["pyliger." + sub] = m

@@ -9,7 +9,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libinmf_b200.so")
 SOURCES = ["inmf_kernels.cu"]
-HEADERS = ["inmf_common.cuh", "bpp.cuh", "blocked.cuh", "sell.cuh", "bpp_fast.cuh", "tc_common.cuh", "tc_pass.cuh", "preprocess.cuh", "blockfmt.cuh", os.path.join(ROOT, "include", "inmf_b200.h")]
+HEADERS = ["inmf_common.cuh", "bpp.cuh", "blocked.cuh", "sell.cuh", "bpp16.cuh", "quantile.cuh", "bpp_fast.cuh", "tc_common.cuh", "tc_pass.cuh", "preprocess.cuh", "blockfmt.cuh", os.path.join(ROOT, "include", "inmf_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -17,18 +17,19 @@ class _Raw(object):
 
     def __init__(self, adata):
         self.X = adata.X
+        self._shape = adata.shape
         self.var = adata.var.copy() if adata.var is not None else None
 
     @property
     def shape(self):
-        return self.X.shape
+        return self._shape
 
 
 class AnnDataLike(object):
     """Duck-typed AnnData: X, layers, obs / var (pandas), obsm / varm, uns, slicing by boolean masks and
     ``copy()`` -- the surface that normalize / scale_not_center / optimize_ALS / online_iNMF use."""
 
-    def __init__(self, scale_data=None, sample_name=None, X=None, obs_names=None, var_names=None):
+    def __init__(self, scale_data=None, sample_name=None, X=None, obs_names=None, var_names=None, shape=None):
         self.X = scale_data if X is None else X
         self.layers = {} if scale_data is None else {"scale_data": scale_data}
         self.obsm = {}
@@ -36,7 +37,8 @@ class AnnDataLike(object):
         self.uns = {"sample_name": sample_name}
         self.isbacked = False
         self._raw = None
-        n, g = self.X.shape
+        self._shape = None if shape is None else (int(shape[0]), int(shape[1]))
+        n, g = self.shape
         import pandas as pd
         self.obs = pd.DataFrame(index=pd.Index(obs_names if obs_names is not None
                                                else ["cell%d" % i for i in range(n)]).astype(str))
@@ -48,9 +50,27 @@ class AnnDataLike(object):
         """Dataset holding raw counts only (what create_liger starts from)."""
         return cls(None, sample_name, X=X, obs_names=obs_names, var_names=var_names)
 
+    @classmethod
+    def backed(cls, store_path, sample_name, dataset=None, obs_names=None, var_names=None):
+        """Dataset whose matrices live in an on-disk ``pyliger_b200.io.CSRStore`` (pyliger's backed mode: nothing but
+        the annotations is in memory).  ``dataset``: which matrix of the store gives the shape (default: raw_data,
+        else the first one present)."""
+        from .io import CSRStore
+        with CSRStore(store_path, "r") as f:
+            names = f.keys()
+            name = dataset or ("raw_data" if "raw_data" in names else names[0])
+            shape = f[name].shape
+        out = cls(None, sample_name, X=None, obs_names=obs_names, var_names=var_names, shape=shape)
+        out.isbacked = True
+        out.uns["backed_path"] = store_path
+        return out
+
+    def uns_keys(self):
+        return list(self.uns.keys())
+
     @property
     def shape(self):
-        return self.X.shape
+        return self._shape if self.X is None else self.X.shape
 
     @property
     def raw(self):
@@ -63,12 +83,13 @@ class AnnDataLike(object):
     def copy(self):
         import copy as _copy
         out = AnnDataLike.__new__(AnnDataLike)
-        out.X = self.X.copy()
+        out.X = None if self.X is None else self.X.copy()
+        out._shape = self._shape
+        out.isbacked = self.isbacked
         out.layers = {name: m.copy() for name, m in self.layers.items()}
         out.obsm = {name: m.copy() for name, m in self.obsm.items()}
         out.varm = {name: m.copy() for name, m in self.varm.items()}
         out.uns = _copy.copy(self.uns)
-        out.isbacked = False
         out._raw = self._raw
         out.obs = self.obs.copy()
         out.var = self.var.copy()
@@ -94,12 +115,13 @@ class AnnDataLike(object):
             return m if all_cols else m[:, c]
 
         out = AnnDataLike.__new__(AnnDataLike)
-        out.X = cut(self.X)
+        out.X = None if self.X is None else cut(self.X)
+        out._shape = None if self._shape is None else (len(r), len(c))
         out.layers = {name: cut(m) for name, m in self.layers.items()}
         out.obsm = {name: m[r] for name, m in self.obsm.items()}
         out.varm = {name: m[c] for name, m in self.varm.items()}
         out.uns = dict(self.uns)
-        out.isbacked = False
+        out.isbacked = self.isbacked
         out._raw = self._raw
         out.obs = self.obs.iloc[r]
         out.var = self.var.iloc[c]

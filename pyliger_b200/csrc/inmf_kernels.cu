@@ -6,6 +6,7 @@
 #include "sell.cuh"
 #include "tc_common.cuh"
 #include "tc_pass.cuh"
+#include "quantile.cuh"
 
 thread_local char g_inmf_err[512] = "";
 
@@ -1738,4 +1739,63 @@ extern "C" int32_t inmf_blockfmt2_f64(int32_t fill, const int64_t* rowptr, const
                                       int64_t* cnt, const int64_t* ptr, uint16_t* offs, void* pairs, void* stream) {
     return blockfmt2_launch<double>(fill, rowptr, colidx, vals, blk2, nblocks, g, row_bytes, W, cnt, ptr, offs, pairs,
                                     stream);
+}
+
+// =================================================================================================
+// quantile_norm (quantile.cuh)
+// =================================================================================================
+extern "C" int32_t inmf_qn_max_factor(const double* H, int64_t ld, int64_t n, const int32_t* dims, int32_t m,
+                                      int32_t center, double* stats_ws, int32_t* cluster, void* stream) {
+    INMF_REQUIRE(m >= 1 && m <= 64 && ld >= 1 && n >= 2, "bad shape (1 <= factors <= 64, at least 2 cells)");
+    cudaStream_t st = (cudaStream_t)stream;
+    INMF_CUDA_CHECK(cudaMemsetAsync(stats_ws, 0, 2 * (size_t)m * sizeof(double), st));
+    int64_t blocks = (n + 63) / 64;
+    if (blocks > (int64_t)inmf_num_sms() * 8) blocks = (int64_t)inmf_num_sms() * 8;
+    qn_colstats_kernel<<<(unsigned)blocks, 256, 0, st>>>(H, ld, n, dims, m, stats_ws);
+    INMF_LAUNCH_CHECK();
+    blocks = (n + 255) / 256;
+    if (blocks > (int64_t)inmf_num_sms() * 8) blocks = (int64_t)inmf_num_sms() * 8;
+    qn_max_factor_kernel<<<(unsigned)blocks, 256, 0, st>>>(H, ld, n, dims, m, stats_ws, center, cluster);
+    INMF_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int32_t inmf_qn_knn(const double* H, int64_t ld, int64_t n, const int32_t* dims, int32_t m, int32_t K,
+                               int32_t* knn, void* stream) {
+    INMF_REQUIRE(m >= 1 && m <= 64 && K >= 1 && K <= QN_KNN_MAXK && n >= 1 && n < ((int64_t)1 << 31), "bad shape");
+    const size_t smem = ((size_t)m * QN_KNN_THREADS + (size_t)QN_KNN_TILE * m) * sizeof(double);
+    INMF_OPTIN_SMEM((qn_knn_kernel), 200 * 1024);
+    int64_t blocks = (n + QN_KNN_THREADS - 1) / QN_KNN_THREADS;
+    if (blocks > (int64_t)inmf_num_sms() * 4) blocks = (int64_t)inmf_num_sms() * 4;
+    qn_knn_kernel<<<(unsigned)blocks, QN_KNN_THREADS, smem, (cudaStream_t)stream>>>(H, ld, n, dims, m, K, knn);
+    INMF_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int32_t inmf_qn_vote(const int32_t* knn, int32_t K, int64_t n, int32_t* cluster, void* stream) {
+    INMF_REQUIRE(K >= 1 && K <= 64 && n >= 0, "bad shape");
+    if (n == 0) return 0;
+    const int use_smem = n <= QN_VOTE_SMEM_CELLS;
+    INMF_OPTIN_SMEM((qn_vote_kernel), 227 * 1024 - 1024);
+    qn_vote_kernel<<<1, 32, use_smem ? (size_t)((n + 15) & ~(int64_t)15) : 0, (cudaStream_t)stream>>>(knn, K, n, cluster,
+                                                                                                 use_smem);
+    INMF_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int32_t inmf_qn_align(const int64_t* group, int32_t ngroups, double* Hk, int64_t ldk, const double* Href,
+                                 int64_t ldr, const int32_t* memb2, const int32_t* off2, const int32_t* memb1,
+                                 const int32_t* off1, const int32_t* samp, int32_t quantiles, int32_t max_sample,
+                                 void* stream) {
+    INMF_REQUIRE(quantiles >= 1 && quantiles <= QN_MAX_QUANTILES, "1 <= quantiles <= 512");
+    INMF_REQUIRE(max_sample >= 1 && max_sample <= 8192, "1 <= max_sample <= 8192");
+    if (ngroups <= 0) return 0;
+    int spow2 = 2;
+    while (spow2 < max_sample) spow2 <<= 1;
+    const size_t smem = (2 * (size_t)spow2 + 2 * (size_t)(quantiles + 1)) * sizeof(double);
+    INMF_OPTIN_SMEM((qn_align_kernel), 200 * 1024);
+    qn_align_kernel<<<(unsigned)ngroups, QN_ALIGN_THREADS, smem, (cudaStream_t)stream>>>(
+        group, Hk, ldk, Href, ldr, memb2, off2, memb1, off1, samp, quantiles, spow2);
+    INMF_LAUNCH_CHECK();
+    return 0;
 }

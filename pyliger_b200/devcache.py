@@ -68,3 +68,34 @@ def forget(host_matrix):
 
 def clear():
     _cache.clear()
+    _dense.clear()
+
+
+# ---- dense arrays (obsm["H"]): device twins for the stages that consume the factors (quantile_norm) -------------
+_dense = {}
+
+
+def register_dense(host_array, device, tensor):
+    """Remember the device tensor a host float64 array was downloaded from.  The host array is frozen (read-only), like
+    the CSR twins above."""
+    if not isinstance(host_array, np.ndarray):
+        return
+    key = id(host_array)
+    try:
+        ref = weakref.ref(host_array, lambda _r, key=key: _dense.pop(key, None))
+    except TypeError:  # pragma: no cover
+        return
+    host_array.flags.writeable = False
+    _dense[key] = (ref, str(device), tensor)
+
+
+def lookup_dense(host_array, device):
+    ent = _dense.get(id(host_array))
+    if ent is None:
+        return None
+    ref, dev, tensor = ent
+    if ref() is not host_array or dev != str(device) or host_array.flags.writeable or \
+            tuple(tensor.shape) != tuple(host_array.shape):
+        _dense.pop(id(host_array), None)
+        return None
+    return tensor

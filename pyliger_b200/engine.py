@@ -586,6 +586,17 @@ class InmfEngine(object):
             out.append(all_gather_rows(local, [hi - lo for lo, hi in sizes], self.group).cpu().numpy())
         return out
 
+    def device_H_views(self, clone=False):
+        """Per dataset, the device rows of H that host_factors() downloads (None when the rows of a dataset are spread
+        over several ranks): registered as twins of the host arrays so that consumers of H skip the upload."""
+        if self.world > 1 and not self.X.presharded:
+            return None
+        out = []
+        for i in range(self.N):
+            v = self.H[int(self.X.own_off[i]):int(self.X.own_off[i + 1]), :self.k]
+            out.append(v.clone() if clone else v)
+        return out
+
     def host_W(self):
         return self.Wt.to(torch.float64).cpu().numpy()
 

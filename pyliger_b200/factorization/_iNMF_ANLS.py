@@ -25,6 +25,7 @@ import numpy as np
 import torch
 from tqdm import tqdm
 
+from .. import devcache
 from ..engine import InmfEngine, launch_als_draw, require_cuda, resolve_dtype
 
 
@@ -90,6 +91,7 @@ def optimize_ALS(
                         use_tc=tensor_core is not None, tc_three_pass=tensor_core != "tf32")
     best_obj = np.inf
     best = None
+    best_dev = None
     info = {"objectives": [], "bpp": None, "iters_run": [], "h2d_bytes": engine.X.h2d_bytes}
     for j in range(nrep):
         if not user_init:  # the seeded draw, generated on the device (same bits as numpy's stream)
@@ -125,6 +127,7 @@ def optimize_ALS(
         info["d2h_bytes"] = info.get("d2h_bytes", 0) + 8 * len(objs)
         if obj0 < best_obj:
             best = engine.host_factors()
+            best_dev = engine.device_H_views(clone=nrep > 1)
             esz = 4 if engine.dtype == torch.float32 else 8  # the factors cross the bus in the compute dtype
             info["d2h_bytes"] += esz * (sum(h.size for h in best[0]) + best[1].size + sum(v.size for v in best[2]))
             best_obj = obj0
@@ -135,6 +138,8 @@ def optimize_ALS(
 
     final_H, final_Wt, final_Vt = best
     for i in range(N):
+        if best_dev is not None:  # the stages that consume H (quantile_norm) find it on the device
+            devcache.register_dense(final_H[i], engine.device, best_dev[i])
         liger_object.adata_list[i].obsm["H"] = final_H[i]
         # the reference stores transposed views of its k x g matrices (:184-185); same values here
         liger_object.adata_list[i].varm["W"] = final_Wt

@@ -5,15 +5,22 @@ Scenario 1 (X_new is None)            -- factorise liger_object's datasets from 
 Scenario 2 (X_new, projection=False)  -- refine W with new datasets, previous A/B/V enter the W update
 Scenario 3 (X_new, projection=True)   -- project new datasets onto the existing W (V = 0)
 
-In-memory AnnData only: the reference's backed mode reads h5sparse files from ./results
-(_online_iNMF.py:555-560); that storage format is outside this path.
-Keyword-only extensions: ``dtype`` ("float64" default / "float32"), ``device``.
+Backed AnnData (``adata.isbacked``): the reference reads its mini-batches from ``./results/<sample>.hdf5`` through
+h5sparse (_online_iNMF.py:410-412, 480-490, 555-560).  Here the store is ``pyliger_b200.io.CSRStore`` (same slicing
+API; a real h5sparse file also works when h5sparse is installed) and the cells are STREAMED: X never becomes resident,
+the rows of the next mini-batch are gathered and copied to the device while the current one is processed
+(``pyliger_b200/streaming.py``); ``stream=True`` does the same for in-memory matrices that should not be uploaded
+whole.  X_new without a ``scale_data`` layer is preprocessed like the reference does (_online_iNMF.py:604-620) into a
+store (``preprocessing/_backed.py``).
+Keyword-only extensions: ``dtype`` ("float64" default / "float32"), ``device``, ``stream``.
 """
 import numpy as np
 from tqdm import tqdm
 
-from ..engine import InmfEngine, resolve_dtype
 import torch
+
+from ..engine import InmfEngine, resolve_dtype
+from ..streaming import StreamingEngine
 
 
 def _h5_idx_generator(chunk_size, matrix_size):
@@ -40,10 +47,37 @@ def _init_V_online(num_cell, k, X, chunk_size, rand_seed):
 
 
 def _scale_data(adata):
+    """The reference's ``_get_scale_data`` (_online_iNMF.py:555-560): the on-disk store of a backed AnnData, the layer
+    of an in-memory one."""
     if getattr(adata, "isbacked", False):
-        raise NotImplementedError(
-            "pyliger_b200.online_iNMF handles in-memory AnnData; backed (h5sparse) input is out of scope")
+        from ..io import open_backed
+        return open_backed(adata, "r")["scale_data"]
     return adata.layers["scale_data"]
+
+
+def _is_streamed(X):
+    return not hasattr(X, "indptr")  # anything that is not an in-memory scipy matrix
+
+
+def _gather_own_rows(engine, outs):
+    """Per-rank row blocks of every dataset (host arrays) -> full per-dataset arrays on every rank."""
+    if engine.world == 1:
+        return outs
+    from ..engine import all_gather_rows, shard_bounds
+    full = []
+    for i, o in enumerate(outs):
+        sizes = [shard_bounds(engine.n_cells[i], r, engine.world) for r in range(engine.world)]
+        t = torch.from_numpy(o).to(engine.device)
+        full.append(all_gather_rows(t, [hi - lo for lo, hi in sizes], engine.group).cpu().numpy())
+    return full
+
+
+def _final_H(engine, with_V=True):
+    """H of every cell of every dataset as host float64 arrays, from the engine's final W, V."""
+    if isinstance(engine, StreamingEngine):
+        return _gather_own_rows(engine, engine.stream_final_H(with_V=with_V))
+    engine.final_H(with_V=with_V)
+    return engine.gather_H()
 
 
 def _to_dev(engine, arr):
@@ -52,7 +86,7 @@ def _to_dev(engine, arr):
 
 
 def _cal_W_V(Xs, num_genes, num_cells, prev_info, W_init, V_init, A_init, B_init, k, value_lambda, max_epochs,
-             miniBatch_max_iters, miniBatch_size, h5_chunk_size, rand_seed, dtype, device, progress):
+             miniBatch_max_iters, miniBatch_size, h5_chunk_size, rand_seed, dtype, device, progress, stream=False):
     """The mini-batch loop of _online_iNMF_cal_W_V (_online_iNMF.py:334-462). Returns the engine,
     holding W, V, A, B on the device."""
     num_files = len(Xs)
@@ -61,8 +95,12 @@ def _cal_W_V(Xs, num_genes, num_cells, prev_info, W_init, V_init, A_init, B_init
     Vs = ([_init_V_online(num_cells[i], k, Xs[i], h5_chunk_size, rand_seed) for i in range(num_files)]
           if V_init is None else V_init)
     n_prev = 0 if prev_info is None else len(prev_info["A_prev"])
-    engine = InmfEngine(Xs, k, value_lambda, dtype=dtype, device=device, replicate=True, n_prev=n_prev,
-                        need_stats=False)  # mini-batch statistics go through the window kernels, not pass 2
+    stream = stream or any(_is_streamed(X) for X in Xs)
+    if stream:  # out-of-core: the cells stay in the store / on the host, mini-batches are streamed
+        engine = StreamingEngine(Xs, k, value_lambda, dtype=dtype, device=device, n_prev=n_prev)
+    else:
+        engine = InmfEngine(Xs, k, value_lambda, dtype=dtype, device=device, replicate=True, n_prev=n_prev,
+                            need_stats=False)  # mini-batch statistics go through the window kernels, not pass 2
 
     miniBatch_sizes = np.asarray(
         [np.round((num_cells[i] / np.sum(num_cells)) * miniBatch_size).astype(int) for i in range(num_files)])
@@ -80,20 +118,26 @@ def _cal_W_V(Xs, num_genes, num_cells, prev_info, W_init, V_init, A_init, B_init
         engine.B_all[p].copy_(_to_dev(engine, prev_info["B_prev"][p]))
         engine.Vt_all[p].copy_(_to_dev(engine, prev_info["V_prev"][p]))
 
-    plan = engine.online_plan(int(total_iters))
-    epoch = 0
-    it_range = tqdm(range(total_iters)) if progress else range(total_iters)
-    for it in it_range:
-        epoch_prev = epoch
+    def step_args(it):
+        """scale_param of _update_A_B (_online_iNMF.py:576-581), including its `1/miniBatch_size` at iter 1, and
+        whether this step starts a new epoch."""
+        epoch_prev = (it * miniBatch_sizes[0]) // num_cells[0]
         epoch = ((it + 1) * miniBatch_sizes[0]) // num_cells[0]
-        # scale_param of _update_A_B (_online_iNMF.py:576-581), including its `1/miniBatch_size` at iter 1
         if it == 0:
             scales = [0.0] * num_files
         elif it == 1:
             scales = [1.0 / m for m in miniBatch_sizes]
         else:
             scales = [(it - 1) / it] * num_files
-        rollover = bool(epoch > 0 and epoch - epoch_prev == 1)
+        return scales, bool(epoch > 0 and epoch - epoch_prev == 1)
+
+    if stream:
+        engine.stream_minibatches(int(total_iters), step_args, miniBatch_max_iters)
+        return engine
+    plan = engine.online_plan(int(total_iters))
+    it_range = tqdm(range(total_iters)) if progress else range(total_iters)
+    for it in it_range:
+        scales, rollover = step_args(it)
         engine.online_step(plan[it], scales, rollover, miniBatch_max_iters, step=it)
     return engine
 

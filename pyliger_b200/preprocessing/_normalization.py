@@ -19,8 +19,13 @@ def normalize(liger_object, remove_missing=True, chunk_size=1000, *, dtype="floa
     sfx = _SUFFIX[dt]
     with torch.cuda.device(device):
         for idx, adata in enumerate(liger_object.adata_list):
-            if adata.isbacked:
-                raise NotImplementedError("pyliger_b200.normalize: backed (HDF5) datasets are out of scope")
+            if adata.isbacked:  # on-disk mode: chunk by chunk against the store (_normalization.py:44-46, 61-88)
+                from ._backed import normalize_online
+                norm_sum, norm_sum_sq = normalize_online(adata, chunk_size, dtype, device)
+                adata.var["norm_sum"] = norm_sum
+                adata.var["norm_sum_sq"] = norm_sum_sq
+                adata.var["norm_mean"] = norm_sum / adata.shape[0]
+                continue
             n, g = adata.shape
             rowptr, colidx, vals, _ = to_device_csr(adata.X, dt, device)
             norm_vals = torch.empty_like(vals)

@@ -22,8 +22,10 @@ def scale_not_center(liger_object, remove_missing=True, chunk_size=1000, *, dtyp
     with torch.cuda.device(device):
         for idx, adata in enumerate(liger_object.adata_list):
             var_gene_idx = np.asarray(adata.var.index.isin(liger_object.var_genes))
-            if adata.isbacked:
-                raise NotImplementedError("pyliger_b200.scale_not_center: backed (HDF5) datasets are out of scope")
+            if adata.isbacked:  # on-disk mode (_scale.py:49-51, 62-89)
+                from ._backed import scale_online
+                liger_object.adata_list[idx] = scale_online(adata, var_gene_idx, chunk_size, dtype, device)
+                continue
             n, g = adata.shape
             norm = adata.layers["norm_data"]
             rowptr, colidx, vals, _ = to_device_csr(norm, dt, device)

@@ -59,3 +59,18 @@ def golden_pre():
 @pytest.fixture(scope="session")
 def golden_hals():
     return load_golden("hals.npz")
+
+
+@pytest.fixture(scope="session")
+def golden_quantile():
+    return load_golden("quantile.npz")
+
+
+QUANTILE_CASES = {
+    "a": dict(quantiles=50, min_cells=20, max_sample=1000, knn_k=20, refine_knn=True, do_center=False, dims_use=None,
+              rand_seed=1),
+    "b": dict(quantiles=20, min_cells=5, max_sample=60, knn_k=15, refine_knn=True, do_center=False, dims_use=None,
+              rand_seed=7),
+    "c": dict(quantiles=30, min_cells=10, max_sample=100, knn_k=20, refine_knn=False, do_center=True,
+              dims_use=[0, 2, 3, 5], rand_seed=3),
+}

@@ -307,10 +307,44 @@ def gen_hals():
     np.savez_compressed(os.path.join(OUT, "hals.npz"), **d)
 
 
+def gen_quantile():
+    """quantile_norm of the unmodified reference on H matrices of a short optimize_ALS run (oracle), three cases:
+    default options on small clusters (no subsampling), max_sample below the cluster sizes (the permutation stream
+    matters), and do_center / dims_use / no kNN refinement."""
+    from pyliger.tools._quantile_norm import quantile_norm as ref_qn
+    from oracle import inmf_oracle as orc
+    d = {}
+    mats = make_datasets([700, 900, 500], 150, 6, density=0.15, structured=True, seed0=2500)
+    res = orc.als(mats, 6, 5.0, 1e-6, 8, rand_seed=1)
+    Hs = [np.ascontiguousarray(h) for h in res["H"]]
+    for i, h in enumerate(Hs):
+        d["H%d" % i] = h
+    cases = {"a": dict(quantiles=50, min_cells=20, max_sample=1000, knn_k=20, refine_knn=True, do_center=False,
+                       dims_use=None, rand_seed=1),
+             "b": dict(quantiles=20, min_cells=5, max_sample=60, knn_k=15, refine_knn=True, do_center=False,
+                       dims_use=None, rand_seed=7),
+             "c": dict(quantiles=30, min_cells=10, max_sample=100, knn_k=20, refine_knn=False, do_center=True,
+                       dims_use=[0, 2, 3, 5], rand_seed=3)}
+    for tag, kw in cases.items():
+        lig = _DuckLiger()
+        lig.adata_list = []
+        for i, h in enumerate(Hs):
+            a = AnnData(X=mats[i], obs={}, uns={"sample_name": "s%d" % i})
+            a.obsm["H"] = h.copy()
+            lig.adata_list.append(a)
+        ref_qn(lig, **kw)
+        for i, a in enumerate(lig.adata_list):
+            d["%s_cluster%d" % (tag, i)] = np.asarray(a.obs["cluster"])
+            d["%s_Hnorm%d" % (tag, i)] = np.asarray(a.obsm["H_norm"])
+        print("quantile", tag, [np.bincount(np.asarray(a.obs["cluster"]), minlength=6).tolist() for a in lig.adata_list])
+    np.savez_compressed(os.path.join(OUT, "quantile.npz"), **d)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["bpp", "als", "online", "preprocess", "hals"]
+    which = sys.argv[1:] or ["bpp", "als", "online", "preprocess", "hals", "quantile"]
     for name in which:
-        {"bpp": gen_bpp, "als": gen_als, "online": gen_online, "preprocess": gen_preprocess, "hals": gen_hals}[name]()
+        {"bpp": gen_bpp, "als": gen_als, "online": gen_online, "preprocess": gen_preprocess, "hals": gen_hals,
+         "quantile": gen_quantile}[name]()
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")

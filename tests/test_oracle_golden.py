@@ -227,3 +227,18 @@ def test_inmf_hals_oracle_matches_reference(golden_hals, tag):
         assert relerr(got["H"][i], d["%s_H%d" % (tag, i)]) < 1e-8
         assert relerr(got["V"][i], d["%s_V%d" % (tag, i)]) < 1e-8
     assert relerr(got["W"], d[tag + "_W"]) < 1e-8
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_quantile_norm_oracle_matches_reference(golden_quantile, tag):
+    """oracle.quantile_norm (brute-force kNN, sequential vote, numpy-global permutation stream) against the executed
+    reference: clusters exact, H_norm to 1e-12."""
+    from conftest import QUANTILE_CASES
+    from oracle import quantile_oracle as qo
+    d = golden_quantile
+    Hs = [d["H%d" % i] for i in range(3)]
+    kw = dict(QUANTILE_CASES[tag])
+    clusters, Hn = qo.quantile_norm(Hs, **kw)
+    for i in range(3):
+        assert np.array_equal(clusters[i], d["%s_cluster%d" % (tag, i)])
+        np.testing.assert_allclose(Hn[i], d["%s_Hnorm%d" % (tag, i)], rtol=1e-12, atol=1e-14)
