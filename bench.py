@@ -225,7 +225,7 @@ def timed_als(ctx, eng, steps, warmup, warm, objs=None):
 def kernel_breakdown(eng, warm, reps):
     """Per-kernel CUDA-event times of one iteration, launched exactly as als_iteration() does."""
     import torch
-    phases = ["pass1", "bpp_H", "pass2", "solve_V", "solve_W", "prep", "objective"]
+    phases = ["pass1", "bpp_H", "pass2", "allreduce", "solve_V", "solve_W", "prep", "objective"]
     acc = {p: 0.0 for p in phases}
     for _ in range(reps):
         evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(phases) + 1)]
@@ -236,16 +236,18 @@ def kernel_breakdown(eng, warm, reps):
         evs[1].record()
         eng.bpp_H(mask=eng.mask_H, warm=warm, clear=eng.H_alt)
         evs[2].record()
-        eng.stats()
+        eng.stats(reduce=False)
         evs[3].record()
-        eng.solve_V(warm=warm)
+        eng.reduce_stats()  # (includes the wait for the slowest rank)
         evs[4].record()
-        eng.solve_W(warm=warm)
+        eng.solve_V(warm=warm)
         evs[5].record()
-        eng.prep()
+        eng.solve_W(warm=warm)
         evs[6].record()
-        eng.objective()
+        eng.prep()
         evs[7].record()
+        eng.objective()
+        evs[8].record()
         torch.cuda.synchronize()
         for i, p in enumerate(phases):
             acc[p] += evs[i].elapsed_time(evs[i + 1]) / reps

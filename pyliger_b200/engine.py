@@ -225,6 +225,7 @@ class InmfEngine(object):
             raise ValueError("pyliger_b200 supports 1 <= k <= 64 factors, got %d" % self.k)
         self.lam = float(value_lambda)
         self.n_prev = int(n_prev)
+        self._chunks = {}
         with torch.cuda.device(self.device):
             self.X = DeviceCSR(mats, self.dtype, self.device, self.rank, self.world,
                                replicate=replicate, presharded=presharded)
@@ -311,9 +312,23 @@ class InmfEngine(object):
                 self.dc2_lo = torch.empty_like(self.dc2_hi)
 
     def _allreduce(self, *tensors):
+        """SUM over the ranks of several tensors (different dtypes) as ONE coalesced NCCL launch."""
         if self.world > 1:
-            for t in tensors:
-                torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM, group=self.group)
+            if len(tensors) == 1:
+                torch.distributed.all_reduce(tensors[0], op=torch.distributed.ReduceOp.SUM, group=self.group)
+                return
+            try:
+                from torch.distributed.distributed_c10d import _coalescing_manager
+                with _coalescing_manager(group=self.group, device=self.device, async_ops=False):
+                    for t in tensors:
+                        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM, group=self.group)
+            except (ImportError, TypeError, RuntimeError, NotImplementedError):  # backend without coalescing (gloo)
+                for t in tensors:
+                    torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM, group=self.group)
+
+    def reduce_stats(self):
+        """All-reduce of the statistics of the last stats(reduce=False)."""
+        self._allreduce(self.St, self.HtH)
 
     # ------------------------------------------------------------------ kernels
     def prep(self, with_V=True):
@@ -441,20 +456,71 @@ class InmfEngine(object):
         _lib.call("inmf_hals", self.sfx, self.HtH, self.St, self.Wt, self.Vt_all, self.lam, self.n_prev,
                   self.n_prev + self.N, self.g, self.k, int(n_inner), _stream())
 
+    # Multi-GPU: the gene-side solves are SHARDED over the ranks (every rank solves a contiguous 1/world chunk of the
+    # N*g columns of V, and of the g columns of W, and the chunks are all-gathered) instead of being repeated on every
+    # rank: at C4 on 8 GPUs the replicated solves were 0.43 ms of a 4.6 ms iteration.  Same kernels per column, so the
+    # iterates do not depend on the number of ranks.
+    shard_solves = True
+
+    def _solve_chunk(self, total, per_seg):
+        """This rank's chunk [c0, c1) of ``total`` columns organised in segments of ``per_seg`` (None if the solves are
+        not sharded): (c0, c1, first segment, device seg_off of the touched partial segments)."""
+        if self.world == 1 or not self.shard_solves:
+            return None
+        key = (total, per_seg)
+        if key not in self._chunks:
+            per = -(-total // self.world)
+            c0, c1 = min(total, self.rank * per), min(total, (self.rank + 1) * per)
+            s0 = c0 // per_seg
+            s1 = max(s0, -(-c1 // per_seg))
+            offs = [c0] + [min(c1, (s + 1) * per_seg) for s in range(s0, s1)]
+            self._chunks[key] = (c0, c1, s0, torch.tensor(offs, dtype=torch.int64, device=self.device), per)
+        return self._chunks[key]
+
+    def _gather_chunks(self, flat, chunk, total):
+        """All ranks' solved chunks of ``flat`` ([total, k]) -> the full array on every rank."""
+        c0, c1, _, _, per = chunk
+        k = self.k
+        if per * self.world == total:  # in-place all-gather (input = output + rank * count)
+            torch.distributed.all_gather_into_tensor(flat.view(-1), flat[c0:c1].reshape(-1), group=self.group)
+            return
+        pad = torch.zeros(per * k, dtype=flat.dtype, device=flat.device)
+        pad[:(c1 - c0) * k] = flat[c0:c1].reshape(-1)
+        out = torch.empty(self.world * per * k, dtype=flat.dtype, device=flat.device)
+        torch.distributed.all_gather_into_tensor(out, pad, group=self.group)
+        flat.view(-1).copy_(out[:total * k])
+
     def solve_V(self, warm=False):
         k, g, N = self.k, self.g, self.N
         _lib.call("inmf_rhs_v", self.sfx, self.St, self.Wt, self.HtH, self.Rv, self.Gv, self.lam, N, g, k,
                   _stream())
-        _lib.call("inmf_bpp", self.sfx, self.Gv, self.Rv, k, self.Vt, k, None, 0, self.mask_V,
-                  self._vw(warm), self.seg_genes, N, g, k, self.bpp_stats[1],
-                  *_lib.ws_args(self.ws_V), _stream())
+        chunk = self._solve_chunk(N * g, g)
+        if chunk is None:
+            _lib.call("inmf_bpp", self.sfx, self.Gv, self.Rv, k, self.Vt, k, None, 0, self.mask_V,
+                      self._vw(warm), self.seg_genes, N, g, k, self.bpp_stats[1],
+                      *_lib.ws_args(self.ws_V), _stream())
+            return
+        c0, c1, s0, offs, _ = chunk
+        if c1 > c0:
+            _lib.call("inmf_bpp", self.sfx, self.Gv[s0:], self.Rv, k, self.Vt, k, None, 0, self.mask_V,
+                      self._vw(warm), offs, offs.numel() - 1, g, k, self.bpp_stats[1],
+                      *_lib.ws_args(self.ws_V), _stream())
+        self._gather_chunks(self.Vt.view(N * g, k), chunk, N * g)
 
     def solve_W(self, warm=False):
         k, g, N = self.k, self.g, self.N
         _lib.call("inmf_rhs_w", self.sfx, self.St, self.Vt, self.HtH, self.Rw, self.Gw, N, g, k, _stream())
-        _lib.call("inmf_bpp", self.sfx, self.Gw, self.Rw, k, self.Wt, k, None, 0, self.mask_W,
-                  self._vw(warm), self.seg_w, 1, g, k, self.bpp_stats[2],
-                  *_lib.ws_args(self.ws_W), _stream())
+        chunk = self._solve_chunk(g, g)
+        if chunk is None:
+            _lib.call("inmf_bpp", self.sfx, self.Gw, self.Rw, k, self.Wt, k, None, 0, self.mask_W,
+                      self._vw(warm), self.seg_w, 1, g, k, self.bpp_stats[2],
+                      *_lib.ws_args(self.ws_W), _stream())
+            return
+        c0, c1, _, offs, _ = chunk
+        if c1 > c0:
+            _lib.call("inmf_bpp", self.sfx, self.Gw, self.Rw, k, self.Wt, k, None, 0, self.mask_W,
+                      self._vw(warm), offs, 1, g, k, self.bpp_stats[2], *_lib.ws_args(self.ws_W), _stream())
+        self._gather_chunks(self.Wt, chunk, g)
 
     def objective(self):
         """Objective from the current St/HtH and the Mt/Gwv/Gvv of the last prep(). Device scalar."""

@@ -183,12 +183,19 @@ def online_iNMF(
     *,
     dtype="float64",
     device=None,
+    stream=False,
 ):
     dt = resolve_dtype(dtype)
     num_genes = len(liger_object.var_genes)
     params = dict(k=k, value_lambda=value_lambda, max_epochs=max_epochs, miniBatch_max_iters=miniBatch_max_iters,
                   miniBatch_size=miniBatch_size, h5_chunk_size=h5_chunk_size, rand_seed=rand_seed, dtype=dt,
-                  device=device, progress=verbose)
+                  device=device, progress=verbose, stream=stream)
+
+    def h_engine(X, lam):
+        """Engine for an H-only pass over one dataset (projection / refresh): streamed if X is (or should be)."""
+        if stream or _is_streamed(X):
+            return StreamingEngine([X], k, lam, dtype=dt, device=device)
+        return InmfEngine([X], k, lam, dtype=dt, device=device, need_stats=False)
 
     if X_new is None:  # ---------------- scenario 1 (_online_iNMF.py:125-178)
         if verbose:
@@ -198,8 +205,7 @@ def online_iNMF(
         engine = _cal_W_V(Xs, num_genes, num_cells, None, W_init, V_init, A_init, B_init, **params)
         if verbose:
             print("Calculate metagene loadings...")
-        engine.final_H()
-        Hs = engine.gather_H()
+        Hs = _final_H(engine)
         W, Vs = _write_back_W_V(engine, W_init, V_init)
         A, B = _host_A_B(engine)
         for i, adata in enumerate(liger_object.adata_list):
@@ -210,22 +216,26 @@ def online_iNMF(
             adata.uns["A"] = A[i]
         return None
 
-    for adata in X_new:
-        if "scale_data" not in adata.layers.keys():
-            raise NotImplementedError(
-                "X_new must carry a 'scale_data' layer; pyliger's online preprocessing of raw AnnData "
-                "(_online_iNMF.py:604-620) is outside this path")
+    # raw datasets are preprocessed into an on-disk store first (_online_iNMF.py:184-190, 275-281, 604-620)
+    X_new = list(X_new)
+    for i, adata in enumerate(X_new):
+        has_scale = "scale_data" in adata.layers.keys()
+        if not has_scale and getattr(adata, "isbacked", False):
+            from ..io import open_backed
+            has_scale = "scale_data" in open_backed(adata, "r").keys()
+        if not has_scale:
+            from ..preprocessing._backed import preprocessing
+            X_new[i] = preprocessing(adata, h5_chunk_size, liger_object.var_genes, dtype="float64", device=device)
 
     if projection:  # ---------------- scenario 3 (_online_iNMF.py:271-331)
         if verbose:
             print("Metagene projection")
         W = liger_object.W if W_init is None else W_init
         for adata in X_new:
-            engine = InmfEngine([_scale_data(adata)], k, 0.0, dtype=dt, device=device, need_stats=False)
+            engine = h_engine(_scale_data(adata), 0.0)
             engine.Wt.copy_(_to_dev(engine, W))
             engine.Vt.zero_()
-            engine.final_H(with_V=False)
-            adata.obsm["H"] = engine.gather_H()[0]
+            adata.obsm["H"] = _final_H(engine, with_V=False)[0]
             adata.varm["W"] = W
             adata.varm["V"] = np.zeros((num_genes, k))
             liger_object.adata_list.append(adata)
@@ -247,21 +257,20 @@ def online_iNMF(
                           **params)
         if verbose:
             print("Calculate metagene loadings...")
-        engine.final_H()
+        Hnew = _final_H(engine)[0]
         W, Vs = _write_back_W_V(engine, W, V_init)
         A, B = _host_A_B(engine)
-        adata.obsm["H"] = engine.gather_H()[0]
+        adata.obsm["H"] = Hnew
         adata.varm["W"] = W
         adata.varm["V"] = Vs[0]
         adata.varm["B"] = B[0]
         adata.uns["A"] = A[0]
     # refresh H of the existing datasets with the refined W and their own V
     for adata in liger_object.adata_list:
-        engine = InmfEngine([_scale_data(adata)], k, value_lambda, dtype=dt, device=device, need_stats=False)
+        engine = h_engine(_scale_data(adata), value_lambda)
         engine.Wt.copy_(_to_dev(engine, W))
         engine.Vt[0].copy_(_to_dev(engine, adata.varm["V"]))
-        engine.final_H()
-        adata.obsm["H"] = engine.gather_H()[0]
+        adata.obsm["H"] = _final_H(engine)[0]
         adata.varm["W"] = W
     for adata in X_new:
         liger_object.adata_list.append(adata)

@@ -169,11 +169,19 @@ class StreamingEngine(InmfEngine):
                          use_blocked=False, need_stats=False)
         self.stream_h2d_bytes = 0
 
+    def _ensure_ws(self, rows):
+        """BPP workspace (and its declared size) for streamed batches of ``rows`` cells per dataset."""
+        if rows > self.max_rows_full:
+            from . import _lib
+            self.max_rows_full = int(rows)
+            self.ws_H = _lib.bpp_workspace(self.max_rows_full, max(self.N, 1), self.k, self.device)
+
     # ------------------------------------------------------------------ mini-batch loop
     def stream_minibatches(self, total_iters, step_args, n_inner):
         """Runs ``total_iters`` mini-batch steps; ``step_args(it)`` -> (scales, rollover).  alloc_online() first."""
         N = self.N
         cnt = [hi - lo for lo, hi in self.sub]
+        self._ensure_ws(max(cnt))
         seg = np.zeros((N + 1, 4), dtype=np.int64)
         seg[:, 0] = np.concatenate([[0], np.cumsum(cnt)])
         seg[:N, 1] = seg[:N, 0]          # the slot holds the datasets' rows back to back
@@ -203,6 +211,7 @@ class StreamingEngine(InmfEngine):
         """H of every cell this rank owns, streamed in row chunks (_online_iNMF_cal_H, _online_iNMF.py:465-508).
         Returns a list of host float64 arrays (this rank's rows of every dataset)."""
         N = self.N
+        self._ensure_ws(chunk_rows)
         self.prep(with_V=with_V)
         own = [shard_bounds(n, self.rank, self.world) for n in self.n_cells]
         reqs = []

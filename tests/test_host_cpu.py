@@ -468,3 +468,81 @@ def test_window_work_vectorised_equals_loop(pieces):
             assert counts[t] == len(ref[t])
             assert work[t, :counts[t]].tolist() == ref[t]
             assert (work[t, counts[t]:, 3] == work[t, counts[t]:, 4]).all()  # padding items are empty
+
+
+def test_csr_store_roundtrip_append_and_slicing(tmp_path):
+    """pyliger_b200.io.CSRStore: the h5sparse-like surface of the backed mode (create_dataset / append / row slicing),
+    zero-copy raw_rows, fancy row selection, read-only protection."""
+    from pyliger_b200.io import CSRStore, h5_idx_generator, write_store
+    m = sps.random(537, 41, density=0.2, random_state=4, format="csr")
+    p = str(tmp_path / "s.csr")
+    with CSRStore(p, "w") as f:
+        for lo, hi in h5_idx_generator(100, m.shape[0]):
+            if "scale_data" not in f.keys():
+                f.create_dataset("scale_data", data=m[lo:hi], chunks=(100,), maxshape=(None,))
+            else:
+                f["scale_data"].append(m[lo:hi])
+    assert list(h5_idx_generator(100, 250)) == [(0, 100), (100, 200), (200, 250)]
+    f = CSRStore(p, "r")
+    ds = f["scale_data"]
+    assert ds.shape == m.shape and ds.nnz == m.nnz and f.keys() == ["scale_data"] and "scale_data" in f
+    assert (ds[:] != m).nnz == 0 and (ds[100:333] != m[100:333]).nnz == 0 and ds[530:9999].shape == (7, 41)
+    ip, ix, dv = ds.raw_rows(17, 29)
+    sub = m[17:29]
+    assert np.array_equal(ip, sub.indptr) and np.array_equal(ix, sub.indices) and np.array_equal(dv, sub.data)
+    idx = np.array([5, 5, 400, 2])
+    assert (ds[idx, :] != m[idx, :]).nnz == 0
+    with pytest.raises(IOError):
+        ds.append(m[:3])
+    with pytest.raises(KeyError):
+        f["norm_data"]
+    with pytest.raises(IOError):
+        CSRStore(str(tmp_path / "missing.csr"), "r")
+    # float32 storage and adding a second dataset to an existing store
+    write_store(p, "norm_data", m, chunk_size=64, dtype="float32", mode="a")
+    g = CSRStore(p, "r")
+    assert g.keys() == ["norm_data", "scale_data"] and g["norm_data"].dtype == np.float32
+    np.testing.assert_allclose(g["norm_data"][:].toarray(), m.toarray(), rtol=1e-6)
+
+
+def test_streaming_window_ranges_wrap_repeatedly():
+    from pyliger_b200.streaming import _window_ranges
+    assert _window_ranges(3, 4, 10) == [(3, 7)]
+    assert _window_ranges(8, 5, 10) == [(8, 10), (0, 3)]
+    assert _window_ranges(27, 25, 10) == [(7, 10), (0, 10), (0, 10), (0, 2)]   # mini-batch larger than the dataset
+    assert _window_ranges(0, 0, 10) == []
+
+
+def test_backed_anndata_like(tmp_path):
+    from pyliger_b200.containers import AnnDataLike
+    from pyliger_b200.io import write_store
+    m = sps.random(30, 12, density=0.3, random_state=1, format="csr")
+    p = write_store(str(tmp_path / "a.csr"), "raw_data", m, chunk_size=7, mode="w")
+    a = AnnDataLike.backed(p, "a")
+    assert a.isbacked and a.shape == (30, 12) and a.X is None and "backed_path" in a.uns_keys()
+    b = a[:, np.arange(12) % 2 == 0].copy()
+    assert b.isbacked and b.shape == (30, 6) and list(b.var.index) == ["g%d" % j for j in range(0, 12, 2)]
+
+
+@pytest.mark.parametrize("world,N,g", [(2, 4, 3000), (8, 4, 3000), (8, 8, 5000), (3, 2, 7), (8, 1, 5)])
+def test_sharded_gene_solve_chunks_partition_the_columns(world, N, g):
+    """engine._solve_chunk: the ranks' chunks tile the N*g columns of the V solve (and the g columns of W) exactly once,
+    and every chunk is expressed as consecutive partial segments with the right first dataset."""
+    from pyliger_b200.engine import InmfEngine
+    for total, per_seg in ((N * g, g), (g, g)):
+        covered = np.zeros(total, dtype=np.int64)
+        for rank in range(world):
+            e = InmfEngine.__new__(InmfEngine)
+            e.world, e.rank, e._chunks, e.device = world, rank, {}, torch.device("cpu")
+            c0, c1, s0, offs, per = e._solve_chunk(total, per_seg)
+            offs = offs.numpy()
+            assert per * world >= total and 0 <= c0 <= c1 <= total
+            covered[c0:c1] += 1
+            if c1 > c0:
+                assert offs[0] == c0 and offs[-1] == c1 and np.all(np.diff(offs) > 0) and s0 == c0 // per_seg
+                for j in range(len(offs) - 1):   # partial segment j lies inside dataset s0 + j
+                    assert offs[j] // per_seg == s0 + j and (offs[j + 1] - 1) // per_seg == s0 + j
+        assert np.all(covered == 1)
+    e = InmfEngine.__new__(InmfEngine)
+    e.world, e.rank, e._chunks = 1, 0, {}
+    assert e._solve_chunk(10, 5) is None

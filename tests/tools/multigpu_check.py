@@ -51,6 +51,15 @@ def main():
     ok &= bool(good)
     print("rank %d/%d online fp64: W err %.2e, H err %.2e, A err %.2e -> %s" % (
         rank, world, werr, herr, aerr, "OK" if good else "FAIL"), flush=True)
+    # out-of-core path: every rank streams only its share of each mini-batch and of the final H pass (X sharded)
+    lig = liger_from_matrices(mats)
+    online_iNMF(lig, k=k, value_lambda=lam, max_epochs=2, miniBatch_size=300, verbose=False, stream=True)
+    werr = np.linalg.norm(lig.W - wo["W"]) / np.linalg.norm(wo["W"])
+    herr = max(np.linalg.norm(lig.H[i] - wo["H"][i]) / np.linalg.norm(wo["H"][i]) for i in range(3))
+    good = werr < 1e-7 and herr < 1e-6 and lig.H[2].shape == wo["H"][2].shape
+    ok &= bool(good)
+    print("rank %d/%d streamed online fp64: W err %.2e, H err %.2e -> %s" % (
+        rank, world, werr, herr, "OK" if good else "FAIL"), flush=True)
     flag = torch.tensor([0 if ok else 1], device="cuda")
     dist.all_reduce(flag)
     dist.destroy_process_group()
