@@ -12,6 +12,7 @@ pyliger_b200.optimize_ALS (warm-started BPP; fp32 is the throughput mode, fp64 t
 
 `extra` carries the other configs of BASELINE.json, each device-timed with CUDA events, max over ranks:
   c2_cold_f32   the same C2 loop with cold-started solves (the reference's literal init = None)
+  c2_mixed      the same C2 loop with dtype="mixed" (bf16 tile in the two passes; labelled reduced precision)
   c2_warm_f64   the same C2 loop in fp64 (parity mode)
   c4_strong     configs[3]: 8 x 250k cells x 5k genes, k = 40, the 2 M cells sharded over the ranks (STRONG scaling)
   c3_online     configs[2]: online_iNMF, 1 M cells (8 x 125k) in 5 000-cell mini-batches, k = 40: mini-batch loop
@@ -528,7 +529,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline legs")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="headline only (skip the c2 cold / fp64, C3, C4, C5 legs)")
-    ap.add_argument("--extra", default="cold,f64,c4,c3,c5,parity", help="which extra legs to run")
+    ap.add_argument("--extra", default="cold,mixed,f64,c4,c3,c5,parity", help="which extra legs to run")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -632,6 +633,22 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "gpu_launches": int(launches_c)}
     del eng
     torch.cuda.empty_cache()
+    if "mixed" in extras and args.dtype == "f32" and k <= 32:
+        engm = InmfEngine(mats, k, lam, dtype="mixed", device=dev, presharded=world > 1)
+        engm.set_als_state(W0, V0, H0)
+        om = [engm.initial_objective()]
+        ms_m, launches_m, om = timed_als(ctx, engm, args.steps, args.warmup, warm, om)
+        accm = kernel_breakdown(engm, warm, 5)
+        extra["c2_mixed"] = {
+            "what": "the headline loop with dtype='mixed': the dense operand of the two passes rounded to bf16 in shared "
+                    "memory (64 instead of 128 operand bytes per non-zero), everything else fp32 -- a labelled "
+                    "reduced-precision mode, not the fp32 headline",
+            "value": cells_total * args.steps / (ms_m * 1e-3), "unit": "cell-iters/s", "ms_per_step": ms_m / args.steps,
+            "steps": args.steps, "warmup": args.warmup, "gpu_launches": int(launches_m),
+            "final_objective_rel_diff_vs_fp32": abs(om[-1] - objs[-1]) / abs(objs[-1]),
+            "roofline": roofline_block(accm, ms_m / args.steps, cells_local, nnz_local, k, 4)}
+        del engm
+        torch.cuda.empty_cache()
     if "f64" in extras and args.dtype == "f32":
         eng64 = InmfEngine(mats, k, lam, dtype=torch.float64, device=dev, presharded=world > 1)
         eng64.set_als_state(W0, V0, H0)

@@ -161,9 +161,21 @@ int32_t inmf_sell_pass_f32(const int64_t* work, int32_t nwork, const int64_t* sl
                            int32_t k, int32_t max_tile_rows, double* gram_out, void* stream);
 
 /* Builder of pairs4: copies the rows slice_rows[s*height + i] (indices into ptr of the row-ordered blocked format built
- * by inmf_blockfmt1/2_f32, -1 = no row) into the slices laid out by slice_ptr, zero padded. */
+ * by inmf_blockfmt1/2_f32, -1 = no row) into the slices laid out by slice_ptr, zero padded.  height = -32: slices of
+ * 32 rows with every row's non-zeros reordered by the parity of (off / 64) for inmf_sell_pass_mixed. */
 int32_t inmf_sell_fill_f32(const int64_t* ptr, const void* pairs, const int64_t* slice_rows, const int64_t* slice_ptr,
                            int64_t nslices, int32_t height, void* pairs4, void* stream);
+
+/* Mixed-precision form of inmf_sell_pass_f32 for k <= 32 (the engine's dtype = "mixed", never its fp32 / fp64 modes):
+ * the dense operand is bf16, 32 values (64 bytes) per row, zero padded (inmf_to_bf16_rows); pairs carry
+ * off = (row of the tile) * 64; X values and the accumulation stay fp32.  Slices of height 32 built by
+ * inmf_sell_fill_f32 with height = -32 (every row's non-zeros ordered by the parity of their tile row, so that the
+ * two rows sharing a 128-byte shared-memory line are not read in the same phase).  No Gram output. */
+int32_t inmf_sell_pass_mixed(const int64_t* work, int32_t nwork, const int64_t* slice_ptr, const int32_t* rowid,
+                             const void* pairs4, const void* dense_bf16, float* out, int64_t ldo, int32_t k,
+                             int32_t max_tile_rows, void* stream);
+/* dst[r][0..32) = bf16(src[r*ld + 0..k)) rounded to nearest even, zero beyond k. */
+int32_t inmf_to_bf16_rows(const float* src, int64_t ld, int64_t rows, int32_t k, void* dst, void* stream);
 
 /* Sufficient statistics of one pass over the cells (accumulating; caller zeroes):
  *   St[s] (g x k) += sum_q X[row(q), :]' H[q, :],   HtH[s] (k x k, double) += sum_q H[q,:]' H[q,:]

@@ -89,7 +89,7 @@ def split_applies(kp, esize):
 
 
 def row_bytes(kp, esize):
-    """Stride that the pairs' byte offsets are premultiplied with."""
+    """Stride that the pairs' byte offsets are premultiplied with (esize = 2: the bf16 tile of the mixed mode)."""
     return 128 if split_applies(kp, esize) else kp * esize
 
 
@@ -135,7 +135,8 @@ def build_sell(bp, kp, height=None):
     dev = bp.ptr.device
     W = bp.work_host[:bp.nwork]
     sp = SellPass()
-    S = sp.height = int(height or (SELL_HEIGHT_KP32 if kp == 32 else 8))
+    sp.height = int(height or (SELL_HEIGHT_KP32 if kp == 32 else 8))  # -32: parity-ordered rows (mixed precision)
+    S = abs(sp.height)
     sp.max_tile_rows = bp.max_tile_rows
     sp.nwork = bp.nwork
     sp.nnz = int(bp.pairs.shape[0])
@@ -175,7 +176,7 @@ def build_sell(bp, kp, height=None):
     rel = slice_rows.view(total_slices, S) - t(W[:, 0])[swid][:, None]
     sp.rowid = torch.where(slice_rows.view(total_slices, S) >= 0, rel, torch.full_like(rel, -1)).to(torch.int32).contiguous()
     sp.pairs4 = torch.empty(max(n4, 1), 4, dtype=torch.int32, device=dev)
-    _lib.call("inmf_sell_fill_f32", "", bp.ptr, bp.pairs, slice_rows, sp.slice_ptr, total_slices, S, sp.pairs4, _stream(dev))
+    _lib.call("inmf_sell_fill_f32", "", bp.ptr, bp.pairs, slice_rows, sp.slice_ptr, total_slices, sp.height, sp.pairs4, _stream(dev))
     work = np.zeros((bp.nwork, WORK_FIELDS), dtype=np.int64)
     work[:, 0] = slice_off[:-1]
     work[:, 1] = slice_off[1:]
@@ -213,6 +214,43 @@ def _own_nnz(X):
     return torch.cat(rows), torch.cat(cols), torch.cat(vals)
 
 
+MIN_ITEM_ROWS = 1024  # a CTA needs a few slices per warp to balance its warps
+
+
+def _wave_chunks(n_sms, pairs, rows):
+    """Row chunks per (dataset, gene block) pair so that the grid fills whole waves of CTAs: with c chunks the grid is
+    pairs * c CTAs on n_sms SMs; pick the c (up to 4 waves) with the best occupancy of its last wave.  C4 on one of
+    8 GPUs: 32 pairs -> 4 chunks = 128 CTAs (86 % of one wave) before, 9 chunks = 288 CTAs (97 % of two waves) now."""
+    best_c, best_eff = 1, 0.0
+    for waves in (1, 2, 3, 4):
+        c = (waves * n_sms) // pairs
+        if c < 1 or (c > 1 and rows // c < MIN_ITEM_ROWS):
+            continue
+        eff = pairs * c / float(-(-pairs * c // n_sms) * n_sms)
+        if eff >= 0.95:  # good enough: fewer, larger items balance better inside a CTA
+            return c
+        if eff > best_eff + 1e-9:
+            best_c, best_eff = c, eff
+    return max(1, best_c)
+
+
+def _wave_blocks(n_sms, n_own, cap):
+    """Cell blocks per dataset for pass 2: at least ceil(n / cap) each (the tile must fit), in total a whole number of
+    waves of CTAs (C4 on one of 8 GPUs: 8 x 22 = 176 blocks = 1.19 waves before, 8 x 37 = 296 = 2 waves now)."""
+    need = [0 if n == 0 else -(-n // cap) for n in n_own]
+    n_tot = max(1, sum(n_own))
+    waves = max(1, -(-sum(need) // n_sms))
+    target = waves * n_sms
+    nb = [0 if n == 0 else max(nd, int(n / n_tot * target)) for n, nd in zip(n_own, need)]
+    # hand the remaining CTAs of the last wave to the datasets with the largest blocks
+    while sum(nb) < target:
+        i = max(range(len(nb)), key=lambda j: (n_own[j] / nb[j]) if nb[j] else -1.0)
+        if nb[i] == 0 or n_own[i] // (nb[i] + 1) < 64:
+            break
+        nb[i] += 1
+    return nb
+
+
 def build_pass1(X, kp, esize, n_sms):
     """Gene-blocked CSR over the owned cells."""
     dev = X.rowptr.device
@@ -240,7 +278,7 @@ def build_pass1(X, kp, esize, n_sms):
         idx_local = (col.to(torch.int64) - gb * gbs)[order]
         bp.pairs = _pack_pairs(idx_local * row_bytes(kp, esize), val[order])  # byte offset of the gathered tile row
         bp.ptr = ptr
-    chunks = max(1, n_sms // max(1, N * NB))
+    chunks = _wave_chunks(n_sms, max(1, N * NB), max(X.n_own) if N else 0)
     work = []
     for s in range(N):
         n = X.n_own[s]
@@ -267,7 +305,7 @@ def build_pass2(X, kp, esize, n_sms):
     g, N = X.g, X.N
     cap = tile_cap_rows(kp, esize)
     n_tot = max(1, X.n_own_total)
-    nb = [0 if n == 0 else max(-(-n // cap), int(round(n / n_tot * n_sms))) for n in X.n_own]
+    nb = _wave_blocks(n_sms, X.n_own, cap)
     cbs = [1 if b == 0 else -(-n // b) for n, b in zip(X.n_own, nb)]
     nb = [0 if n == 0 else -(-n // c) for n, c in zip(X.n_own, cbs)]
     blk_off = np.concatenate([[0], np.cumsum(nb)]).astype(np.int64)

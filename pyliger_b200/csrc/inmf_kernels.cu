@@ -1461,16 +1461,49 @@ extern "C" int32_t inmf_sell_pass_f32(const int64_t* work, int32_t nwork, const 
 #undef INMF_SELL_ARGS
 }
 
+extern "C" int32_t inmf_sell_pass_mixed(const int64_t* work, int32_t nwork, const int64_t* slice_ptr,
+                                        const int32_t* rowid, const void* pairs4, const void* dense_bf16, float* out,
+                                        int64_t ldo, int32_t k, int32_t max_tile_rows, void* stream) {
+    INMF_REQUIRE(k >= 1 && k <= 32, "the mixed-precision passes are for k <= 32");
+    INMF_REQUIRE(ldo >= k, "ldo must be >= k");
+    INMF_REQUIRE((reinterpret_cast<uintptr_t>(pairs4) & 15) == 0 && (reinterpret_cast<uintptr_t>(dense_bf16) & 15) == 0,
+                 "pairs4 and the bf16 operand must be 16-byte aligned");
+    if (nwork <= 0) return 0;
+    const size_t smem = 128 + (size_t)max_tile_rows * 64;
+    INMF_REQUIRE(smem <= 227 * 1024, "dense tile does not fit in shared memory");
+    INMF_OPTIN_SMEM((sell32h_pass_kernel), 227 * 1024);
+    sell32h_pass_kernel<<<(unsigned)nwork, SELL32_THREADS, smem, (cudaStream_t)stream>>>(
+        work, slice_ptr, rowid, reinterpret_cast<const int4*>(pairs4), reinterpret_cast<const uint16_t*>(dense_bf16), out,
+        ldo, k);
+    INMF_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int32_t inmf_to_bf16_rows(const float* src, int64_t ld, int64_t rows, int32_t k, void* dst, void* stream) {
+    INMF_REQUIRE(k >= 1 && k <= 32 && ld >= k, "bad shape (k <= 32)");
+    if (rows <= 0) return 0;
+    int64_t blocks = (rows * 16 + 255) / 256;
+    const int64_t cap = (int64_t)inmf_num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    to_bf16_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, ld, rows, k,
+                                                                            reinterpret_cast<uint32_t*>(dst));
+    INMF_LAUNCH_CHECK();
+    return 0;
+}
+
 extern "C" int32_t inmf_sell_fill_f32(const int64_t* ptr, const void* pairs, const int64_t* slice_rows,
                                       const int64_t* slice_ptr, int64_t nslices, int32_t height, void* pairs4,
                                       void* stream) {
     if (nslices <= 0) return 0;
-    INMF_REQUIRE(height == 8 || height == 32, "slice height must be 8 or 32");
+    INMF_REQUIRE(height == 8 || height == 32 || height == -32, "slice height must be 8 or 32 (-32: parity ordered)");
     INMF_REQUIRE((reinterpret_cast<uintptr_t>(pairs4) & 15) == 0, "pairs4 must be 16-byte aligned");
     int64_t blocks = (nslices + 7) / 8;
     const int64_t cap = (int64_t)inmf_num_sms() * 16;
     if (blocks > cap) blocks = cap;
-    if (height == 8)
+    if (height == -32)
+        sell_fill_parity_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+            ptr, reinterpret_cast<const int2*>(pairs), slice_rows, slice_ptr, nslices, reinterpret_cast<int4*>(pairs4));
+    else if (height == 8)
         sell_fill_kernel<8><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
             ptr, reinterpret_cast<const int2*>(pairs), slice_rows, slice_ptr, nslices, reinterpret_cast<int4*>(pairs4));
     else

@@ -371,9 +371,184 @@ sell32_pass_kernel(const int64_t* __restrict__ work, const int64_t* __restrict__
     }
 }
 
+// =====================================================================================================
+// Mixed precision: the gathered tile in bf16 (64-byte rows), fp32 pairs and fp32 accumulation.
+//
+// The fp32 kernels above sit on the shared-memory operand bandwidth (128 B per non-zero at 128 B/clk/SM: ncu 1.03
+// wavefronts per non-zero, data pipe 91 % busy).  Halving the operand halves that bound; X itself (the values of the
+// pairs) and the accumulators stay fp32, so only the dense factor (W + V_s, or H) is rounded, to 8 significant bits.
+// One lane per row as in sell32_pass_kernel: a tile row is four 16-byte chunks, lane l reads them in the order
+// (l + j) mod 4 and converts each bf16 pair with one shift / one mask.  Two rows share a 128-byte bank line, so lanes
+// l and l + 4 of a phase collide when their rows have the same parity: the builder orders every row's non-zeros
+// "matching parity first" for lanes with bit 2 clear and "other parity first" for lanes with bit 2 set, which leaves
+// a conflict only where the two halves of the rows differ in length (~5 % of the steps).
+// Pairs: {int32 off = tile row * 64, float val}.  This is the dtype="mixed" mode of the engine, never the fp32 path.
+// =====================================================================================================
+__device__ __forceinline__ void lds128u(uint32_t addr, uint32_t (&m)[4]) {
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(m[0]), "=r"(m[1]), "=r"(m[2]), "=r"(m[3]) : "r"(addr));
+}
+
+__global__ void __launch_bounds__(SELL32_THREADS, 1)
+sell32h_pass_kernel(const int64_t* __restrict__ work, const int64_t* __restrict__ slice_ptr,
+                    const int32_t* __restrict__ rowid, const int4* __restrict__ pairs,
+                    const uint16_t* __restrict__ dense, float* __restrict__ out, int64_t ldo, int k) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+    int* next_slice = reinterpret_cast<int*>(smem_raw + 16);
+    unsigned char* tile = smem_raw + 128;
+    const int64_t* wd = work + (size_t)blockIdx.x * SELL_WORK_FIELDS;
+    const int slice_begin = (int)wd[0], slice_end = (int)wd[1];
+    const int64_t dense_row0 = wd[2];
+    const int tile_rows = (int)wd[3];
+    const int64_t out_row_base = wd[4];
+    const int lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        *next_slice = slice_begin;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const size_t total = (size_t)tile_rows * 64;
+        mbar_expect_tx(bar, (uint32_t)total);
+        const unsigned char* sp = reinterpret_cast<const unsigned char*>(dense + (size_t)dense_row0 * 32);
+        for (size_t off = 0; off < total; off += 32768) {
+            const size_t n = (total - off < 32768) ? (total - off) : 32768;
+            bulk_g2s(tile + off, sp + off, (uint32_t)n, bar);
+        }
+    }
+    uint32_t tb[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) tb[j] = smem_u32(tile) + (uint32_t)(((lane + j) & 3) * 16);
+    const int vec_ok = (((ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0)) ? 4
+                       : (((ldo & 1) == 0) && ((reinterpret_cast<uintptr_t>(out) & 7) == 0)) ? 2 : 1;
+    mbar_wait(bar, 0);
+    int s = 0;
+    if (lane == 0) s = atomicAdd(next_slice, 1);
+    s = __shfl_sync(INMF_FULL_MASK, s, 0);
+    int64_t base = 0, lim = 0;
+    if (s < slice_end) {
+        base = slice_ptr[s];
+        lim = slice_ptr[s + 1];
+    }
+    while (s < slice_end) {
+        const int L2 = (int)((lim - base) >> 5);
+        const int4* __restrict__ p = pairs + base + lane;
+        const int rid = rowid[(size_t)s * 32 + lane];
+        float acc[4][8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc[j][u] = 0.f;
+        const int4 z4 = make_int4(0, 0, 0, 0);
+        int4 A = (0 < L2) ? sell_ld(p) : z4;
+        int4 B = (1 < L2) ? sell_ld(p + 32) : z4;
+        for (int j = 0; j < L2; j += 2) {
+            const int4 A2 = (j + 2 < L2) ? sell_ld(p + (size_t)(j + 2) * 32) : z4;
+            const int4 B2 = (j + 3 < L2) ? sell_ld(p + (size_t)(j + 3) * 32) : z4;
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+                const int off = h == 0 ? A.x : h == 1 ? A.z : h == 2 ? B.x : B.z;
+                const float v = __int_as_float(h == 0 ? A.y : h == 1 ? A.w : h == 2 ? B.y : B.w);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t m[4];
+                    lds128u(tb[c] + (uint32_t)off, m);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {  // bf16 pair -> two fp32: low half << 16, high half masked
+                        acc[c][2 * u] = fmaf(v, __uint_as_float(m[u] << 16), acc[c][2 * u]);
+                        acc[c][2 * u + 1] = fmaf(v, __uint_as_float(m[u] & 0xffff0000u), acc[c][2 * u + 1]);
+                    }
+                }
+            }
+            A = A2;
+            B = B2;
+        }
+        int sn = 0;
+        if (lane == 0) sn = atomicAdd(next_slice, 1);
+        sn = __shfl_sync(INMF_FULL_MASK, sn, 0);
+        int64_t nbase = 0, nlim = 0;
+        if (sn < slice_end) {
+            nbase = slice_ptr[sn];
+            nlim = slice_ptr[sn + 1];
+        }
+        if (rid >= 0) {
+            float* o = out + (out_row_base + rid) * ldo;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int col0 = ((lane + c) & 3) * 8;
+                const float lo4[4] = {acc[c][0], acc[c][1], acc[c][2], acc[c][3]};
+                const float hi4[4] = {acc[c][4], acc[c][5], acc[c][6], acc[c][7]};
+                sell_out4(o, col0, k, lo4, vec_ok);
+                sell_out4(o, col0 + 4, k, hi4, vec_ok);
+            }
+        }
+        s = sn;
+        base = nbase;
+        lim = nlim;
+    }
+}
+
+// fp32 rows (ld floats apart) -> bf16 rows of 32 (round to nearest even), zero padded beyond k.
+__global__ void __launch_bounds__(256) to_bf16_rows_kernel(const float* __restrict__ src, int64_t ld, int64_t rows, int k,
+                                                           uint32_t* __restrict__ dst) {
+    const int64_t total = rows * 16;  // one thread per bf16 PAIR
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = t >> 4;
+        const int c = (int)(t & 15) * 2;
+        const float a = c < k ? src[r * ld + c] : 0.f;
+        const float b = c + 1 < k ? src[r * ld + c + 1] : 0.f;
+        const uint32_t ua = __float_as_uint(a), ub = __float_as_uint(b);
+        const uint32_t ra = (ua + 0x7fffu + ((ua >> 16) & 1u)) >> 16;   // finite inputs: RNE on the dropped 16 bits
+        const uint32_t rb = (ub + 0x7fffu + ((ub >> 16) & 1u)) >> 16;
+        dst[t] = ra | (rb << 16);
+    }
+}
+
 // Builder: copies the rows listed in slice_rows (ptr indices of the row-ordered blocked format, -1 = no row) into
 // the step-interleaved slices of HEIGHT rows.  One warp per slice; HEIGHT = 8: lane = (row i = lane / 4, step-pair
 // phase c = lane % 4); HEIGHT = 32: lane = row.
+// Parity-ordered variant for the mixed-precision kernel (64-byte tile rows, HEIGHT = 32): lane = row; the row's
+// non-zeros whose tile row has parity == bit 2 of the lane come first, the others after, each in their original order.
+__global__ void __launch_bounds__(256) sell_fill_parity_kernel(const int64_t* __restrict__ ptr,
+                                                               const int2* __restrict__ src,
+                                                               const int64_t* __restrict__ slice_rows,
+                                                               const int64_t* __restrict__ slice_ptr, int64_t nslices,
+                                                               int4* __restrict__ dst) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int want = (lane >> 2) & 1;
+    for (int64_t s = warp0; s < nslices; s += nwarp) {
+        const int64_t base = slice_ptr[s];
+        const int L2 = (int)((slice_ptr[s + 1] - base) >> 5);
+        const int64_t row = slice_rows[s * 32 + lane];
+        int64_t beg = 0;
+        int len = 0;
+        if (row >= 0) {
+            beg = ptr[row];
+            len = (int)(ptr[row + 1] - beg);
+        }
+        int outpos = 0;
+        int2 hold = make_int2(0, 0);
+        for (int pass = 0; pass < 2; ++pass) {
+            for (int t = 0; t < len; ++t) {
+                const int2 a = src[beg + t];
+                const int par = (a.x >> 6) & 1;
+                if ((par == want) != (pass == 0)) continue;
+                if (outpos & 1) dst[base + (int64_t)(outpos >> 1) * 32 + lane] = make_int4(hold.x, hold.y, a.x, a.y);
+                else hold = a;
+                ++outpos;
+            }
+        }
+        if (outpos & 1) {
+            dst[base + (int64_t)(outpos >> 1) * 32 + lane] = make_int4(hold.x, hold.y, 0, 0);
+            ++outpos;
+        }
+        for (int jj = outpos >> 1; jj < L2; ++jj) dst[base + (int64_t)jj * 32 + lane] = make_int4(0, 0, 0, 0);
+    }
+}
+
 template <int HEIGHT>
 __global__ void __launch_bounds__(256) sell_fill_kernel(const int64_t* __restrict__ ptr, const int2* __restrict__ src,
                                                         const int64_t* __restrict__ slice_rows,

@@ -17,15 +17,23 @@ from . import _lib, blocked, devcache, staging
 _SUFFIX = {torch.float32: "f32", torch.float64: "f64"}
 
 
+def is_mixed(dtype):
+    """dtype="mixed": fp32 everywhere except the dense operand of the two X-streaming passes, which is rounded to
+    bf16 (csrc/sell.cuh, sell32h_pass_kernel).  A named reduced-precision mode, k <= 32."""
+    return isinstance(dtype, str) and dtype in ("mixed", "bf16-tile")
+
+
 def resolve_dtype(dtype):
     if dtype in (torch.float32, torch.float64):
         return dtype
+    if is_mixed(dtype):
+        return torch.float32
     name = np.dtype(dtype).name if not isinstance(dtype, str) else dtype
     if name in ("float32", "f32", "fp32"):
         return torch.float32
     if name in ("float64", "f64", "fp64"):
         return torch.float64
-    raise ValueError("dtype must be float32 or float64, got %r" % (dtype,))
+    raise ValueError("dtype must be float32, float64 or 'mixed', got %r" % (dtype,))
 
 
 def require_cuda(device=None):
@@ -207,7 +215,10 @@ class InmfEngine(object):
                  replicate=False, n_prev=0, presharded=False, use_blocked=True, need_stats=True, use_tc=False,
                  tc_three_pass=True):
         # use_tc: dense-tile tcgen05 form of the two passes (fp32 only): 3xTF32 (fp32-grade) by default
-        self.use_tc = bool(use_tc) and resolve_dtype(dtype) == torch.float32
+        self.mixed = is_mixed(dtype)
+        if self.mixed and not 1 <= int(k) <= 32:
+            raise ValueError("dtype='mixed' supports k <= 32 factors, got %d" % int(k))
+        self.use_tc = bool(use_tc) and resolve_dtype(dtype) == torch.float32 and not self.mixed
         self.tc_three_pass = bool(tc_three_pass)
         self.use_blocked = bool(use_blocked)
         self.need_stats = bool(need_stats)
@@ -290,7 +301,13 @@ class InmfEngine(object):
         if self.use_blocked and X.n_own_total > 0:
             esize = 4 if dt == torch.float32 else 8
             sms = torch.cuda.get_device_properties(dev).multi_processor_count
-            if not self.use_tc:
+            if self.mixed:  # bf16 tiles: 64-byte rows, parity-ordered slices of 32 rows
+                self.pass1 = blocked.build_sell(blocked.build_pass1(X, 32, 2, sms), 32, height=-32)
+                self.Mt16 = torch.empty(N * g, 32, dtype=torch.int16, device=dev)
+                if self.need_stats:
+                    self.pass2 = blocked.build_sell(blocked.build_pass2(X, 32, 2, sms), 32, height=-32)
+                    self.H16 = torch.empty(max(X.n_own_total, 1), 32, dtype=torch.int16, device=dev)
+            elif not self.use_tc:
                 sell = blocked.sell_applies(self.ldm, esize)
                 self.pass1 = blocked.build_pass1(X, self.ldm, esize, sms)
                 if sell:
@@ -311,20 +328,28 @@ class InmfEngine(object):
                 self.dc2_hi = torch.empty(self.tc2.total_chunks * per, dtype=dt, device=dev)
                 self.dc2_lo = torch.empty_like(self.dc2_hi)
 
+    coalesce_allreduce = True
+
     def _allreduce(self, *tensors):
-        """SUM over the ranks of several tensors (different dtypes) as ONE coalesced NCCL launch."""
-        if self.world > 1:
-            if len(tensors) == 1:
-                torch.distributed.all_reduce(tensors[0], op=torch.distributed.ReduceOp.SUM, group=self.group)
-                return
-            try:
-                from torch.distributed.distributed_c10d import _coalescing_manager
-                with _coalescing_manager(group=self.group, device=self.device, async_ops=False):
-                    for t in tensors:
-                        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM, group=self.group)
-            except (ImportError, TypeError, RuntimeError, NotImplementedError):  # backend without coalescing (gloo)
-                for t in tensors:
-                    torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM, group=self.group)
+        """SUM over the ranks.  Tensors of one dtype go out as ONE coalesced NCCL launch; different dtypes (fp32 St +
+        fp64 H'H) as one launch per dtype (c10d's coalescing of mixed dtypes is not relied upon)."""
+        if self.world <= 1:
+            return
+        by_dtype = {}
+        for t in tensors:
+            by_dtype.setdefault(t.dtype, []).append(t)
+        for group_t in by_dtype.values():
+            if len(group_t) > 1 and self.coalesce_allreduce:
+                try:
+                    from torch.distributed.distributed_c10d import _coalescing_manager
+                    with _coalescing_manager(group=self.group, device=self.device, async_ops=False):
+                        for t in group_t:
+                            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM, group=self.group)
+                    continue
+                except (ImportError, TypeError, RuntimeError, NotImplementedError):  # backend without coalescing
+                    pass
+            for t in group_t:
+                torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM, group=self.group)
 
     def reduce_stats(self):
         """All-reduce of the statistics of the last stats(reduce=False)."""
@@ -364,6 +389,16 @@ class InmfEngine(object):
 
     def _blocked(self, p, work, nwork, dense, out, ldo, gram):
         """One tiled pass (out += X_blocked * dense tile): sliced, plain or split-tile kernel, as the format was built."""
+        if isinstance(p, blocked.SellPass) and p.height == -32:  # mixed precision: the operand goes through bf16
+            rows = dense.numel() // self.ldm
+            buf = self.Mt16 if p is self.pass1 else self.H16
+            _lib.call("inmf_to_bf16_rows", "", dense, self.ldm, rows, self.k, buf, _stream())
+            _lib.call("inmf_sell_pass_mixed", "", work, nwork, p.slice_ptr, p.rowid, p.pairs4, buf, out, ldo, self.k,
+                      p.max_tile_rows, _stream())
+            if gram is not None:  # H'H from the fp32 H (not from the rounded tile)
+                _lib.call("inmf_gram_rows", self.sfx, dense, self.ldm, self.seg_full, self.N, self.max_rows_full, gram,
+                          self.k, _stream())
+            return
         if isinstance(p, blocked.SellPass):
             _lib.call("inmf_sell_pass_f32", "", work, nwork, p.slice_ptr, p.rowid, p.pairs4, p.height, dense, self.ldm, out, ldo,
                       self.k, p.max_tile_rows, gram, _stream())

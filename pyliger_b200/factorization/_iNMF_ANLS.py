@@ -2,7 +2,11 @@
 (/root/reference/src/pyliger/factorization/_iNMF_ANLS.py:8-196), CUDA kernels underneath.
 
 Keyword-only extensions (defaults preserve reference behaviour):
-  dtype       "float64" (default, parity mode) or "float32" (throughput mode)
+  dtype       "float64" (default, parity mode), "float32" (throughput mode) or "mixed": float32 with the dense
+              operand of the two X-streaming passes (W + V_i, H) rounded to bf16 in shared memory -- halves the
+              operand traffic that bounds those kernels; X, the accumulation, the solves and the statistics stay
+              fp32.  k <= 32.  A labelled reduced-precision mode (objective within the 1e-3 fp32 tolerance, see
+              tests/test_gpu_parity.py::test_c1_mixed_precision_mode), never what "float32" means
   device      torch device (default: current CUDA device)
   warm_start  start each BPP solve from the previous iteration's passive sets -- the reference solver's own
               ``init`` argument (_utilities.py:222-225); NNLS with an SPD Gram matrix has a unique solution, so the
@@ -87,7 +91,7 @@ def optimize_ALS(
     pending = None
     if not user_init:  # the first seeded draw runs on one SM while X is uploaded and laid out
         pending = launch_als_draw(require_cuda(device), ns, num_genes, k, rand_seed - 1, h_stream)
-    engine = InmfEngine(X, k, value_lambda, dtype=resolve_dtype(dtype), device=device, presharded=presharded,
+    engine = InmfEngine(X, k, value_lambda, dtype=dtype, device=device, presharded=presharded,
                         use_tc=tensor_core is not None, tc_three_pass=tensor_core != "tf32")
     best_obj = np.inf
     best = None

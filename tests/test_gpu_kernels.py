@@ -418,3 +418,47 @@ def test_sell_passes_match_numpy_and_row_ordered_passes(dev, k, height, budget_r
     np.testing.assert_allclose(objs, res[False][3], rtol=1e-3)
     # (no comparison of the final H of the two fp32 runs: on this random toy problem the ALS map amplifies summation-
     # order differences; trajectories are pinned against the oracle in test_gpu_parity.py)
+
+
+def _bf16_round(a):
+    """float32 -> bf16 (round to nearest even) -> float32, in numpy."""
+    u = np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+    r = ((u + 0x7FFF + ((u >> 16) & 1)) >> 16) << 16
+    return r.astype(np.uint32).view(np.float32)
+
+
+@pytest.mark.parametrize("k", [3, 20, 30, 32])
+@pytest.mark.parametrize("budget_rows", [50, 100000])
+def test_mixed_precision_passes_equal_numpy_with_bf16_operand(dev, k, budget_rows):
+    """dtype="mixed": the two passes with the dense operand rounded to bf16 (and nothing else): R = X bf16(W+V)',
+    S = X' bf16(H) to fp32 round-off, H'H from the unrounded H; parity-ordered slices, several tiles and one."""
+    from pyliger_b200 import blocked
+    lam = 2.0
+    mats, W, V, H = _rand_problem(300 + k, ns=(333, 171, 70), g=130, k=k, density=0.25)
+    old = blocked.SMEM_BUDGET
+    blocked.SMEM_BUDGET = min(old, budget_rows * 64)
+    try:
+        eng = _engine(mats, k, lam, "mixed")
+        assert eng.mixed and eng.pass1.height == -32 and eng.pass2.height == -32 and eng.dtype == torch.float32
+        eng.set_als_state(W, V, H)
+        eng.prep()
+        eng.stats()
+        St, HtH = eng.St.clone(), eng.HtH.clone()
+        eng.rhs_H()
+        R = eng.H.clone()
+    finally:
+        blocked.SMEM_BUDGET = old
+    off = 0
+    for i in range(len(mats)):
+        n = mats[i].shape[0]
+        Mi = _bf16_round((W + V[i]).astype(np.float32)).astype(np.float64)
+        Hi32 = H[i].astype(np.float32)
+        assert relerr(R[off:off + n, :k].cpu().numpy(), np.asarray(mats[i].dot(Mi.T))) < 5e-6
+        assert relerr(St[i].cpu().numpy(), np.asarray(mats[i].T.dot(_bf16_round(Hi32).astype(np.float64)))) < 5e-6
+        assert relerr(HtH[i].cpu().numpy(), Hi32.astype(np.float64).T @ Hi32.astype(np.float64)) < 5e-6
+        # and the rounding is the only difference to the exact products: 2^-9 per operand entry
+        assert relerr(R[off:off + n, :k].cpu().numpy(), np.asarray(mats[i].dot((W + V[i]).T))) < 4e-3
+        off += n
+    assert float(R[:, k:].abs().max().item() if R.shape[1] > k else 0.0) == 0.0
+    with pytest.raises(ValueError):
+        _engine(mats, 33, lam, "mixed")

@@ -586,3 +586,17 @@ def test_inmf_hals_vs_reference(golden_hals, tag, dtype, capsys):
         assert relerr(lig.adata_list[i].obsm["H"], d["%s_H%d" % (tag, i)]) < FAC_TOL[dtype]
         assert relerr(lig.adata_list[i].varm["V"], d["%s_V%d" % (tag, i)]) < FAC_TOL[dtype]
         assert relerr(lig.adata_list[i].varm["W"], d[tag + "_W"]) < FAC_TOL[dtype]
+
+
+def test_c1_mixed_precision_mode(c1_problem):
+    """dtype="mixed" (bf16 tile in the two passes, everything else fp32) on C1 at full size, 30 iterations: every
+    objective within the north star's fp32 tolerance (1e-3); the factor errors and the per-cell active-set agreement
+    of this reduced-precision mode are reported (and bounded loosely)."""
+    from pyliger_b200 import optimize_ALS
+    mats, want = c1_problem
+    lig = _liger(mats)
+    info = optimize_ALS(lig, 20, 5.0, 1e-6, 30, rand_seed=1, dtype="mixed", return_info=True, progress=False)
+    obj, h, w, v, agree = _trajectory_report("C1 mixed", lig, info, want, 2)
+    assert obj < 1e-3
+    assert h < 0.2 and w < 0.2 and v < 0.2 and agree > 0.5
+    assert info["bpp"]["H"]["not_converged"] == 0
