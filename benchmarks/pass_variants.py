@@ -67,9 +67,9 @@ def main():
         pass
     ref = None
     for variant in args.variants.split(","):
-        blocked.SELL = variant.startswith("sell")
+        blocked.SELL = variant.startswith("sell") or variant == "mixed"
         blocked.SELL_HEIGHT_KP32 = 8 if variant == "sell8" else 32
-        eng = InmfEngine(mats, k, 5.0, dtype=torch.float32, device=dev)
+        eng = InmfEngine(mats, k, 5.0, dtype="mixed" if variant == "mixed" else torch.float32, device=dev)
         eng.set_als_state(W0, V0, H0)
         eng.initial_objective()
         for i in range(4):
@@ -94,6 +94,24 @@ def main():
                "bpp_H_ms": tb[0] - tcopy[0],
                "pass1_frac": bytes_pass / (t1[0] * 1e-3) / 1e9 / peak, "pass2_frac": bytes_pass / (t2[0] * 1e-3) / 1e9 / peak,
                "clk_per_nnz_pass1": t1[0] * 1e-3 * 1.965e9 * 148 / nnz, "clk_per_nnz_pass2": t2[0] * 1e-3 * 1.965e9 * 148 / nnz}
+        if variant == "mixed":  # the pieces of the mixed passes on their own
+            from pyliger_b200 import _lib
+            from pyliger_b200.engine import _stream
+            p1, p2 = eng.pass1, eng.pass2
+            out["to_bf16_Mt_ms"] = timed(lambda: _lib.call("inmf_to_bf16_rows", "", eng.Mt, eng.ldm, eng.N * eng.g, k,
+                                                          eng.Mt16, _stream()), args.reps)[0]
+            out["to_bf16_H_ms"] = timed(lambda: _lib.call("inmf_to_bf16_rows", "", eng.H, eng.ldm, eng.H.shape[0], k,
+                                                         eng.H16, _stream()), args.reps)[0]
+            out["kernel_pass1_ms"] = timed(lambda: _lib.call("inmf_sell_pass_mixed", "", p1.work, p1.nwork, p1.slice_ptr,
+                                                            p1.rowid, p1.pairs4, eng.Mt16, R, eng.ldm, k,
+                                                            p1.max_tile_rows, _stream()), args.reps)[0]
+            out["kernel_pass2_ms"] = timed(lambda: _lib.call("inmf_sell_pass_mixed", "", p2.work, p2.nwork, p2.slice_ptr,
+                                                            p2.rowid, p2.pairs4, eng.H16, eng.St, k, k,
+                                                            p2.max_tile_rows, _stream()), args.reps)[0]
+            out["to_bf16_gram_ms"] = timed(lambda: _lib.call("inmf_to_bf16_gram", "", eng.H, eng.ldm, eng.seg_full_off,
+                                                            eng.N, eng.max_rows_full, k, eng.H16, eng.HtH, _stream()),
+                                           args.reps)[0]
+            out["memset_St_ms"] = timed(lambda: (eng.St.zero_(), eng.HtH.zero_()), args.reps)[0]
         if isinstance(eng.pass1, blocked.SellPass):
             out["pad1"] = eng.pass1.padded / max(1, eng.pass1.nnz)
             out["pad2"] = eng.pass2.padded / max(1, eng.pass2.nnz)

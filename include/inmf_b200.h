@@ -174,6 +174,10 @@ int32_t inmf_sell_fill_f32(const int64_t* ptr, const void* pairs, const int64_t*
 int32_t inmf_sell_pass_mixed(const int64_t* work, int32_t nwork, const int64_t* slice_ptr, const int32_t* rowid,
                              const void* pairs4, const void* dense_bf16, float* out, int64_t ldo, int32_t k,
                              int32_t max_tile_rows, void* stream);
+/* The same conversion for H (rows [seg_off[s], seg_off[s+1]) = dataset s) fused with the statistics H'H of the
+ * UNROUNDED values: gram[s] (k x k, double) += sum_r H[r,:]' H[r,:] (accumulating; caller zeroes). */
+int32_t inmf_to_bf16_gram(const float* H, int64_t ld, const int64_t* seg_off, int32_t nseg, int64_t max_seg_rows,
+                          int32_t k, void* dst, double* gram, void* stream);
 /* dst[r][0..32) = bf16(src[r*ld + 0..k)) rounded to nearest even, zero beyond k. */
 int32_t inmf_to_bf16_rows(const float* src, int64_t ld, int64_t rows, int32_t k, void* dst, void* stream);
 

@@ -38,7 +38,7 @@ EXPORTED_SYMBOLS = ["inmf_version", "inmf_last_error", "inmf_launch_count", "inm
                     "inmf_tc_relayout_f32", "inmf_tc_pass_f32", "inmf_tc_debug_buffer", "inmf_select_count", "inmf_mt19937_uniform", "inmf_blocked_split_f32", "inmf_blocked_wide_f32",
                     "inmf_sell_pass_f32", "inmf_sell_fill_f32",
                     "inmf_qn_max_factor", "inmf_qn_knn", "inmf_qn_vote", "inmf_qn_align",
-                    "inmf_sell_pass_mixed", "inmf_to_bf16_rows"] + [
+                    "inmf_sell_pass_mixed", "inmf_to_bf16_rows", "inmf_to_bf16_gram"] + [
     "%s_%s" % (n, t) for n in _TYPED for t in ("f32", "f64")
 ]
 
@@ -84,6 +84,8 @@ def load():
     lib.inmf_sell_fill_f32.argtypes = [_PTR, _PTR, _PTR, _PTR, _I64, _I32, _PTR, _PTR]
     lib.inmf_sell_pass_mixed.restype = _I32
     lib.inmf_sell_pass_mixed.argtypes = [_PTR, _I32, _PTR, _PTR, _PTR, _PTR, _PTR, _I64, _I32, _I32, _PTR]
+    lib.inmf_to_bf16_gram.restype = _I32
+    lib.inmf_to_bf16_gram.argtypes = [_PTR, _I64, _PTR, _I32, _I64, _I32, _PTR, _PTR, _PTR]
     lib.inmf_to_bf16_rows.restype = _I32
     lib.inmf_to_bf16_rows.argtypes = [_PTR, _I64, _I64, _I32, _PTR, _PTR]
     lib.inmf_qn_max_factor.restype = _I32

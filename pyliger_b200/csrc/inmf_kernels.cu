@@ -1479,6 +1479,20 @@ extern "C" int32_t inmf_sell_pass_mixed(const int64_t* work, int32_t nwork, cons
     return 0;
 }
 
+extern "C" int32_t inmf_to_bf16_gram(const float* H, int64_t ld, const int64_t* seg_off, int32_t nseg,
+                                     int64_t max_seg_rows, int32_t k, void* dst, double* gram, void* stream) {
+    INMF_REQUIRE(k >= 1 && k <= 32 && ld >= k && nseg >= 1 && nseg <= 65535, "bad shape (k <= 32)");
+    if (max_seg_rows <= 0) return 0;
+    int64_t blocks = (max_seg_rows + GRAMCVT_WARPS * 16 - 1) / (GRAMCVT_WARPS * 16);  // >= 16 rows per warp
+    int64_t cap = ((int64_t)inmf_num_sms() * 8 + nseg - 1) / nseg;
+    if (cap < 1) cap = 1;
+    if (blocks > cap) blocks = cap;
+    to_bf16_gram_kernel<<<dim3((unsigned)blocks, (unsigned)nseg), GRAMCVT_WARPS * 32, 0, (cudaStream_t)stream>>>(
+        H, ld, seg_off, k, reinterpret_cast<uint32_t*>(dst), gram);
+    INMF_LAUNCH_CHECK();
+    return 0;
+}
+
 extern "C" int32_t inmf_to_bf16_rows(const float* src, int64_t ld, int64_t rows, int32_t k, void* dst, void* stream) {
     INMF_REQUIRE(k >= 1 && k <= 32 && ld >= k, "bad shape (k <= 32)");
     if (rows <= 0) return 0;

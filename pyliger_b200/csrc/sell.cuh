@@ -455,8 +455,8 @@ sell32h_pass_kernel(const int64_t* __restrict__ work, const int64_t* __restrict_
                     uint32_t m[4];
                     lds128u(tb[c] + (uint32_t)off, m);
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {  // bf16 pair -> two fp32: low half << 16, high half masked
-                        acc[c][2 * u] = fmaf(v, __uint_as_float(m[u] << 16), acc[c][2 * u]);
+                    for (int u = 0; u < 4; ++u) {  // bf16 pair -> two fp32: byte permute / mask, both on the ALU pipe
+                        acc[c][2 * u] = fmaf(v, __uint_as_float(__byte_perm(m[u], 0u, 0x1044)), acc[c][2 * u]);
                         acc[c][2 * u + 1] = fmaf(v, __uint_as_float(m[u] & 0xffff0000u), acc[c][2 * u + 1]);
                     }
                 }
@@ -486,6 +486,56 @@ sell32h_pass_kernel(const int64_t* __restrict__ work, const int64_t* __restrict_
         s = sn;
         base = nbase;
         lim = nlim;
+    }
+}
+
+// H (fp32, cells x ld) -> bf16 rows of 32 AND H'H of the unrounded values, per segment (dataset), one streaming pass.
+// A warp walks rows; lane l owns column l: it rounds its value (even lanes pack a pair), keeps the row in a per-warp
+// shared line, and accumulates row l of the Gram, G[l][j] += h_l h_j, from 8 broadcast 128-bit loads per row.  The
+// warps of a CTA are folded through shared memory before one double-precision atomicAdd per entry.
+#define GRAMCVT_WARPS 8
+__global__ void __launch_bounds__(GRAMCVT_WARPS * 32) to_bf16_gram_kernel(const float* __restrict__ H, int64_t ld,
+                                                                          const int64_t* __restrict__ seg_off, int k,
+                                                                          uint32_t* __restrict__ dst,
+                                                                          double* __restrict__ gram) {
+    __shared__ __align__(16) float rowbuf[GRAMCVT_WARPS][2][32];
+    __shared__ float fold[32][33];
+    const int seg = blockIdx.y;
+    const int64_t r0 = seg_off[seg], r1 = seg_off[seg + 1];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float acc[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+    int buf = 0;
+    for (int64_t r = r0 + (int64_t)blockIdx.x * GRAMCVT_WARPS + warp; r < r1; r += (int64_t)gridDim.x * GRAMCVT_WARPS) {
+        const float h = lane < k ? H[r * ld + lane] : 0.f;
+        const uint32_t u = __float_as_uint(h);
+        const uint32_t rb = (u + 0x7fffu + ((u >> 16) & 1u)) >> 16;   // finite inputs: round to nearest even
+        const uint32_t nb = __shfl_down_sync(INMF_FULL_MASK, rb, 1);
+        if ((lane & 1) == 0) dst[r * 16 + (lane >> 1)] = rb | (nb << 16);
+        rowbuf[warp][buf][lane] = h;
+        __syncwarp();
+        const float4* rv = reinterpret_cast<const float4*>(rowbuf[warp][buf]);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const float4 v = rv[q];
+            acc[4 * q] = fmaf(h, v.x, acc[4 * q]);
+            acc[4 * q + 1] = fmaf(h, v.y, acc[4 * q + 1]);
+            acc[4 * q + 2] = fmaf(h, v.z, acc[4 * q + 2]);
+            acc[4 * q + 3] = fmaf(h, v.w, acc[4 * q + 3]);
+        }
+        buf ^= 1;
+    }
+    for (int w = 0; w < GRAMCVT_WARPS; ++w) {
+        if (warp == w) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) fold[lane][j] = (w == 0 ? 0.f : fold[lane][j]) + acc[j];
+        }
+        __syncthreads();
+    }
+    for (int e = threadIdx.x; e < k * k; e += blockDim.x) {
+        const int i = e / k, j = e - i * k;
+        atomicAdd(&gram[(size_t)seg * k * k + e], (double)fold[i][j]);
     }
 }
 

@@ -392,12 +392,13 @@ class InmfEngine(object):
         if isinstance(p, blocked.SellPass) and p.height == -32:  # mixed precision: the operand goes through bf16
             rows = dense.numel() // self.ldm
             buf = self.Mt16 if p is self.pass1 else self.H16
-            _lib.call("inmf_to_bf16_rows", "", dense, self.ldm, rows, self.k, buf, _stream())
+            if gram is not None:  # pass 2: H -> bf16 and H'H of the fp32 H (not of the rounded tile) in one pass
+                _lib.call("inmf_to_bf16_gram", "", dense, self.ldm, self.seg_full_off, self.N, self.max_rows_full, self.k,
+                          buf, gram, _stream())
+            else:
+                _lib.call("inmf_to_bf16_rows", "", dense, self.ldm, rows, self.k, buf, _stream())
             _lib.call("inmf_sell_pass_mixed", "", work, nwork, p.slice_ptr, p.rowid, p.pairs4, buf, out, ldo, self.k,
                       p.max_tile_rows, _stream())
-            if gram is not None:  # H'H from the fp32 H (not from the rounded tile)
-                _lib.call("inmf_gram_rows", self.sfx, dense, self.ldm, self.seg_full, self.N, self.max_rows_full, gram,
-                          self.k, _stream())
             return
         if isinstance(p, blocked.SellPass):
             _lib.call("inmf_sell_pass_f32", "", work, nwork, p.slice_ptr, p.rowid, p.pairs4, p.height, dense, self.ldm, out, ldo,
