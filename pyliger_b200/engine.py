@@ -497,11 +497,12 @@ class InmfEngine(object):
     # rank: at C4 on 8 GPUs the replicated solves were 0.43 ms of a 4.6 ms iteration.  Same kernels per column, so the
     # iterates do not depend on the number of ranks.
     shard_solves = True
+    shard_min_columns = 32768  # smaller solves are latency-bound: a shard takes as long as the whole + the gather
 
     def _solve_chunk(self, total, per_seg):
         """This rank's chunk [c0, c1) of ``total`` columns organised in segments of ``per_seg`` (None if the solves are
         not sharded): (c0, c1, first segment, device seg_off of the touched partial segments)."""
-        if self.world == 1 or not self.shard_solves:
+        if self.world == 1 or not self.shard_solves or total < self.shard_min_columns:
             return None
         key = (total, per_seg)
         if key not in self._chunks:

@@ -533,7 +533,7 @@ def test_sharded_gene_solve_chunks_partition_the_columns(world, N, g):
         covered = np.zeros(total, dtype=np.int64)
         for rank in range(world):
             e = InmfEngine.__new__(InmfEngine)
-            e.world, e.rank, e._chunks, e.device = world, rank, {}, torch.device("cpu")
+            e.world, e.rank, e._chunks, e.device, e.shard_min_columns = world, rank, {}, torch.device("cpu"), 0
             c0, c1, s0, offs, per = e._solve_chunk(total, per_seg)
             offs = offs.numpy()
             assert per * world >= total and 0 <= c0 <= c1 <= total
