@@ -526,6 +526,7 @@ def main():
     ap.add_argument("--config", default="C2", choices=["C2", "C4"],
                     help="headline workload: C2 (default, weak scaling) or C4 (8 x 250k cells sharded over the ranks)")
     ap.add_argument("--cells", type=int, default=0, help="cells per dataset per GPU (default: the config's)")
+    ap.add_argument("--graph", type=int, default=1, help="1: CUDA-graphed warm iterations (the engine default), 0: eager")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline legs")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="headline only (skip the c2 cold / fp64, C3, C4, C5 legs)")
@@ -548,6 +549,7 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    InmfEngine.use_graph = bool(args.graph)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:

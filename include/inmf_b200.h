@@ -44,6 +44,8 @@ int32_t inmf_version(void);
 const char* inmf_last_error(void);
 /* Number of kernels this library has launched since it was loaded (host-side counter). */
 int64_t inmf_launch_count(void);
+/* A CUDA graph captured from calls into this library was replayed: add the n kernels it contains to the counter. */
+void inmf_note_graph_launches(int64_t n);
 
 /* Batched block-principal-pivoting NNLS; one problem per column, G shared per segment.
  * Replaces nnlsm_blockpivot + normal_eq_comb (_utilities.py:181-358) for all six call sites
@@ -152,13 +154,25 @@ int32_t inmf_hals_h_f64(const double* G, const double* R, int64_t ldr, double* H
  *   height = 8: four lanes per row (any kp);  height = 32 (kp == 32 only): one lane per row, the pair stream is not
  *   replicated across lanes and every lane walks the 16-byte chunks of its tile row in a rotated, bank-conflict-free
  *   order.
- *   work int64[nwork][8] = { slice_begin, slice_end, dense_row0, tile_rows, out_row_base, gram_seg, 0, 0 }
+ *   work int64[nwork][8] = { slice_begin, slice_end, dense_row0, tile_rows, out_row_base, gram_seg, part, 0 }
  * dense has kp floats per row (kp = 32 for k <= 32, else k rounded up to 4); the tile is held in shared memory as
  * [rows x 32] + [rows x rs], rs = 0 / 8 / 16 / 32 for kp - 32 = 0 / <= 8 / <= 16 / <= 32, so max_tile_rows is bounded by
  * (227 KB - 128) / ((32 + rs) * 4).  out rows are accumulated (caller zeroes). */
 int32_t inmf_sell_pass_f32(const int64_t* work, int32_t nwork, const int64_t* slice_ptr, const int32_t* rowid,
                            const void* pairs4, int32_t height, const float* dense, int32_t kp, float* out, int64_t ldo,
-                           int32_t k, int32_t max_tile_rows, double* gram_out, void* stream);
+                           int32_t k, int32_t max_tile_rows, double* gram_out, int64_t part_stride,
+                           int64_t gram_part_stride, void* stream);
+
+/* Deterministic (bit-reproducible) accumulation.  By default the passes add their per-tile partial sums into the
+ * outputs with floating-point atomics, whose order depends on the CTA schedule.  With part_stride > 0 in
+ * inmf_sell_pass_f32, `out` (and gram_out, gram_part_stride doubles apart) is an array of partial buffers: work item w
+ * STORES its rows into partial work[w][6] (one writer per element), and inmf_reduce_parts_* then forms
+ * out[i] = part[0][i] + part[1][i] + ... in that fixed order.  inmf_set_deterministic(1) additionally makes
+ * inmf_prep_* and inmf_objective_* use one CTA per reduction (their double-precision atomics otherwise make the last
+ * bits of the Gram matrices / the objective depend on the schedule); returns the previous setting.  Process-wide. */
+int32_t inmf_set_deterministic(int32_t on);
+int32_t inmf_reduce_parts_f32(const float* part, int32_t nparts, int64_t stride, int64_t n, float* out, void* stream);
+int32_t inmf_reduce_parts_f64(const double* part, int32_t nparts, int64_t stride, int64_t n, double* out, void* stream);
 
 /* Builder of pairs4: copies the rows slice_rows[s*height + i] (indices into ptr of the row-ordered blocked format built
  * by inmf_blockfmt1/2_f32, -1 = no row) into the slices laid out by slice_ptr, zero padded.  height = -32: slices of

@@ -29,16 +29,17 @@ _TYPED = {
     "inmf_blocked_spmm": [_PTR, _I32, _PTR, _PTR, _PTR, _I32, _PTR, _I64, _I32, _I32, _PTR, _PTR],
     "inmf_normalize_rows": [_PTR, _PTR, _PTR, _I64, _PTR, _PTR, _PTR, _PTR, _PTR],
     "inmf_select_scale": [_PTR, _PTR, _PTR, _I64, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR],
+    "inmf_reduce_parts": [_PTR, _I32, _I64, _I64, _PTR, _PTR],
     "inmf_hals_h": [_PTR, _PTR, _I64, _PTR, _I64, _PTR, _I32, _I64, _I32, _PTR],
     "inmf_blockfmt1": [_I32, _PTR, _PTR, _PTR, _PTR, _I32, _I64, _I32, _I32, _I32, _PTR, _PTR, _PTR],
     "inmf_blockfmt2": [_I32, _PTR, _PTR, _PTR, _PTR, _I32, _I32, _I32, _I32, _PTR, _PTR, _PTR, _PTR, _PTR],
 }
 
-EXPORTED_SYMBOLS = ["inmf_version", "inmf_last_error", "inmf_launch_count", "inmf_bpp_workspace_bytes", "inmf_tc_selftest",
+EXPORTED_SYMBOLS = ["inmf_version", "inmf_last_error", "inmf_launch_count", "inmf_note_graph_launches", "inmf_bpp_workspace_bytes", "inmf_tc_selftest",
                     "inmf_tc_relayout_f32", "inmf_tc_pass_f32", "inmf_tc_debug_buffer", "inmf_select_count", "inmf_mt19937_uniform", "inmf_blocked_split_f32", "inmf_blocked_wide_f32",
                     "inmf_sell_pass_f32", "inmf_sell_fill_f32",
                     "inmf_qn_max_factor", "inmf_qn_knn", "inmf_qn_vote", "inmf_qn_align",
-                    "inmf_sell_pass_mixed", "inmf_to_bf16_rows", "inmf_to_bf16_gram"] + [
+                    "inmf_sell_pass_mixed", "inmf_to_bf16_rows", "inmf_to_bf16_gram", "inmf_set_deterministic"] + [
     "%s_%s" % (n, t) for n in _TYPED for t in ("f32", "f64")
 ]
 
@@ -65,6 +66,8 @@ def load():
     lib.inmf_last_error.argtypes = []
     lib.inmf_launch_count.restype = _I64
     lib.inmf_launch_count.argtypes = []
+    lib.inmf_note_graph_launches.restype = None
+    lib.inmf_note_graph_launches.argtypes = [_I64]
     lib.inmf_bpp_workspace_bytes.restype = _I64
     lib.inmf_bpp_workspace_bytes.argtypes = [_I64, _I32, _I32]
     lib.inmf_tc_selftest.restype = _I32
@@ -79,11 +82,14 @@ def load():
         getattr(lib, name).restype = _I32
         getattr(lib, name).argtypes = _TYPED["inmf_blocked_spmm"]
     lib.inmf_sell_pass_f32.restype = _I32
-    lib.inmf_sell_pass_f32.argtypes = [_PTR, _I32, _PTR, _PTR, _PTR, _I32, _PTR, _I32, _PTR, _I64, _I32, _I32, _PTR, _PTR]
+    lib.inmf_sell_pass_f32.argtypes = [_PTR, _I32, _PTR, _PTR, _PTR, _I32, _PTR, _I32, _PTR, _I64, _I32, _I32, _PTR, _I64, _I64,
+                                       _PTR]
     lib.inmf_sell_fill_f32.restype = _I32
     lib.inmf_sell_fill_f32.argtypes = [_PTR, _PTR, _PTR, _PTR, _I64, _I32, _PTR, _PTR]
     lib.inmf_sell_pass_mixed.restype = _I32
     lib.inmf_sell_pass_mixed.argtypes = [_PTR, _I32, _PTR, _PTR, _PTR, _PTR, _PTR, _I64, _I32, _I32, _PTR]
+    lib.inmf_set_deterministic.restype = _I32
+    lib.inmf_set_deterministic.argtypes = [_I32]
     lib.inmf_to_bf16_gram.restype = _I32
     lib.inmf_to_bf16_gram.argtypes = [_PTR, _I64, _PTR, _I32, _I64, _I32, _PTR, _PTR, _PTR]
     lib.inmf_to_bf16_rows.restype = _I32

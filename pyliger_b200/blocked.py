@@ -123,7 +123,7 @@ class BlockedPass(object):
 
 class SellPass(object):
     """Sliced form of a BlockedPass (csrc/sell.cuh): rows of every work item sorted by length, 8 per slice."""
-    __slots__ = ("work", "nwork", "slice_ptr", "rowid", "pairs4", "max_tile_rows", "nnz", "padded", "height")
+    __slots__ = ("work", "nwork", "slice_ptr", "rowid", "pairs4", "max_tile_rows", "nnz", "padded", "height", "nparts")
 
 
 SELL_HEIGHT_KP32 = 32  # slice height at kp == 32: 32 (one lane per row) or 8 (four lanes per row)
@@ -146,6 +146,7 @@ def build_sell(bp, kp, height=None):
         sp.rowid = torch.zeros(S, dtype=torch.int32, device=dev)
         sp.pairs4 = torch.zeros(1, 4, dtype=torch.int32, device=dev)
         sp.padded = 0
+        sp.nparts = 1
         return sp
     lo = W[:, 0] + W[:, 3]
     nrows = W[:, 4] - W[:, 3]
@@ -184,6 +185,8 @@ def build_sell(bp, kp, height=None):
     work[:, 3] = W[:, 2]
     work[:, 4] = W[:, 5]
     work[:, 5] = W[:, 6]
+    work[:, 6] = W[:, 7]
+    sp.nparts = int(W[:, 7].max()) + 1
     sp.work = torch.from_numpy(work).to(dev)
     return sp
 
@@ -291,7 +294,7 @@ def build_pass1(X, kp, esize, n_sms):
                 continue
             for lo in range(0, n, per):
                 work.append([NB * int(X.own_off[s]) + b * n, s * g + b * gbs, rows_b, lo, min(n, lo + per),
-                             int(X.own_off[s]), -1, 0])
+                             int(X.own_off[s]), -1, b])  # last field: partial buffer of the deterministic mode
     bp.nwork = len(work)
     bp.work_host = np.asarray(work if work else [[0] * WORK_FIELDS], dtype=np.int64)
     bp.work = torch.from_numpy(bp.work_host).to(dev)
@@ -341,7 +344,7 @@ def build_pass2(X, kp, esize, n_sms):
             rows_b = min(cbs[s], X.n_own[s] - b * cbs[s])
             for ci, lo in enumerate(range(0, g, per)):
                 work.append([g * (int(blk_off[s]) + b), int(X.own_off[s]) + b * cbs[s], rows_b, lo, min(g, lo + per),
-                             s * g, s if ci == 0 else -1, 0])
+                             s * g, s if ci == 0 else -1, b])
     bp.nwork = len(work)
     bp.work_host = np.asarray(work if work else [[0] * WORK_FIELDS], dtype=np.int64)
     bp.work = torch.from_numpy(bp.work_host).to(dev)

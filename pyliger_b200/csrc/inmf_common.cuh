@@ -120,9 +120,11 @@ __device__ __forceinline__ int64_t seg_row(const SegWin& w, int64_t j) {
 // =================================================================================================
 #define GRAM_TILE_ROWS 64
 
+// plain = true: `out` belongs to this CTA alone (a partial buffer of the deterministic mode): every entry is owned by one
+// thread, which adds to it without an atomic.
 template <typename T>
 __device__ __forceinline__ void tile_gram_accumulate(const T* __restrict__ tile, int ldt, int rows, int k,
-                                                     double* __restrict__ out, double scale) {
+                                                     double* __restrict__ out, double scale, bool plain = false) {
     const int nb = (k + 3) >> 2;
     for (int blk = threadIdx.x; blk < nb * nb; blk += blockDim.x) {
         const int bi = blk / nb, bj = blk % nb;
@@ -149,7 +151,10 @@ __device__ __forceinline__ void tile_gram_accumulate(const T* __restrict__ tile,
 #pragma unroll
             for (int b = 0; b < 4; ++b) {
                 const int i = 4 * bi + a, j = 4 * bj + b;
-                if (i < k && j < k) atomicAdd(&out[(size_t)i * k + j], scale * (double)acc[a][b]);
+                if (i < k && j < k) {
+                    if (plain) out[(size_t)i * k + j] += scale * (double)acc[a][b];
+                    else atomicAdd(&out[(size_t)i * k + j], scale * (double)acc[a][b]);
+                }
             }
     }
 }

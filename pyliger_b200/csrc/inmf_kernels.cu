@@ -12,8 +12,19 @@ thread_local char g_inmf_err[512] = "";
 
 long long g_inmf_launches = 0;
 
-extern "C" int32_t inmf_version(void) { return 100; }
+// Deterministic launch configurations (see include/inmf_b200.h, inmf_set_deterministic).
+static int g_inmf_deterministic = 0;
+extern "C" int32_t inmf_set_deterministic(int32_t on) {
+    const int old = __atomic_exchange_n(&g_inmf_deterministic, on ? 1 : 0, __ATOMIC_RELAXED);
+    return old;
+}
+static inline bool inmf_deterministic() { return __atomic_load_n(&g_inmf_deterministic, __ATOMIC_RELAXED) != 0; }
+
+extern "C" int32_t inmf_version(void) { return 200; }
 extern "C" int64_t inmf_launch_count(void) { return (int64_t)__atomic_load_n(&g_inmf_launches, __ATOMIC_RELAXED); }
+// Kernels of this library that ran through a CUDA-graph replay (the host-side counter above only sees the launches made
+// while the graph was captured): the caller reports how many kernel nodes each replay contained.
+extern "C" void inmf_note_graph_launches(int64_t n) { __atomic_add_fetch(&g_inmf_launches, (long long)n, __ATOMIC_RELAXED); }
 extern "C" const char* inmf_last_error(void) { return g_inmf_err; }
 
 // =================================================================================================
@@ -426,6 +437,7 @@ static int32_t prep_launch(const T* Wt, const T* Vt, T* Mt, int64_t ldm, double*
     INMF_CUDA_CHECK(cudaMemsetAsync(Gvv, 0, kk, st));
     int64_t tiles = (g + GRAM_TILE_ROWS - 1) / GRAM_TILE_ROWS;
     if (tiles > 1024) tiles = 1024;
+    if (inmf_deterministic()) tiles = 1;  // one CTA per segment: every Gram entry is summed by one thread, in row order
     const size_t smem = 2 * (size_t)GRAM_TILE_ROWS * ldm * sizeof(T);
     INMF_OPTIN_SMEM((prep_kernel<T>), 100 * 1024);
     prep_kernel<T><<<dim3((unsigned)tiles, (unsigned)nseg), 256, smem, st>>>(Wt, Vt, Mt, ldm, Gwv, Gvv, g, k);
@@ -663,7 +675,9 @@ static int32_t sqnorm_launch(const int64_t* rowptr, const T* vals, const int64_t
     INMF_REQUIRE(nseg >= 1 && nseg <= 65535, "nseg out of range");
     cudaStream_t st = (cudaStream_t)stream;
     INMF_CUDA_CHECK(cudaMemsetAsync(out, 0, nseg * sizeof(double), st));
-    sqnorm_kernel<T><<<dim3(inmf_num_sms() * 2, nseg), 256, 0, st>>>(rowptr, vals, seg_desc, out);
+    // deterministic mode: one CTA per segment (fixed summation tree)
+    sqnorm_kernel<T><<<dim3(inmf_deterministic() ? 1 : inmf_num_sms() * 2, nseg), inmf_deterministic() ? 1024 : 256, 0,
+                       st>>>(rowptr, vals, seg_desc, out);
     INMF_LAUNCH_CHECK();
     return 0;
 }
@@ -787,24 +801,29 @@ template <typename T>
 __global__ void objective_kernel(const T* __restrict__ St, const T* __restrict__ Mt, int64_t ldm,
                                  const double* __restrict__ HtH, const double* __restrict__ Gwv,
                                  const double* __restrict__ Gvv, const double* __restrict__ xnorm2, double lambda,
-                                 int64_t g, int k, double* __restrict__ obj) {
-    const int s = blockIdx.y;
-    const T* S = St + (size_t)s * g * k;
-    const T* M = Mt + (size_t)s * g * ldm;
+                                 int64_t g, int k, int nseg, double* __restrict__ obj) {
     double acc = 0.0;
-    const int64_t total = g * k;
-    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t c = t / k;
-        const int j = (int)(t - c * k);
-        acc += (double)S[t] * (double)M[c * ldm + j];
-    }
-    acc *= -2.0;
-    if (blockIdx.x == 0) {
-        const double* C = HtH + (size_t)s * k * k;
-        const double* A = Gwv + (size_t)s * k * k;
-        const double* B = Gvv + (size_t)s * k * k;
-        for (int t = threadIdx.x; t < k * k; t += blockDim.x) acc += C[t] * (A[t] + lambda * B[t]);
-        if (threadIdx.x == 0) acc += xnorm2[s];
+    // (grid.y == nseg: one segment per block row; grid = (1, 1) in deterministic mode: one CTA walks all segments,
+    // so the only cross-thread sums are the fixed-order reductions below)
+    for (int s = blockIdx.y; s < nseg; s += gridDim.y) {
+        const T* S = St + (size_t)s * g * k;
+        const T* M = Mt + (size_t)s * g * ldm;
+        double a2 = 0.0;
+        const int64_t total = g * k;
+        for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+             t += (int64_t)gridDim.x * blockDim.x) {
+            const int64_t c = t / k;
+            const int j = (int)(t - c * k);
+            a2 += (double)S[t] * (double)M[c * ldm + j];
+        }
+        acc += -2.0 * a2;
+        if (blockIdx.x == 0) {
+            const double* C = HtH + (size_t)s * k * k;
+            const double* A = Gwv + (size_t)s * k * k;
+            const double* B = Gvv + (size_t)s * k * k;
+            for (int t = threadIdx.x; t < k * k; t += blockDim.x) acc += C[t] * (A[t] + lambda * B[t]);
+            if (threadIdx.x == 0) acc += xnorm2[s];
+        }
     }
     acc = warp_sum(acc);
     __shared__ double part[32];
@@ -826,8 +845,9 @@ static int32_t objective_launch(const T* St, const T* Mt, int64_t ldm, const dou
     INMF_CUDA_CHECK(cudaMemsetAsync(obj, 0, sizeof(double), st));
     int64_t blocks = (g * k + 255) / 256;
     if (blocks > 64) blocks = 64;
-    objective_kernel<T><<<dim3((unsigned)blocks, (unsigned)nseg), 256, 0, st>>>(St, Mt, ldm, HtH, Gwv, Gvv, xnorm2,
-                                                                               lambda, g, k, obj);
+    const bool det = inmf_deterministic();
+    objective_kernel<T><<<dim3(det ? 1u : (unsigned)blocks, det ? 1u : (unsigned)nseg), det ? 1024 : 256, 0, st>>>(
+        St, Mt, ldm, HtH, Gwv, Gvv, xnorm2, lambda, g, k, nseg, obj);
     INMF_LAUNCH_CHECK();
     return 0;
 }
@@ -1424,19 +1444,22 @@ extern "C" int32_t inmf_blocked_wide_f32(const int64_t* work, int32_t nwork, con
 template <int REM>
 static int32_t sell_pass_one(const int64_t* work, int32_t nwork, const int64_t* slice_ptr, const int32_t* rowid,
                              const void* pairs4, const float* dense, int32_t kp, float* out, int64_t ldo, int32_t k,
-                             int32_t max_tile_rows, double* gram_out, void* stream) {
+                             int32_t max_tile_rows, double* gram_out, int64_t part_stride, int64_t gram_part_stride,
+                             void* stream) {
     const size_t smem = 128 + (size_t)max_tile_rows * (32 + REM) * sizeof(float);
     INMF_REQUIRE(smem <= 227 * 1024, "dense tile does not fit in shared memory");
     INMF_OPTIN_SMEM((sell_pass_kernel<REM>), 227 * 1024);
     sell_pass_kernel<REM><<<(unsigned)nwork, 1024, smem, (cudaStream_t)stream>>>(
-        work, slice_ptr, rowid, reinterpret_cast<const int4*>(pairs4), dense, kp, out, ldo, k, max_tile_rows, gram_out);
+        work, slice_ptr, rowid, reinterpret_cast<const int4*>(pairs4), dense, kp, out, ldo, k, max_tile_rows, gram_out,
+        part_stride, gram_part_stride);
     INMF_LAUNCH_CHECK();
     return 0;
 }
 extern "C" int32_t inmf_sell_pass_f32(const int64_t* work, int32_t nwork, const int64_t* slice_ptr,
                                       const int32_t* rowid, const void* pairs4, int32_t height, const float* dense,
                                       int32_t kp, float* out, int64_t ldo, int32_t k, int32_t max_tile_rows,
-                                      double* gram_out, void* stream) {
+                                      double* gram_out, int64_t part_stride, int64_t gram_part_stride, void* stream) {
+    INMF_REQUIRE(part_stride >= 0 && gram_part_stride >= 0, "partial strides must be >= 0");
     INMF_REQUIRE(k >= 1 && k <= INMF_MAX_K, "k must be in [1, 64]");
     INMF_REQUIRE(kp >= 32 && kp >= k && kp % 4 == 0 && kp <= 64, "kp must be a multiple of 4 in [max(k, 32), 64]");
     INMF_REQUIRE(ldo >= k, "ldo must be >= k");
@@ -1448,17 +1471,49 @@ extern "C" int32_t inmf_sell_pass_f32(const int64_t* work, int32_t nwork, const 
         INMF_REQUIRE(smem <= 227 * 1024, "dense tile does not fit in shared memory");
         INMF_OPTIN_SMEM((sell32_pass_kernel), 227 * 1024);
         sell32_pass_kernel<<<(unsigned)nwork, SELL32_THREADS, smem, (cudaStream_t)stream>>>(
-            work, slice_ptr, rowid, reinterpret_cast<const int4*>(pairs4), dense, out, ldo, k, gram_out);
+            work, slice_ptr, rowid, reinterpret_cast<const int4*>(pairs4), dense, out, ldo, k, gram_out, part_stride,
+            gram_part_stride);
         INMF_LAUNCH_CHECK();
         return 0;
     }
     const int rem = kp - 32;
-#define INMF_SELL_ARGS work, nwork, slice_ptr, rowid, pairs4, dense, kp, out, ldo, k, max_tile_rows, gram_out, stream
+#define INMF_SELL_ARGS \
+    work, nwork, slice_ptr, rowid, pairs4, dense, kp, out, ldo, k, max_tile_rows, gram_out, part_stride, gram_part_stride, stream
     if (rem == 0) return sell_pass_one<0>(INMF_SELL_ARGS);
     if (rem <= 8) return sell_pass_one<8>(INMF_SELL_ARGS);
     if (rem <= 16) return sell_pass_one<16>(INMF_SELL_ARGS);
     return sell_pass_one<32>(INMF_SELL_ARGS);
 #undef INMF_SELL_ARGS
+}
+
+// out[i] = part[0][i] + part[1][i] + ... in that order (the deterministic mode's ordered sum of partial buffers).
+template <typename T>
+__global__ void __launch_bounds__(256) reduce_parts_kernel(const T* __restrict__ part, int nparts, int64_t stride,
+                                                           int64_t n, T* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        T acc = part[i];
+        for (int p = 1; p < nparts; ++p) acc += part[(size_t)p * stride + i];
+        out[i] = acc;
+    }
+}
+template <typename T>
+static int32_t reduce_parts_launch(const T* part, int32_t nparts, int64_t stride, int64_t n, T* out, void* stream) {
+    INMF_REQUIRE(nparts >= 1 && stride >= n && n >= 0, "bad partial layout");
+    if (n == 0) return 0;
+    int64_t blocks = (n + 255) / 256;
+    const int64_t cap = (int64_t)inmf_num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    reduce_parts_kernel<T><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(part, nparts, stride, n, out);
+    INMF_LAUNCH_CHECK();
+    return 0;
+}
+extern "C" int32_t inmf_reduce_parts_f32(const float* part, int32_t nparts, int64_t stride, int64_t n, float* out,
+                                         void* stream) {
+    return reduce_parts_launch<float>(part, nparts, stride, n, out, stream);
+}
+extern "C" int32_t inmf_reduce_parts_f64(const double* part, int32_t nparts, int64_t stride, int64_t n, double* out,
+                                         void* stream) {
+    return reduce_parts_launch<double>(part, nparts, stride, n, out, stream);
 }
 
 extern "C" int32_t inmf_sell_pass_mixed(const int64_t* work, int32_t nwork, const int64_t* slice_ptr,

@@ -26,7 +26,11 @@
 #include "blocked.cuh"
 
 #define SELL_WORK_FIELDS 8
-// work[w] = { slice_begin, slice_end, dense_row0, tile_rows, out_row_base, gram_seg (-1: none), unused, unused }
+// work[w] = { slice_begin, slice_end, dense_row0, tile_rows, out_row_base, gram_seg (-1: none), part, unused }
+// Deterministic mode (part_stride > 0): `out` is an array of partial buffers part_stride elements apart; work item w
+// STORES its rows into partial `part` (rows of one partial are written by exactly one work item, each by one lane
+// group, so no atomics and no dependence on the order in which CTAs run); the caller then adds the partials in a fixed
+// order (inmf_reduce_parts_*).  gram_out likewise (gram_part_stride doubles apart).
 #define SELL_U 2  // 128-bit pair loads per pipeline stage
 
 __device__ __forceinline__ int4 sell_ld(const int4* p) {
@@ -106,8 +110,15 @@ __device__ __forceinline__ void red_add2(float* p, float a, float b) {
     asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
 }
 
-// out[col0 .. col0+3] += v[0..3] for the columns < k.  vec = 4: rows are 16-byte aligned, 2: 8-byte aligned, else 1.
+// out[col0 .. col0+3] += v[0..3] for the columns < k.  vec = 4: rows are 16-byte aligned, 2: 8-byte aligned, else 1;
+// vec = 0: plain stores (deterministic mode, zeros included).
 __device__ __forceinline__ void sell_out4(float* __restrict__ o, int col0, int k, const float (&v)[4], int vec) {
+    if (vec == 0) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (col0 + u < k) o[col0 + u] = v[u];
+        return;
+    }
     if (vec == 4 && col0 + 4 <= k) {
         if (v[0] != 0.f || v[1] != 0.f || v[2] != 0.f || v[3] != 0.f) red_add4(o + col0, v);
     } else if (vec >= 2 && col0 + 4 <= k) {
@@ -125,7 +136,7 @@ __global__ void __launch_bounds__(1024, 1)
 sell_pass_kernel(const int64_t* __restrict__ work, const int64_t* __restrict__ slice_ptr,
                  const int32_t* __restrict__ rowid, const int4* __restrict__ pairs, const float* __restrict__ dense,
                  int KP, float* __restrict__ out, int64_t ldo, int k, int max_tile_rows,
-                 double* __restrict__ gram_out) {
+                 double* __restrict__ gram_out, int64_t part_stride, int64_t gram_part_stride) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
     int* next_slice = reinterpret_cast<int*>(smem_raw + 16);
@@ -137,7 +148,13 @@ sell_pass_kernel(const int64_t* __restrict__ work, const int64_t* __restrict__ s
     const int tile_rows = (int)wd[3];
     const int64_t out_row_base = wd[4];
     const int gram_seg = (int)wd[5];
+    if (part_stride > 0) {
+        out += (size_t)wd[6] * part_stride;
+        if (gram_out != nullptr) gram_out += (size_t)wd[6] * gram_part_stride;
+    }
     const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    (void)nwarps;
+    (void)warp;
 
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);
@@ -175,7 +192,8 @@ sell_pass_kernel(const int64_t* __restrict__ work, const int64_t* __restrict__ s
         tR = smem_u32(trem) + (uint32_t)((sub + 4 * par) * 16);
         tR2 = smem_u32(trem) + (uint32_t)((sub + 4 * (1 - par)) * 16);
     }
-    const int vec_ok = (((ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0)) ? 4
+    const int vec_ok = part_stride > 0 ? 0
+                       : (((ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0)) ? 4
                        : (((ldo & 1) == 0) && ((reinterpret_cast<uintptr_t>(out) & 7) == 0)) ? 2 : 1;
 
     mbar_wait(bar, 0);
@@ -184,9 +202,9 @@ sell_pass_kernel(const int64_t* __restrict__ work, const int64_t* __restrict__ s
     // and the latency-bound Gram loop costs no tail.
     if (gram_seg >= 0 && gram_out != nullptr) {
         if constexpr (REM == 0)
-            tile_gram_accumulate<float>(tmain, 32, tile_rows, k, gram_out + (size_t)gram_seg * k * k, 1.0);
+            tile_gram_accumulate<float>(tmain, 32, tile_rows, k, gram_out + (size_t)gram_seg * k * k, 1.0, part_stride > 0);
         else
-            split_gram_accumulate(tmain, trem, REM, tile_rows, k, gram_out + (size_t)gram_seg * k * k);
+            split_gram_accumulate(tmain, trem, REM, tile_rows, k, gram_out + (size_t)gram_seg * k * k, part_stride > 0);
     }
     int s = 0;
     if (lane == 0) s = atomicAdd(next_slice, 1);
@@ -239,8 +257,12 @@ sell_pass_kernel(const int64_t* __restrict__ work, const int64_t* __restrict__ s
             sell_out4(o, 4 * sub + 16 * (1 - par), k, c.b, vec_ok);
             if constexpr (REM == 8) {
 #pragma unroll
-                for (int u = 0; u < 2; ++u)
-                    if (32 + 2 * sub + u < k && c.r[u] != 0.f) red_add(o + 32 + 2 * sub + u, c.r[u]);
+                for (int u = 0; u < 2; ++u) {
+                    if (32 + 2 * sub + u < k) {
+                        if (vec_ok == 0) o[32 + 2 * sub + u] = c.r[u];
+                        else if (c.r[u] != 0.f) red_add(o + 32 + 2 * sub + u, c.r[u]);
+                    }
+                }
             } else if constexpr (REM == 16) {
                 float q[4] = {c.r[0], c.r[1], c.r[2], c.r[3]};
                 sell_out4(o, 32 + 4 * sub, k, q, vec_ok);
@@ -276,7 +298,8 @@ sell_pass_kernel(const int64_t* __restrict__ work, const int64_t* __restrict__ s
 __global__ void __launch_bounds__(SELL32_THREADS, 1)
 sell32_pass_kernel(const int64_t* __restrict__ work, const int64_t* __restrict__ slice_ptr,
                    const int32_t* __restrict__ rowid, const int4* __restrict__ pairs, const float* __restrict__ dense,
-                   float* __restrict__ out, int64_t ldo, int k, double* __restrict__ gram_out) {
+                   float* __restrict__ out, int64_t ldo, int k, double* __restrict__ gram_out, int64_t part_stride,
+                   int64_t gram_part_stride) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
     int* next_slice = reinterpret_cast<int*>(smem_raw + 16);
@@ -287,7 +310,11 @@ sell32_pass_kernel(const int64_t* __restrict__ work, const int64_t* __restrict__
     const int tile_rows = (int)wd[3];
     const int64_t out_row_base = wd[4];
     const int gram_seg = (int)wd[5];
-    const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (part_stride > 0) {
+        out += (size_t)wd[6] * part_stride;
+        if (gram_out != nullptr) gram_out += (size_t)wd[6] * gram_part_stride;
+    }
+    const int lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);
@@ -307,12 +334,13 @@ sell32_pass_kernel(const int64_t* __restrict__ work, const int64_t* __restrict__
     uint32_t tb[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) tb[j] = smem_u32(tile) + (uint32_t)(((lane + j) & 7) * 16);
-    const int vec_ok = (((ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0)) ? 4
+    const int vec_ok = part_stride > 0 ? 0
+                       : (((ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0)) ? 4
                        : (((ldo & 1) == 0) && ((reinterpret_cast<uintptr_t>(out) & 7) == 0)) ? 2 : 1;
 
     mbar_wait(bar, 0);
     if (gram_seg >= 0 && gram_out != nullptr)  // first, by the warps that own output blocks (see sell_pass_kernel)
-        tile_gram_accumulate<float>(tile, 32, tile_rows, k, gram_out + (size_t)gram_seg * k * k, 1.0);
+        tile_gram_accumulate<float>(tile, 32, tile_rows, k, gram_out + (size_t)gram_seg * k * k, 1.0, part_stride > 0);
     int s = 0;
     if (lane == 0) s = atomicAdd(next_slice, 1);
     s = __shfl_sync(INMF_FULL_MASK, s, 0);

@@ -13,6 +13,9 @@ Keyword-only extensions (defaults preserve reference behaviour):
               iterates are the same (tests: trajectories equal to 4e-16 in fp64 with and without) while the
               solver needs ~2 instead of 4-5 factorisations per column.  Default True; False = the reference's
               literal cold start (init=None) in every iteration
+  deterministic  (float32) bit-reproducible iterations: the sliced passes store per-tile partial sums that are added in
+              a fixed order instead of with floating-point atomics, and the Gram / objective reductions use one CTA
+              each.  Slower (about +10 % at C2); default False
   return_info if True, return a dict with the per-iteration objectives and solver counters
               (the reference returns None; the default stays None)
   tensor_core None (default) = CUDA-core passes; "tf32x3" / "tf32" = experimental dense-tile tcgen05 form
@@ -66,6 +69,7 @@ def optimize_ALS(
     progress=True,
     presharded=False,
     tensor_core=None,
+    deterministic=False,
 ):
     N = liger_object.num_samples
     ns = [adata.shape[0] for adata in liger_object.adata_list]
@@ -92,7 +96,8 @@ def optimize_ALS(
     if not user_init:  # the first seeded draw runs on one SM while X is uploaded and laid out
         pending = launch_als_draw(require_cuda(device), ns, num_genes, k, rand_seed - 1, h_stream)
     engine = InmfEngine(X, k, value_lambda, dtype=dtype, device=device, presharded=presharded,
-                        use_tc=tensor_core is not None, tc_three_pass=tensor_core != "tf32")
+                        use_tc=tensor_core is not None, tc_three_pass=tensor_core != "tf32",
+                        deterministic=deterministic)
     best_obj = np.inf
     best = None
     best_dev = None

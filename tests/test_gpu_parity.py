@@ -600,3 +600,62 @@ def test_c1_mixed_precision_mode(c1_problem):
     assert obj < 1e-3
     assert h < 0.2 and w < 0.2 and v < 0.2 and agree > 0.5
     assert info["bpp"]["H"]["not_converged"] == 0
+
+
+@pytest.mark.parametrize("k,budget_rows", [(30, 100000), (40, 60), (12, 25)])
+def test_deterministic_mode_is_bit_reproducible(k, budget_rows):
+    """optimize_ALS(dtype='float32', deterministic=True): two runs give bitwise identical objectives and factors (the
+    default mode accumulates with floating-point atomics: equal only to round-off), and both agree with the default
+    mode to fp32 tolerance.  Small tiles force several gene / cell blocks (ordered sums over > 2 partials)."""
+    from pyliger_b200 import blocked, optimize_ALS
+    from pyliger_b200.synth import make_datasets
+    mats = make_datasets([2100, 1700, 900], 500, k, density=0.1, seed0=3500 + k)
+    old = blocked.SMEM_BUDGET
+    kp = max(32, (k + 3) // 4 * 4)
+    blocked.SMEM_BUDGET = min(old, budget_rows * blocked.smem_row_bytes(kp, 4))
+    try:
+        runs = []
+        for det in (True, True, False):
+            lig = _liger(mats)
+            info = optimize_ALS(lig, k, 5.0, 1e-6, 6, rand_seed=1, dtype="float32", deterministic=det, return_info=True,
+                                progress=False)
+            runs.append((np.array(info["objectives"][0]), [h.copy() for h in lig.H], lig.W.copy(),
+                         [v.copy() for v in lig.V]))
+    finally:
+        blocked.SMEM_BUDGET = old
+    a, b, c = runs
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[2], b[2])
+    assert all(np.array_equal(x, y) for x, y in zip(a[1], b[1])) and all(np.array_equal(x, y) for x, y in zip(a[3], b[3]))
+    np.testing.assert_allclose(a[0], c[0], rtol=1e-5)
+    assert relerr(a[2], c[2]) < 1e-2
+    with pytest.raises(ValueError):
+        optimize_ALS(_liger(mats), k, dtype="float64", deterministic=True, progress=False)
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_graphed_iterations_equal_eager_iterations(dtype):
+    """Warm-started iterations replayed as CUDA graphs (engine.use_graph) against the eager launch sequence: same
+    objectives and factors (fp64: to round-off of the atomics; the kernels and their order are identical), early stop
+    with a dropped speculative pass 1 included."""
+    from pyliger_b200 import optimize_ALS
+    from pyliger_b200.engine import InmfEngine
+    from pyliger_b200.synth import make_datasets
+    mats = make_datasets([1500, 1100, 700], 300, 12, density=0.1, seed0=3700)
+    res = {}
+    old = InmfEngine.use_graph
+    try:
+        for graph in (True, False):
+            InmfEngine.use_graph = graph
+            for thresh, iters in ((1e-9, 9), (3e-3, 30)):
+                lig = _liger(mats)
+                info = optimize_ALS(lig, 12, 5.0, thresh, iters, rand_seed=1, dtype=dtype, return_info=True, progress=False)
+                res[(graph, thresh)] = (np.array(info["objectives"][0]), [h.copy() for h in lig.H], lig.W.copy())
+    finally:
+        InmfEngine.use_graph = old
+    tol = 1e-12 if dtype == "float64" else 1e-5
+    for thresh in (1e-9, 3e-3):
+        a, b = res[(True, thresh)], res[(False, thresh)]
+        assert a[0].shape == b[0].shape and (thresh == 1e-9 or 3 < len(a[0]) < 30)
+        np.testing.assert_allclose(a[0], b[0], rtol=tol)
+        assert relerr(a[2], b[2]) < (1e-10 if dtype == "float64" else 1e-3)
+        assert all(relerr(x, y) < (1e-10 if dtype == "float64" else 1e-3) for x, y in zip(a[1], b[1]))
