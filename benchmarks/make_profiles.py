@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Turn the raw outputs of benchmarks/final_profile.sh (gpurun_out/) into the tracked summaries under profiles/."""
+"""Turn the raw outputs of benchmarks/final_profile_r2.sh (gpurun_out/) into the tracked summaries under profiles/.
+(Round 1's summaries, r1_*, were produced by the round-1 version of this script and are kept as they are.)"""
 import collections
 import csv
 import json
@@ -11,14 +12,16 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT, PROF = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
-OURS = re.compile(r"blocked_(spmm|split|wide)_kernel|bpp_kernel|ginv_kernel|rhs_[vw]_kernel|prep_kernel|objective_kernel|"
+OURS = re.compile(r"sell(32h?)?_(pass|fill|fill_parity)_kernel|bpp16_kernel|to_bf16_(rows|gram)_kernel|reduce_parts_kernel|"
+                  r"hals_h_kernel|qn_\w+_kernel|"
+                  r"blocked_(spmm|split|wide)_kernel|bpp_kernel|ginv_kernel|rhs_[vw]_kernel|prep_kernel|objective_kernel|"
                   r"sqnorm_kernel|combine_g_kernel|blockfmt[12]_kernel|mt19937_uniform_kernel|gram_rows_kernel|"
                   r"stats_scatter_kernel|spmm_rows_kernel|hals_(inc_)?kernel|update_ab_kernel|normalize_rows_kernel|"
                   r"select_(count|scale)_kernel|tc_(pass|relayout)_kernel")
 
 
 def launches():
-    rows = list(csv.reader(l for l in open(os.path.join(OUT, "launches_final.csv")) if not l.startswith("==")))
+    rows = list(csv.reader(l for l in open(os.path.join(OUT, "r2_launches.csv")) if not l.startswith("==")))
     h = rows[0]
     ki, vi, ui = h.index("Kernel Name"), h.index("Metric Value"), h.index("Metric Unit")
     agg, other = collections.OrderedDict(), [0, 0.0]
@@ -36,61 +39,60 @@ def launches():
             other[0] += 1
             other[1] += v
     tot = sum(a[1] for a in agg.values())
-    out = ["# Round 1 (final build) launch list: ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv "
-           "-- python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e",
-           "# (cold-cache, serialised per-launch times: compare SHARES with bench.py's CUDA-event breakdown, not absolutes)",
+    out = ["# Round 2 (final build) launch list: ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv "
+           "-- python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e --no-extra --graph 0",
+           "# (cold-cache, serialised per-launch times: compare SHARES with bench.py's CUDA-event breakdown, not absolutes;",
+           "#  --graph 0 = the eager launch sequence, the same kernels the graphs replay)",
            "# one B200, C2 workload (4 x 50k cells x 3k genes, k=30, fp32); the process runs 1 init + 3 warm-up + 2 timed "
            "+ 5 breakdown iterations",
-           "# kernels of libinmf_b200.so only; the first 600 launches of the process also hold %d torch launches "
-           "(%.1f ms) of the synthetic data generator and plumbing (cumsum, copies)" % (other[0], other[1] / 1e3),
-           "# bpp_kernel<float, 1> = H solve (complement-set build; averaged over cold and early iterations, which need "
-           "more rounds than the converged ones bench.py's breakdown times), <float, 0> = V and W solves;",
-           "# blockfmt* / mt19937 = one-off build of the blocked copies of X and the seeded init",
+           "# kernels of libinmf_b200.so only; the captured launches also hold %d torch launches (%.1f ms) of the synthetic "
+           "data generator and plumbing (sort, cumsum, copies)" % (other[0], other[1] / 1e3),
+           "# sell32_pass_kernel = both X-streaming passes; bpp16_kernel = H solve (half-warp lockstep), bpp_kernel = V / W "
+           "solves and the (empty) deferral lists; blockfmt* / sell_fill / mt19937 = one-off format build and seeded init",
            "%-58s %6s %12s %8s %7s" % ("kernel", "count", "total_us", "avg_us", "share")]
     for n, (c, t) in sorted(agg.items(), key=lambda x: -x[1][1]):
         out.append("%-58s %6d %12.1f %8.1f %6.1f%%" % (n[:58], c, t, t / c, 100 * t / tot))
     out.append("%-58s %6d %12.1f" % ("TOTAL", sum(a[0] for a in agg.values()), tot))
-    open(os.path.join(PROF, "r1_launches.txt"), "w").write("\n".join(out) + "\n")
-    shutil.copy(os.path.join(OUT, "launches_final.csv"), os.path.join(PROF, "r1_launches.csv"))
+    open(os.path.join(PROF, "r2_launches.txt"), "w").write("\n".join(out) + "\n")
+    shutil.copy(os.path.join(OUT, "r2_launches.csv"), os.path.join(PROF, "r2_launches.csv"))
     print("\n".join(out))
 
 
 def full():
     body = subprocess.run([sys.executable, os.path.join(ROOT, "benchmarks", "ncu_summary.py"),
-                           os.path.join(OUT, "prof_final.ncu-rep")], capture_output=True, text=True).stdout
-    hdr = ("# Round 1 (final build): ncu --set full --clock-control none --import-source on -k regex:blocked_|bpp_kernel "
-           "-s 20 -c 5 -- python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e\n"
-           "# launches in order: bpp(W) of the previous iteration, blocked pass 1, bpp(H) [complement-set build <float, 1>], "
-           "blocked pass 2, bpp(V)\n"
-           "# (the captured iteration is the 5th from a random start: passive sets still move, so bpp(H) needs more rounds "
-           "than in bench.py's breakdown,\n#  which is taken after 25 iterations; cold-cache, serialised times)\n"
-           "# reading: the blocked passes sit on the L1/shared-memory data pipe (l1tex 89-93 %, DRAM 14-15 %); bpp(H) is "
-           "issue bound\n")
-    open(os.path.join(PROF, "r1_ncu_full_summary.txt"), "w").write(hdr + body)
+                           os.path.join(OUT, "r2_prof.ncu-rep")], capture_output=True, text=True).stdout
+    hdr = ("# Round 2 (final build): ncu --set full --clock-control none --import-source on "
+           "-k 'regex:sell32_pass|bpp16_kernel' -s 13 -c 3 -- python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e "
+           "--no-extra --graph 0\n"
+           "# launches in order: sell32_pass (pass 1), bpp16_kernel (H solve, warm), sell32_pass (pass 2) of the 5th "
+           "iteration; C2 workload, fp32, one B200 (cold-cache, serialised times)\n"
+           "# reading: the passes sit on the shared-memory operand bound (smem_wavefronts / 48.0 M non-zeros = 1.04-1.10 per "
+           "non-zero, LSU data pipe ~90 % busy, DRAM ~22 %); the H solve is issue / latency bound\n")
+    open(os.path.join(PROF, "r2_ncu_full_summary.txt"), "w").write(hdr + body)
     vals = re.findall(r"== (?:void )?(\w+).*?\n\s+time=.*?dram_rd=([\d.]+)Mbyte\s+dram_wr=([\d.]+)Mbyte", body)
-    label = {"spmm": "blocked_wide_kernel (pass 1)", "bpp_H": "bpp_kernel<float,true> (H solve)",
-             "stats": "blocked_wide_kernel (pass 2)"}
-    d = {"source": "ncu --set full --clock-control none, gpurun_out/prof_final.ncu-rep (summarised in "
-                   "profiles/r1_ncu_full_summary.txt); C2 workload, fp32, one B200; dram__bytes_read.sum + "
+    label = {"pass1": "sell32_pass_kernel (pass 1)", "bpp_H": "bpp16_kernel<float,2> (H solve)",
+             "pass2": "sell32_pass_kernel (pass 2)"}
+    d = {"source": "ncu --set full --clock-control none, gpurun_out/r2_prof.ncu-rep (summarised in "
+                   "profiles/r2_ncu_full_summary.txt); C2 workload, fp32, one B200; dram__bytes_read.sum + "
                    "dram__bytes_write.sum per launch", "kernels": {}}
-    for n, (_, rd, wr) in zip(["bpp_W", "spmm", "bpp_H", "stats", "bpp_V"], vals):
-        if n in label:
-            rd_b, wr_b = int(round(float(rd) * 1e6)), int(round(float(wr) * 1e6))
-            d["kernels"][n] = {"kernel": label[n], "dram_bytes_per_launch": rd_b + wr_b, "dram_read": rd_b,
-                               "dram_write": wr_b}
-    json.dump(d, open(os.path.join(PROF, "r1_ncu_traffic.json"), "w"), indent=1)
+    for n, (_, rd, wr) in zip(["pass1", "bpp_H", "pass2"], vals):
+        rd_b, wr_b = int(round(float(rd) * 1e6)), int(round(float(wr) * 1e6))
+        d["kernels"][n] = {"kernel": label[n], "dram_bytes_per_launch": rd_b + wr_b, "dram_read": rd_b, "dram_write": wr_b}
+    json.dump({"C2": d}, open(os.path.join(PROF, "r2_ncu_traffic.json"), "w"), indent=1)
     print(hdr + body[:3000])
 
 
 def copies():
-    for src, dst in (("c5_bpp_final.jsonl", "r1_c5_bpp_microbench_v2.jsonl"), ("c1_parity_final.json", "r1_c1_parity.json"),
-                     ("bench_final_n1.json", "r1_bench_n1.json"), ("bench_final_ref.json", "r1_bench_reference_arm.json"),
-                     ("bench_final_c4_n1.json", "r1_bench_c4_n1.json")):
-        if os.path.exists(os.path.join(OUT, src)):
-            shutil.copy(os.path.join(OUT, src), os.path.join(PROF, dst))
+    for src, dst in (("r2_bench_n1.json", "r2_bench_n1.json"), ("r2_bench_ref.json", "r2_bench_reference_arm.json"),
+                     ("r2_bench_n2.json", "r2_bench_n2.json"), ("r2_bench_n8.json", "r2_bench_n8.json")):
+        p = os.path.join(OUT, src)
+        if os.path.exists(p):
+            lines = [l for l in open(p).read().splitlines() if l.startswith("{")]
+            if lines:
+                open(os.path.join(PROF, dst), "w").write(lines[-1] + "\n")
 
 
 if __name__ == "__main__":
-    launches()
-    full()
-    copies()
+    which = sys.argv[1:] or ["launches", "full", "copies"]
+    for w in which:
+        {"launches": launches, "full": full, "copies": copies}[w]()
