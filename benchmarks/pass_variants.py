@@ -69,6 +69,7 @@ def main():
     for variant in args.variants.split(","):
         blocked.SELL = variant.startswith("sell") or variant == "mixed"
         blocked.SELL_HEIGHT_KP32 = 8 if variant == "sell8" else 32
+        blocked.SELL_HEIGHT_KP40 = 8 if variant == "sell8" else 33
         eng = InmfEngine(mats, k, 5.0, dtype="mixed" if variant == "mixed" else torch.float32, device=dev)
         eng.set_als_state(W0, V0, H0)
         eng.initial_objective()

@@ -153,7 +153,9 @@ int32_t inmf_hals_h_f64(const double* G, const double* R, int64_t ldr, double* H
  *   rowid int32[nslices*height]: output row of slice row i relative to the work item's out_row_base, -1 = no row.
  *   height = 8: four lanes per row (any kp);  height = 32 (kp == 32 only): one lane per row, the pair stream is not
  *   replicated across lanes and every lane walks the 16-byte chunks of its tile row in a rotated, bank-conflict-free
- *   order.
+ *   order;  height = 33 (32 < kp <= 40): 32 rows per slice, one lane per row, [rows x 32] + [rows x 8] tile, the
+ *   non-zeros of every row ordered by (tile row mod 4) so that the 32-byte remainder rows of a phase fall in different
+ *   bank groups (inmf_sell_fill_f32 with height = 33 builds that order).
  *   work int64[nwork][8] = { slice_begin, slice_end, dense_row0, tile_rows, out_row_base, gram_seg, part, 0 }
  * dense has kp floats per row (kp = 32 for k <= 32, else k rounded up to 4); the tile is held in shared memory as
  * [rows x 32] + [rows x rs], rs = 0 / 8 / 16 / 32 for kp - 32 = 0 / <= 8 / <= 16 / <= 32, so max_tile_rows is bounded by

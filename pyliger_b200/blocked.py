@@ -127,6 +127,7 @@ class SellPass(object):
 
 
 SELL_HEIGHT_KP32 = 32  # slice height at kp == 32: 32 (one lane per row) or 8 (four lanes per row)
+SELL_HEIGHT_KP40 = 33  # 32 < kp <= 40: 33 (one lane per row, residue-ordered non-zeros) or 8 (four lanes per row)
 
 
 def build_sell(bp, kp, height=None):
@@ -135,8 +136,9 @@ def build_sell(bp, kp, height=None):
     dev = bp.ptr.device
     W = bp.work_host[:bp.nwork]
     sp = SellPass()
-    sp.height = int(height or (SELL_HEIGHT_KP32 if kp == 32 else 8))  # -32: parity-ordered rows (mixed precision)
-    S = abs(sp.height)
+    # -32: parity-ordered rows (mixed precision); 33: 32 residue-ordered rows (32 < kp <= 40)
+    sp.height = int(height or (SELL_HEIGHT_KP32 if kp == 32 else (SELL_HEIGHT_KP40 if 32 < kp <= 40 else 8)))
+    S = 32 if sp.height == 33 else abs(sp.height)
     sp.max_tile_rows = bp.max_tile_rows
     sp.nwork = bp.nwork
     sp.nnz = int(bp.pairs.shape[0])

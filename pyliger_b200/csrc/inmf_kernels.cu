@@ -1464,8 +1464,19 @@ extern "C" int32_t inmf_sell_pass_f32(const int64_t* work, int32_t nwork, const 
     INMF_REQUIRE(kp >= 32 && kp >= k && kp % 4 == 0 && kp <= 64, "kp must be a multiple of 4 in [max(k, 32), 64]");
     INMF_REQUIRE(ldo >= k, "ldo must be >= k");
     INMF_REQUIRE((reinterpret_cast<uintptr_t>(pairs4) & 15) == 0, "pairs4 must be 16-byte aligned");
-    INMF_REQUIRE(height == 8 || (height == 32 && kp == 32), "slice height must be 8, or 32 with kp == 32");
+    INMF_REQUIRE(height == 8 || (height == 32 && kp == 32) || (height == 33 && kp > 32 && kp <= 40),
+                 "slice height must be 8, 32 with kp == 32, or 33 (32 residue-ordered rows) with 32 < kp <= 40");
     if (nwork <= 0) return 0;
+    if (height == 33) {
+        const size_t smem = 128 + (size_t)max_tile_rows * 40 * sizeof(float);
+        INMF_REQUIRE(smem <= 227 * 1024, "dense tile does not fit in shared memory");
+        INMF_OPTIN_SMEM((sell32r_pass_kernel), 227 * 1024);
+        sell32r_pass_kernel<<<(unsigned)nwork, SELL32_THREADS, smem, (cudaStream_t)stream>>>(
+            work, slice_ptr, rowid, reinterpret_cast<const int4*>(pairs4), dense, kp, out, ldo, k, max_tile_rows, gram_out,
+            part_stride, gram_part_stride);
+        INMF_LAUNCH_CHECK();
+        return 0;
+    }
     if (height == 32) {
         const size_t smem = 128 + (size_t)max_tile_rows * 128;
         INMF_REQUIRE(smem <= 227 * 1024, "dense tile does not fit in shared memory");
@@ -1564,12 +1575,16 @@ extern "C" int32_t inmf_sell_fill_f32(const int64_t* ptr, const void* pairs, con
                                       const int64_t* slice_ptr, int64_t nslices, int32_t height, void* pairs4,
                                       void* stream) {
     if (nslices <= 0) return 0;
-    INMF_REQUIRE(height == 8 || height == 32 || height == -32, "slice height must be 8 or 32 (-32: parity ordered)");
+    INMF_REQUIRE(height == 8 || height == 32 || height == -32 || height == 33,
+                 "slice height must be 8 or 32 (-32: parity ordered, 33: residue ordered)");
     INMF_REQUIRE((reinterpret_cast<uintptr_t>(pairs4) & 15) == 0, "pairs4 must be 16-byte aligned");
     int64_t blocks = (nslices + 7) / 8;
     const int64_t cap = (int64_t)inmf_num_sms() * 16;
     if (blocks > cap) blocks = cap;
-    if (height == -32)
+    if (height == 33)
+        sell_fill_residue_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+            ptr, reinterpret_cast<const int2*>(pairs), slice_rows, slice_ptr, nslices, reinterpret_cast<int4*>(pairs4));
+    else if (height == -32)
         sell_fill_parity_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
             ptr, reinterpret_cast<const int2*>(pairs), slice_rows, slice_ptr, nslices, reinterpret_cast<int4*>(pairs4));
     else if (height == 8)

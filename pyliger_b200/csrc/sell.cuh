@@ -400,6 +400,129 @@ sell32_pass_kernel(const int64_t* __restrict__ work, const int64_t* __restrict__
 }
 
 // =====================================================================================================
+// One lane per row for 32 < k <= 40 (the k = 40 target shape): [rows x 32] main tile + [rows x 8] remainder.
+//
+// The main part is read as in sell32_pass_kernel (rotated chunk order, conflict free).  A remainder row is 32 bytes =
+// two 16-byte chunks, four rows per 128-byte bank line: its bank position is (2 * (row mod 4) + chunk), i.e. data
+// dependent, and the four-lanes-per-row kernel pays ~2-way conflicts for it (plus 0.25 wavefront per non-zero for the
+// replicated pair stream).  Here even lanes read chunk 0 first and chunk 1 second, odd lanes the other way round, so
+// in each of the two loads the even lanes hit even positions and the odd lanes odd ones; and the builder
+// (sell_fill_residue_kernel) orders every row's non-zeros so that at step j lane l gathers a tile row with
+// (row mod 4) == (l / 2 + j) mod 4 while its supply of that residue class lasts -- the four even (odd) lanes of a
+// phase then hit four different positions.  Conflicts remain only where a row runs out of a class early.
+// =====================================================================================================
+__global__ void __launch_bounds__(SELL32_THREADS, 1)
+sell32r_pass_kernel(const int64_t* __restrict__ work, const int64_t* __restrict__ slice_ptr,
+                    const int32_t* __restrict__ rowid, const int4* __restrict__ pairs, const float* __restrict__ dense,
+                    int KP, float* __restrict__ out, int64_t ldo, int k, int max_tile_rows,
+                    double* __restrict__ gram_out, int64_t part_stride, int64_t gram_part_stride) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+    int* next_slice = reinterpret_cast<int*>(smem_raw + 16);
+    float* tmain = reinterpret_cast<float*>(smem_raw + 128);
+    float* trem = tmain + (size_t)max_tile_rows * 32;
+    const int64_t* wd = work + (size_t)blockIdx.x * SELL_WORK_FIELDS;
+    const int slice_begin = (int)wd[0], slice_end = (int)wd[1];
+    const int64_t dense_row0 = wd[2];
+    const int tile_rows = (int)wd[3];
+    const int64_t out_row_base = wd[4];
+    const int gram_seg = (int)wd[5];
+    if (part_stride > 0) {
+        out += (size_t)wd[6] * part_stride;
+        if (gram_out != nullptr) gram_out += (size_t)wd[6] * gram_part_stride;
+    }
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        mbar_expect_tx(bar, (uint32_t)((size_t)tile_rows * KP * sizeof(float)));
+        *next_slice = slice_begin;
+    }
+    __syncthreads();
+    {
+        const float* src = dense + (size_t)dense_row0 * KP;
+        const int R = KP - 32;  // remainder floats per row in global memory (4 or 8)
+        for (int r = threadIdx.x; r < tile_rows; r += blockDim.x) {
+            bulk_g2s(tmain + (size_t)r * 32, src + (size_t)r * KP, 128u, bar);
+            bulk_g2s(trem + (size_t)r * 8, src + (size_t)r * KP + 32, (uint32_t)(R * sizeof(float)), bar);
+        }
+    }
+    uint32_t tb[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) tb[j] = smem_u32(tmain) + (uint32_t)(((lane + j) & 7) * 16);
+    const uint32_t rA = smem_u32(trem) + (uint32_t)((lane & 1) * 16);
+    const uint32_t rB = smem_u32(trem) + (uint32_t)((1 - (lane & 1)) * 16);
+    const int vec_ok = part_stride > 0 ? 0
+                       : (((ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0)) ? 4
+                       : (((ldo & 1) == 0) && ((reinterpret_cast<uintptr_t>(out) & 7) == 0)) ? 2 : 1;
+    mbar_wait(bar, 0);
+    if (gram_seg >= 0 && gram_out != nullptr)
+        split_gram_accumulate(tmain, trem, 8, tile_rows, k, gram_out + (size_t)gram_seg * k * k, part_stride > 0);
+    int s = 0;
+    if (lane == 0) s = atomicAdd(next_slice, 1);
+    s = __shfl_sync(INMF_FULL_MASK, s, 0);
+    int64_t base = 0, lim = 0;
+    if (s < slice_end) {
+        base = slice_ptr[s];
+        lim = slice_ptr[s + 1];
+    }
+    while (s < slice_end) {
+        const int L2 = (int)((lim - base) >> 5);
+        const int4* __restrict__ p = pairs + base + lane;
+        const int rid = rowid[(size_t)s * 32 + lane];
+        float acc[8][4], ra[4], rb[4];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int u = 0; u < 4; ++u) acc[j][u] = 0.f;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) ra[u] = rb[u] = 0.f;
+        const int4 z4 = make_int4(0, 0, 0, 0);
+        int4 A = (0 < L2) ? sell_ld(p) : z4;
+        for (int j = 0; j < L2; ++j) {
+            const int4 A2 = (j + 1 < L2) ? sell_ld(p + (size_t)(j + 1) * 32) : z4;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int off = h == 0 ? A.x : A.z;
+                const float v = __int_as_float(h == 0 ? A.y : A.w);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    float m[4];
+                    lds128(tb[c] + (uint32_t)off, m);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) acc[c][u] = fmaf(v, m[u], acc[c][u]);
+                }
+                float m[4], n[4];
+                lds128(rA + ((uint32_t)off >> 2), m);
+                lds128(rB + ((uint32_t)off >> 2), n);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) ra[u] = fmaf(v, m[u], ra[u]);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) rb[u] = fmaf(v, n[u], rb[u]);
+            }
+            A = A2;
+        }
+        int sn = 0;
+        if (lane == 0) sn = atomicAdd(next_slice, 1);
+        sn = __shfl_sync(INMF_FULL_MASK, sn, 0);
+        int64_t nbase = 0, nlim = 0;
+        if (sn < slice_end) {
+            nbase = slice_ptr[sn];
+            nlim = slice_ptr[sn + 1];
+        }
+        if (rid >= 0) {
+            float* o = out + (out_row_base + rid) * ldo;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) sell_out4(o, ((lane + c) & 7) * 4, k, acc[c], vec_ok);
+            sell_out4(o, 32 + 4 * (lane & 1), k, ra, vec_ok);        // even lanes: ra = factors 32..35, rb = 36..39
+            sell_out4(o, 32 + 4 * (1 - (lane & 1)), k, rb, vec_ok);
+        }
+        s = sn;
+        base = nbase;
+        lim = nlim;
+    }
+}
+
+// =====================================================================================================
 // Mixed precision: the gathered tile in bf16 (64-byte rows), fp32 pairs and fp32 accumulation.
 //
 // The fp32 kernels above sit on the shared-memory operand bandwidth (128 B per non-zero at 128 B/clk/SM: ncu 1.03
@@ -619,6 +742,56 @@ __global__ void __launch_bounds__(256) sell_fill_parity_kernel(const int64_t* __
                 ++outpos;
             }
         }
+        if (outpos & 1) {
+            dst[base + (int64_t)(outpos >> 1) * 32 + lane] = make_int4(hold.x, hold.y, 0, 0);
+            ++outpos;
+        }
+        for (int jj = outpos >> 1; jj < L2; ++jj) dst[base + (int64_t)jj * 32 + lane] = make_int4(0, 0, 0, 0);
+    }
+}
+
+// Residue-ordered variant for sell32r_pass_kernel (HEIGHT = 32, lane = row): at step j the lane emits a non-zero whose
+// tile row satisfies (row mod 4) == (lane / 2 + j) mod 4 if its row still has one (in original order within the
+// class), else the next one of the class with the most left.  off = tile row * 128.
+__global__ void __launch_bounds__(256) sell_fill_residue_kernel(const int64_t* __restrict__ ptr,
+                                                                const int2* __restrict__ src,
+                                                                const int64_t* __restrict__ slice_rows,
+                                                                const int64_t* __restrict__ slice_ptr, int64_t nslices,
+                                                                int4* __restrict__ dst) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t s = warp0; s < nslices; s += nwarp) {
+        const int64_t base = slice_ptr[s];
+        const int L2 = (int)((slice_ptr[s + 1] - base) >> 5);
+        const int64_t row = slice_rows[s * 32 + lane];
+        int64_t beg = 0;
+        int len = 0;
+        if (row >= 0) {
+            beg = ptr[row];
+            len = (int)(ptr[row + 1] - beg);
+        }
+        int left[4] = {0, 0, 0, 0}, cur[4] = {0, 0, 0, 0};
+        for (int t = 0; t < len; ++t) ++left[(src[beg + t].x >> 7) & 3];
+        int2 hold = make_int2(0, 0);
+        for (int j = 0; j < len; ++j) {
+            int c = ((lane >> 1) + j) & 3;
+            if (left[c] == 0) {
+                int best = 0;
+#pragma unroll
+                for (int q = 1; q < 4; ++q)
+                    if (left[q] > left[best]) best = q;
+                c = best;
+            }
+            int t = cur[c];
+            while (((src[beg + t].x >> 7) & 3) != c) ++t;  // next non-zero of class c (left[c] > 0 guarantees one)
+            const int2 a = src[beg + t];
+            cur[c] = t + 1;
+            --left[c];
+            if (j & 1) dst[base + (int64_t)(j >> 1) * 32 + lane] = make_int4(hold.x, hold.y, a.x, a.y);
+            else hold = a;
+        }
+        int outpos = len;
         if (outpos & 1) {
             dst[base + (int64_t)(outpos >> 1) * 32 + lane] = make_int4(hold.x, hold.y, 0, 0);
             ++outpos;

@@ -368,7 +368,7 @@ def test_wide_tile_passes_match_plain_passes(dev, k):
 
 
 @pytest.mark.parametrize("k,height", [(3, 32), (20, 32), (30, 32), (32, 32), (20, 8), (30, 8), (32, 8), (33, 8), (40, 8),
-                                      (44, 8), (48, 8), (50, 8), (64, 8)])
+                                      (33, 33), (36, 33), (37, 33), (40, 33), (44, 8), (48, 8), (50, 8), (64, 8)])
 @pytest.mark.parametrize("budget_rows", [37, 100000])
 def test_sell_passes_match_numpy_and_row_ordered_passes(dev, k, height, budget_rows):
     """inmf_sell_pass_f32 (rows sorted by length, slices of 8 rows, 4 lanes per row) against numpy and against the
@@ -380,9 +380,10 @@ def test_sell_passes_match_numpy_and_row_ordered_passes(dev, k, height, budget_r
     mats[0] = sps.csr_matrix(mats[0].multiply(np.arange(mats[0].shape[0])[:, None] % 7 != 0))  # empty rows
     mats[1] = sps.csr_matrix(mats[1].multiply(np.arange(130)[None, :] % 5 != 0))               # empty columns
     kp = max(32, (k + 3) // 4 * 4)
-    old = (blocked.SMEM_BUDGET, blocked.SELL, blocked.SELL_HEIGHT_KP32)
+    old = (blocked.SMEM_BUDGET, blocked.SELL, blocked.SELL_HEIGHT_KP32, blocked.SELL_HEIGHT_KP40)
     blocked.SMEM_BUDGET = min(old[0], budget_rows * blocked.smem_row_bytes(kp, 4))
     blocked.SELL_HEIGHT_KP32 = height
+    blocked.SELL_HEIGHT_KP40 = height
     res = {}
     try:
         for sell in (False, True):
@@ -403,7 +404,7 @@ def test_sell_passes_match_numpy_and_row_ordered_passes(dev, k, height, budget_r
             objs = [float(eng.initial_objective())] + [float(eng.als_iteration(warm=i > 0).item()) for i in range(3)]
             res[sell] = (St, HtH, R, objs, eng.H.clone())
     finally:
-        blocked.SMEM_BUDGET, blocked.SELL, blocked.SELL_HEIGHT_KP32 = old
+        blocked.SMEM_BUDGET, blocked.SELL, blocked.SELL_HEIGHT_KP32, blocked.SELL_HEIGHT_KP40 = old
     St, HtH, R, objs, Hf = res[True]
     off = 0
     for i in range(len(mats)):
