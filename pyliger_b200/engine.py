@@ -249,6 +249,32 @@ class InmfEngine(object):
             self._alloc()
 
     # ------------------------------------------------------------------ buffers
+    # Debug aid (compute-sanitizer is not available on every pool): guard_elems > 0 brackets every buffer the kernels
+    # write with bands of a sentinel value; check_guards() reports the buffers whose bands were touched.
+    guard_elems = 0
+    _GUARD = {torch.float32: 7.25e33, torch.float64: 7.25e33, torch.int64: 0x5A5A5A5A5A5A5A5A, torch.int16: 0x5A5A}
+
+    def _zeros(self, *shape, dtype=None, name=None):
+        dtype = self.dtype if dtype is None else dtype
+        ge = int(self.guard_elems)
+        if not ge:
+            return torch.zeros(*shape, dtype=dtype, device=self.device)
+        n = int(np.prod(shape))
+        raw = torch.full((n + 2 * ge,), self._GUARD[dtype], dtype=dtype, device=self.device)
+        raw[ge:ge + n] = 0
+        self.__dict__.setdefault("_guards", []).append((name or "buffer%d" % len(self.__dict__.get("_guards", [])),
+                                                        raw, ge, n))
+        return raw[ge:ge + n].view(*shape)
+
+    def check_guards(self):
+        """Names of the guarded buffers with a modified band (empty list = no out-of-bounds write seen)."""
+        bad = []
+        for name, raw, ge, n in self.__dict__.get("_guards", []):
+            ref = torch.full((ge,), self._GUARD[raw.dtype], dtype=raw.dtype, device=raw.device)
+            if not (torch.equal(raw[:ge], ref) and torch.equal(raw[ge + n:], ref)):
+                bad.append(name)
+        return bad
+
     def _alloc(self):
         X, k, dev, dt = self.X, self.k, self.device, self.dtype
         N, g = X.N, X.g
@@ -259,32 +285,32 @@ class InmfEngine(object):
         if dt == torch.float32 and self.use_blocked:
             self.ldm = max(32, self.ldm)
         f64 = torch.float64
-        z = lambda *shape, dtype=dt: torch.zeros(*shape, dtype=dtype, device=dev)
-        self.Wt = z(g, k)
+        z = self._zeros
+        self.Wt = z(g, k, name="Wt")
         # stacked [previous datasets (online scenario 2) | current datasets]
-        self.Vt_all = z(self.n_prev + N, g, k)
+        self.Vt_all = z(self.n_prev + N, g, k, name="Vt")
         self.Vt = self.Vt_all[self.n_prev:]
-        self.H = z(max(X.n_own_total, 1), self.ldm)  # leading dimension ldm: pad columns stay zero
-        self.Mt = z(N, g, self.ldm)
-        self.G = z(N, k, k, dtype=f64)
-        self.Gwv = z(N, k, k, dtype=f64)
-        self.Gvv = z(N, k, k, dtype=f64)
-        self.St = z(N, g, k)
-        self.HtH = z(N, k, k, dtype=f64)
-        self.Rv = z(N, g, k)
-        self.Rw = z(g, k)
-        self.Gv = z(N, k, k, dtype=f64)
-        self.Gw = z(1, k, k, dtype=f64)
+        self.H = z(max(X.n_own_total, 1), self.ldm, name="H")  # leading dimension ldm: pad columns stay zero
+        self.Mt = z(N, g, self.ldm, name="Mt")
+        self.G = z(N, k, k, dtype=f64, name="G")
+        self.Gwv = z(N, k, k, dtype=f64, name="Gwv")
+        self.Gvv = z(N, k, k, dtype=f64, name="Gvv")
+        self.St = z(N, g, k, name="St")
+        self.HtH = z(N, k, k, dtype=f64, name="HtH")
+        self.Rv = z(N, g, k, name="Rv")
+        self.Rw = z(g, k, name="Rw")
+        self.Gv = z(N, k, k, dtype=f64, name="Gv")
+        self.Gw = z(1, k, k, dtype=f64, name="Gw")
         # BPP workspaces (G^-1 + the half-warp solver's deferral lists), one per solve shape
         self.ws_H = _lib.bpp_workspace(max(max(X.n_own) if N else 0, 1), max(N, 1), k, dev)
         self.ws_V = _lib.bpp_workspace(g, max(N, 1), k, dev)
         self.ws_W = _lib.bpp_workspace(g, 1, k, dev)
-        self.xnorm2 = z(N, dtype=f64)
-        self.obj = z(1, dtype=f64)
-        self.bpp_stats = torch.zeros(3, 8, dtype=torch.int64, device=dev)  # rows: H, V, W solves
-        self.mask_H = torch.zeros(max(X.n_own_total, 1), dtype=torch.int64, device=dev)
-        self.mask_V = torch.zeros(N * g, dtype=torch.int64, device=dev)
-        self.mask_W = torch.zeros(g, dtype=torch.int64, device=dev)
+        self.xnorm2 = z(N, dtype=f64, name="xnorm2")
+        self.obj = z(1, dtype=f64, name="obj")
+        self.bpp_stats = z(3, 8, dtype=torch.int64, name="bpp_stats")  # rows: H, V, W solves
+        self.mask_H = z(max(X.n_own_total, 1), dtype=torch.int64, name="mask_H")
+        self.mask_V = z(N * g, dtype=torch.int64, name="mask_V")
+        self.mask_W = z(g, dtype=torch.int64, name="mask_W")
         full = np.zeros((N + 1, 4), dtype=np.int64)
         full[:, 0] = X.own_off
         full[:N, 1] = X.row_base[:N]
@@ -312,10 +338,10 @@ class InmfEngine(object):
             sms = torch.cuda.get_device_properties(dev).multi_processor_count
             if self.mixed:  # bf16 tiles: 64-byte rows, parity-ordered slices of 32 rows
                 self.pass1 = blocked.build_sell(blocked.build_pass1(X, 32, 2, sms), 32, height=-32)
-                self.Mt16 = torch.empty(N * g, 32, dtype=torch.int16, device=dev)
+                self.Mt16 = z(N * g, 32, dtype=torch.int16, name="Mt16")
                 if self.need_stats:
                     self.pass2 = blocked.build_sell(blocked.build_pass2(X, 32, 2, sms), 32, height=-32)
-                    self.H16 = torch.empty(max(X.n_own_total, 1), 32, dtype=torch.int16, device=dev)
+                    self.H16 = z(max(X.n_own_total, 1), 32, dtype=torch.int16, name="H16")
             elif not self.use_tc:
                 sell = blocked.sell_applies(self.ldm, esize)
                 self.pass1 = blocked.build_pass1(X, self.ldm, esize, sms)
@@ -513,7 +539,7 @@ class InmfEngine(object):
         """One HALS sweep over H in place (iNMF_HALS, _utilities.py:132-148): right-hand sides by pass 1 into a scratch
         buffer, then the per-cell Gauss-Seidel sweep.  Requires prep() of the current W, V."""
         if getattr(self, "R_hals", None) is None:
-            self.R_hals = torch.zeros_like(self.H)
+            self.R_hals = self._zeros(*self.H.shape, name="R_hals")
         self.rhs_H(out=self.R_hals)
         if self.max_rows_full > 0:
             _lib.call("inmf_hals_h", self.sfx, self.G, self.R_hals, self.ldm, self.H, self.ldm, self.seg_full_off, self.N,
@@ -683,7 +709,7 @@ class InmfEngine(object):
         if self._begun:
             return
         if self.H_alt is None:
-            self.H_alt = torch.zeros_like(self.H)
+            self.H_alt = self._zeros(*self.H.shape, name="H_alt")
             self._clean_ptr = self.H_alt.data_ptr()
         self.H, self.H_alt = self.H_alt, self.H
         with _Range("inmf.pass1_rhs_H"):
@@ -862,18 +888,19 @@ class InmfEngine(object):
         N, g, k, dev, dt = self.N, self.g, self.k, self.device, self.dtype
         nall = self.n_prev + N
         f64 = torch.float64
-        self.A_all = torch.zeros(nall, k, k, dtype=f64, device=dev)
-        self.B_all = torch.zeros(nall, g, k, dtype=dt, device=dev)
+        z = self._zeros
+        self.A_all = z(nall, k, k, dtype=f64, name="A")
+        self.B_all = z(nall, g, k, name="B")
         self.A = self.A_all[self.n_prev:]
         self.B = self.B_all[self.n_prev:]
-        self.A_old = torch.zeros(N, k, k, dtype=f64, device=dev)
-        self.B_old = torch.zeros(N, g, k, dtype=dt, device=dev)
-        self.HHt = torch.zeros(N, k, k, dtype=f64, device=dev)
-        self.XHt = torch.zeros(N, g, k, dtype=dt, device=dev)
+        self.A_old = z(N, k, k, dtype=f64, name="A_old")
+        self.B_old = z(N, g, k, name="B_old")
+        self.HHt = z(N, k, k, dtype=f64, name="HHt")
+        self.XHt = z(N, g, k, name="XHt")
         self.mbs = [int(m) for m in miniBatch_sizes]
         self.sub = [shard_bounds(m, self.rank, self.world) for m in self.mbs]  # this rank's part of a batch
         self.max_sub = max(hi - lo for lo, hi in self.sub)
-        self.H_mb = torch.zeros(max(sum(hi - lo for lo, hi in self.sub), 1), self.ldm, dtype=dt, device=dev)
+        self.H_mb = z(max(sum(hi - lo for lo, hi in self.sub), 1), self.ldm, name="H_mb")
         self.win = None  # blocked pass-1 copy over all resident cells for the mini-batch windows
         self.inv_mb = torch.tensor([1.0 / m for m in self.mbs], dtype=f64, device=dev)
 

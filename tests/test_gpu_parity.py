@@ -659,3 +659,37 @@ def test_graphed_iterations_equal_eager_iterations(dtype):
         np.testing.assert_allclose(a[0], b[0], rtol=tol)
         assert relerr(a[2], b[2]) < (1e-10 if dtype == "float64" else 1e-3)
         assert all(relerr(x, y) < (1e-10 if dtype == "float64" else 1e-3) for x, y in zip(a[1], b[1]))
+
+
+@pytest.mark.parametrize("dtype,k,det", [("float64", 12, False), ("float32", 12, False), ("float32", 36, False),
+                                         ("float32", 50, False), ("mixed", 30, False), ("float32", 30, True)])
+def test_kernels_write_inside_their_buffers(monkeypatch, dtype, k, det):
+    """Every buffer the engine hands to a kernel is bracketed by sentinel bands (InmfEngine.guard_elems): after
+    optimize_ALS, iNMF_HALS and online_iNMF with small tiles (several gene / cell blocks, ragged last slices) no band
+    has been written.  (Stands in for compute-sanitizer memcheck, which is not available on the GPU pool.)"""
+    from pyliger_b200 import blocked, iNMF_HALS, online_iNMF, optimize_ALS
+    from pyliger_b200.engine import InmfEngine
+    from pyliger_b200.synth import make_datasets
+    engines = []
+    orig = InmfEngine._alloc
+
+    def recording_alloc(self):
+        engines.append(self)
+        return orig(self)
+    monkeypatch.setattr(InmfEngine, "_alloc", recording_alloc)
+    monkeypatch.setattr(InmfEngine, "guard_elems", 256)
+    kp = max(32, (k + 3) // 4 * 4)
+    monkeypatch.setattr(blocked, "SMEM_BUDGET", min(blocked.SMEM_BUDGET, 200 * blocked.smem_row_bytes(kp, 4)))
+    mats = make_datasets([1333, 1071, 517], 411, k, density=0.12, seed0=3900 + k)
+    optimize_ALS(_liger(mats), k, 5.0, 1e-6, 5, rand_seed=1, dtype=dtype, deterministic=det, progress=False)
+    if dtype != "mixed" and not det:
+        iNMF_HALS(_liger(mats), k, max_iters=4, rand_seed=1, dtype=dtype, verbose=False)
+        online_iNMF(_liger(mats), k=k, miniBatch_size=600, max_epochs=2, rand_seed=1, dtype=dtype, verbose=False)
+    assert engines and all(e.__dict__.get("_guards") for e in engines)
+    for e in engines:
+        assert e.check_guards() == []
+    # the check itself sees a stray write
+    e = engines[0]
+    name, raw, ge, n = e._guards[0]
+    raw[ge + n] = 0
+    assert e.check_guards() == [name]

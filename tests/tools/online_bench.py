@@ -107,7 +107,13 @@ def main():
             it = 5 + rep
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(7)]
             ev[0].record(); eng.prep()
-            ev[1].record(); eng.rhs_H(seg_desc=plan[it], max_rows=eng.max_sub, out=eng.H_mb)
+            ev[1].record()
+            if eng.win is not None:  # the tiled window pass the real step uses
+                bp, work, counts = eng.win
+                eng.H_mb.zero_()
+                eng._blocked(bp, work[it], int(counts[it]), eng.Mt, eng.H_mb, eng.ldm, None)
+            else:
+                eng.rhs_H(seg_desc=plan[it], max_rows=eng.max_sub, out=eng.H_mb)
             ev[2].record(); eng.bpp_H(seg_desc=plan[it], max_rows=eng.max_sub, out=eng.H_mb)
             ev[3].record(); eng.stats(seg_desc=plan[it], max_rows=eng.max_sub, H=eng.H_mb, St=eng.XHt, HtH=eng.HHt)
             ev[4].record()
