@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(1024, 1)
 blocked_spmm_kernel(const int64_t* __restrict__ work, const int64_t* __restrict__ ptr,
                     const typename PairTraits<T>::Pair* __restrict__ pairs, const T* __restrict__ dense, int KP,
                     T* __restrict__ out, int64_t ldo, int k, double* __restrict__ gram_out) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
     T* tile = reinterpret_cast<T*>(smem_raw + 128);
     const int64_t* wd = work + (size_t)blockIdx.x * INMF_WORK_FIELDS;
@@ -420,7 +420,7 @@ blocked_split_kernel(const int64_t* __restrict__ work, const int64_t* __restrict
                      const float* __restrict__ dense, int KP, float* __restrict__ out, int64_t ldo, int k,
                      int max_tile_rows, double* __restrict__ gram_out) {
     constexpr int RS = 8 * RL;  // remainder floats per row in shared memory
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
     float* tmain = reinterpret_cast<float*>(smem_raw + 128);
     float* trem = tmain + (size_t)max_tile_rows * 32;
@@ -596,7 +596,7 @@ blocked_wide_kernel(const int64_t* __restrict__ work, const int64_t* __restrict_
                     const float* __restrict__ dense, float* __restrict__ out, int64_t ldo, int k,
                     double* __restrict__ gram_out) {
     constexpr int KP = 32;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
     float* tile = reinterpret_cast<float*>(smem_raw + 128);
     const int64_t* wd = work + (size_t)blockIdx.x * INMF_WORK_FIELDS;

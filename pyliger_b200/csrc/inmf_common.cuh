@@ -8,6 +8,21 @@
 
 #define INMF_FULL_MASK 0xffffffffu
 
+// Checked build (python -m pyliger_b200.build -DINMF_CHECKED): device-side bounds checks on the data-dependent
+// addresses of the gather kernels and the work lists; a failed check prints its location and traps the kernel.
+#ifdef INMF_CHECKED
+#define INMF_CHECK(cond)                                                                          \
+    do {                                                                                          \
+        if (!(cond)) {                                                                            \
+            printf("INMF_CHECK failed: %s (%s:%d) block %d thread %d\n", #cond, __FILE__, __LINE__, \
+                   (int)blockIdx.x, (int)threadIdx.x);                                            \
+            __trap();                                                                             \
+        }                                                                                         \
+    } while (0)
+#else
+#define INMF_CHECK(cond) ((void)0)
+#endif
+
 extern thread_local char g_inmf_err[512];
 
 #define INMF_CUDA_CHECK(call)                                                                   \

@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(256) qn_max_factor_kernel(const double* __rest
 __global__ void __launch_bounds__(QN_KNN_THREADS) qn_knn_kernel(const double* __restrict__ H, int64_t ld, int64_t n,
                                                                 const int32_t* __restrict__ dims, int m, int K,
                                                                 int32_t* __restrict__ knn) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
     double* qs = reinterpret_cast<double*>(smem_raw);            // [m][QN_KNN_THREADS]  queries, factor-major
     double* cs = qs + (size_t)m * QN_KNN_THREADS;                // [QN_KNN_TILE][m]     candidates, point-major
     const int tid = threadIdx.x;
@@ -218,7 +218,7 @@ qn_align_kernel(const int64_t* __restrict__ group, double* Hk, int64_t ldk, cons
                 const int32_t* __restrict__ memb2, const int32_t* __restrict__ off2,
                 const int32_t* __restrict__ memb1, const int32_t* __restrict__ off1,
                 const int32_t* __restrict__ samp, int Q, int spow2) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
     double* s2 = reinterpret_cast<double*>(smem_raw);   // [spow2]
     double* s1 = s2 + spow2;                            // [spow2]
     double* q2 = s1 + spow2;                            // [Q + 1]

@@ -137,7 +137,7 @@ sell_pass_kernel(const int64_t* __restrict__ work, const int64_t* __restrict__ s
                  const int32_t* __restrict__ rowid, const int4* __restrict__ pairs, const float* __restrict__ dense,
                  int KP, float* __restrict__ out, int64_t ldo, int k, int max_tile_rows,
                  double* __restrict__ gram_out, int64_t part_stride, int64_t gram_part_stride) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
     int* next_slice = reinterpret_cast<int*>(smem_raw + 16);
     float* tmain = reinterpret_cast<float*>(smem_raw + 128);
@@ -231,14 +231,20 @@ sell_pass_kernel(const int64_t* __restrict__ work, const int64_t* __restrict__ s
             for (int t = 0; t < SELL_U; ++t) B[t] = (j + SELL_U + t < L2) ? sell_ld(p + (size_t)(j + SELL_U + t) * 8) : z4;
 #pragma unroll
             for (int t = 0; t < SELL_U; ++t)
-                if (j + t < L2) sell_consume<REM>(A[t], tA, tB, tR, tR2, c);
+                if (j + t < L2) {
+                    INMF_CHECK((uint32_t)A[t].x < (uint32_t)tile_rows * 128u && (uint32_t)A[t].z < (uint32_t)tile_rows * 128u);
+                    sell_consume<REM>(A[t], tA, tB, tR, tR2, c);
+                }
             j += SELL_U;
             if (j >= L2) break;
 #pragma unroll
             for (int t = 0; t < SELL_U; ++t) A[t] = (j + SELL_U + t < L2) ? sell_ld(p + (size_t)(j + SELL_U + t) * 8) : z4;
 #pragma unroll
             for (int t = 0; t < SELL_U; ++t)
-                if (j + t < L2) sell_consume<REM>(B[t], tA, tB, tR, tR2, c);
+                if (j + t < L2) {
+                    INMF_CHECK((uint32_t)B[t].x < (uint32_t)tile_rows * 128u && (uint32_t)B[t].z < (uint32_t)tile_rows * 128u);
+                    sell_consume<REM>(B[t], tA, tB, tR, tR2, c);
+                }
             j += SELL_U;
         }
         // next slice (dynamic, longest first): fetch before the output so the latencies overlap
@@ -300,7 +306,7 @@ sell32_pass_kernel(const int64_t* __restrict__ work, const int64_t* __restrict__
                    const int32_t* __restrict__ rowid, const int4* __restrict__ pairs, const float* __restrict__ dense,
                    float* __restrict__ out, int64_t ldo, int k, double* __restrict__ gram_out, int64_t part_stride,
                    int64_t gram_part_stride) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
     int* next_slice = reinterpret_cast<int*>(smem_raw + 16);
     float* tile = reinterpret_cast<float*>(smem_raw + 128);
@@ -369,6 +375,7 @@ sell32_pass_kernel(const int64_t* __restrict__ work, const int64_t* __restrict__
             for (int h = 0; h < 4; ++h) {
                 const int off = h == 0 ? A.x : h == 1 ? A.z : h == 2 ? B.x : B.z;
                 const float v = __int_as_float(h == 0 ? A.y : h == 1 ? A.w : h == 2 ? B.y : B.w);
+                INMF_CHECK((uint32_t)off < (uint32_t)tile_rows * 128u && (off & 127) == 0);
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
                     float m[4];
@@ -416,7 +423,7 @@ sell32r_pass_kernel(const int64_t* __restrict__ work, const int64_t* __restrict_
                     const int32_t* __restrict__ rowid, const int4* __restrict__ pairs, const float* __restrict__ dense,
                     int KP, float* __restrict__ out, int64_t ldo, int k, int max_tile_rows,
                     double* __restrict__ gram_out, int64_t part_stride, int64_t gram_part_stride) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
     int* next_slice = reinterpret_cast<int*>(smem_raw + 16);
     float* tmain = reinterpret_cast<float*>(smem_raw + 128);
@@ -484,6 +491,7 @@ sell32r_pass_kernel(const int64_t* __restrict__ work, const int64_t* __restrict_
             for (int h = 0; h < 2; ++h) {
                 const int off = h == 0 ? A.x : A.z;
                 const float v = __int_as_float(h == 0 ? A.y : A.w);
+                INMF_CHECK((uint32_t)off < (uint32_t)tile_rows * 128u && (off & 127) == 0);
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
                     float m[4];
@@ -543,7 +551,7 @@ __global__ void __launch_bounds__(SELL32_THREADS, 1)
 sell32h_pass_kernel(const int64_t* __restrict__ work, const int64_t* __restrict__ slice_ptr,
                     const int32_t* __restrict__ rowid, const int4* __restrict__ pairs,
                     const uint16_t* __restrict__ dense, float* __restrict__ out, int64_t ldo, int k) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
     int* next_slice = reinterpret_cast<int*>(smem_raw + 16);
     unsigned char* tile = smem_raw + 128;
@@ -601,6 +609,7 @@ sell32h_pass_kernel(const int64_t* __restrict__ work, const int64_t* __restrict_
             for (int h = 0; h < 4; ++h) {
                 const int off = h == 0 ? A.x : h == 1 ? A.z : h == 2 ? B.x : B.z;
                 const float v = __int_as_float(h == 0 ? A.y : h == 1 ? A.w : h == 2 ? B.y : B.w);
+                INMF_CHECK((uint32_t)off < (uint32_t)tile_rows * 64u && (off & 63) == 0);
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     uint32_t m[4];

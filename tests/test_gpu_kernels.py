@@ -160,6 +160,44 @@ def test_update_ab_kat6(dev, golden_online):
     np.testing.assert_array_equal(A[0].cpu().numpy(), [[1e-15, 0], [0, 1e-15]])
 
 
+@pytest.mark.parametrize("N,k,n_prev,n_inner", [(1, 5, 0, 1), (1, 40, 0, 2), (2, 20, 0, 1), (3, 33, 1, 1), (4, 30, 0, 1),
+                                                (5, 64, 2, 2), (8, 40, 0, 1), (8, 12, 3, 1), (9, 40, 0, 1), (13, 17, 4, 1),
+                                                (20, 24, 0, 1), (8, 64, 0, 1), (2, 64, 0, 1)])
+@pytest.mark.parametrize("dtype,tol", [("float64", 1e-10), ("float32", 2e-4)])
+def test_hals_sweeps_all_kernel_shapes_vs_oracle(dev, N, k, n_prev, n_inner, dtype, tol):
+    """inmf_hals picks its kernel by the number of current datasets and factors (lane groups per dataset for <= 8
+    current datasets, column-per-lane forms beyond); every form against the oracle's _update_W_HALS / _update_V_HALS
+    (_utilities.py:102-129), with previous datasets (scenario 2) and repeated inner iterations."""
+    from oracle import inmf_oracle as orc
+    from pyliger_b200 import _lib
+    from pyliger_b200.engine import _stream, resolve_dtype
+    rng = np.random.RandomState(100 * N + k)
+    g = 301
+    nall = N
+    Hs = [rng.rand(3 * k + 7, k) * (rng.rand(3 * k + 7, k) < 0.6) for _ in range(nall)]
+    A = np.stack([h.T @ h / len(h) for h in Hs])
+    for i in range(nall):
+        A[i][np.diag_indices(k)] += 1e-3
+    B = rng.rand(nall, g, k)
+    W0 = rng.rand(g, k)
+    V0 = rng.rand(nall, g, k) * (rng.rand(nall, g, k) < 0.7)
+    W, V = W0.copy(), [v.copy() for v in V0]
+    for _ in range(n_inner):  # _online_iNMF.py:444-460: W over all datasets, V over the current ones
+        W = orc.hals_W(list(A), list(B), W, V)
+        V[n_prev:] = orc.hals_V(list(A[n_prev:]), list(B[n_prev:]), W, V[n_prev:], 5.0)
+    dt = resolve_dtype(dtype)
+    sfx = "f64" if dt == torch.float64 else "f32"
+    Ad = torch.from_numpy(A).to(dev)
+    Bd = torch.from_numpy(B).to(dev, dt)
+    Wd = torch.from_numpy(W0).to(dev, dt)
+    Vd = torch.from_numpy(V0).to(dev, dt)
+    _lib.call("inmf_hals", sfx, Ad, Bd, Wd, Vd, 5.0, n_prev, nall, g, k, n_inner, _stream())
+    assert relerr(Wd.cpu().numpy(), W) < tol
+    assert relerr(Vd.cpu().numpy(), np.stack(V)) < tol
+    if n_prev:
+        np.testing.assert_array_equal(Vd[:n_prev].cpu().numpy(), torch.from_numpy(V0[:n_prev]).to(dt).numpy())
+
+
 @pytest.mark.parametrize("dtype,tol", [("float64", 1e-11), ("float32", 5e-5)])
 def test_hals_sweep_golden(dev, golden_online, dtype, tol):
     from pyliger_b200 import _lib
