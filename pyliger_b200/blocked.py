@@ -118,12 +118,13 @@ def _pack_pairs(idx_local, vals):
 
 
 class BlockedPass(object):
-    __slots__ = ("work", "nwork", "ptr", "pairs", "max_tile_rows", "split", "work_host")
+    __slots__ = ("work", "nwork", "ptr", "pairs", "max_tile_rows", "split", "work_host", "blocks")
 
 
 class SellPass(object):
     """Sliced form of a BlockedPass (csrc/sell.cuh): rows of every work item sorted by length, 8 per slice."""
-    __slots__ = ("work", "nwork", "slice_ptr", "rowid", "pairs4", "max_tile_rows", "nnz", "padded", "height", "nparts")
+    __slots__ = ("work", "nwork", "slice_ptr", "rowid", "pairs4", "max_tile_rows", "nnz", "padded", "height", "nparts",
+                 "work_host")
 
 
 SELL_HEIGHT_KP32 = 32  # slice height at kp == 32: 32 (one lane per row) or 8 (four lanes per row)
@@ -189,6 +190,7 @@ def build_sell(bp, kp, height=None):
     work[:, 5] = W[:, 6]
     work[:, 6] = W[:, 7]
     sp.nparts = int(W[:, 7].max()) + 1
+    sp.work_host = work
     sp.work = torch.from_numpy(work).to(dev)
     return sp
 
@@ -304,14 +306,18 @@ def build_pass1(X, kp, esize, n_sms):
     return bp
 
 
-def build_pass2(X, kp, esize, n_sms):
-    """Cell-blocked CSC over the owned cells."""
+def build_pass2(X, kp, esize, n_sms, cbs=None, chunks=None):
+    """Cell-blocked CSC over the owned cells.  ``cbs``: cells per block of every dataset (default: blocks sized to fill
+    whole waves of CTAs); ``chunks``: gene ranges per block (default: what fills the SMs once)."""
     dev = X.rowptr.device
     g, N = X.g, X.N
     cap = tile_cap_rows(kp, esize)
     n_tot = max(1, X.n_own_total)
-    nb = _wave_blocks(n_sms, X.n_own, cap)
-    cbs = [1 if b == 0 else -(-n // b) for n, b in zip(X.n_own, nb)]
+    if cbs is None:
+        nb = _wave_blocks(n_sms, X.n_own, cap)
+        cbs = [1 if b == 0 else -(-n // b) for n, b in zip(X.n_own, nb)]
+    else:
+        cbs = [max(1, min(int(c), cap)) for c in cbs]
     nb = [0 if n == 0 else -(-n // c) for n, c in zip(X.n_own, cbs)]
     blk_off = np.concatenate([[0], np.cumsum(nb)]).astype(np.int64)
     total_blocks = int(blk_off[-1])
@@ -338,17 +344,32 @@ def build_pass2(X, kp, esize, n_sms):
         idx_local = (local_row - cb * cbs_t[seg])[order]
         bp.pairs = _pack_pairs(idx_local * row_bytes(kp, esize), val[order])  # byte offset of the gathered tile row
         bp.ptr = ptr
-    chunks = max(1, n_sms // max(1, total_blocks))
-    per = -(-g // chunks)
-    work = []
-    for s in range(N):
-        for b in range(nb[s]):
-            rows_b = min(cbs[s], X.n_own[s] - b * cbs[s])
-            for ci, lo in enumerate(range(0, g, per)):
-                work.append([g * (int(blk_off[s]) + b), int(X.own_off[s]) + b * cbs[s], rows_b, lo, min(g, lo + per),
-                             s * g, s if ci == 0 else -1, b])
+    if chunks is None:
+        chunks = max(1, n_sms // max(1, total_blocks))
+    per = -(-g // max(1, int(chunks)))
+    glo = np.arange(0, g, per, dtype=np.int64)
+    nch = len(glo)
+    # items in (dataset, block, gene range) order: item index = (blk_off[s] + b) * nch + ci
+    blk_s = np.repeat(np.arange(N, dtype=np.int64), nb)
+    blk_b = np.arange(total_blocks, dtype=np.int64) - blk_off[:-1][blk_s] if total_blocks else np.zeros(0, np.int64)
+    n_own = np.asarray(X.n_own, dtype=np.int64)
+    cbs_a = np.asarray(cbs, dtype=np.int64)
+    own_off = np.asarray(X.own_off, dtype=np.int64)
+    work = np.zeros((total_blocks, nch, WORK_FIELDS), dtype=np.int64)
+    if total_blocks:
+        work[:, :, 0] = (g * np.arange(total_blocks, dtype=np.int64))[:, None]
+        work[:, :, 1] = (own_off[blk_s] + blk_b * cbs_a[blk_s])[:, None]
+        work[:, :, 2] = np.minimum(cbs_a[blk_s], n_own[blk_s] - blk_b * cbs_a[blk_s])[:, None]
+        work[:, :, 3] = glo[None, :]
+        work[:, :, 4] = np.minimum(g, glo + per)[None, :]
+        work[:, :, 5] = (blk_s * g)[:, None]
+        work[:, :, 6] = -1
+        work[:, 0, 6] = blk_s
+        work[:, :, 7] = blk_b[:, None]
+    work = work.reshape(total_blocks * nch, WORK_FIELDS)
     bp.nwork = len(work)
-    bp.work_host = np.asarray(work if work else [[0] * WORK_FIELDS], dtype=np.int64)
+    bp.work_host = np.ascontiguousarray(work) if len(work) else np.zeros((1, WORK_FIELDS), dtype=np.int64)
+    bp.blocks = (list(nb), list(cbs), blk_off, nch)
     bp.work = torch.from_numpy(bp.work_host).to(dev)
     bp.max_tile_rows = max(cbs) if cbs else 1
     return bp
@@ -540,3 +561,106 @@ def window_work(X, NB, gbs, plan, pieces):
     work[pad] = 0
     work[pad, 6] = -1
     return work, counts
+
+
+# ------------------------------------------------------------------------------------------------------
+# Mini-batch statistics of online_iNMF as a pass 2 over block-aligned windows
+# ------------------------------------------------------------------------------------------------------
+class _ResidentView(object):
+    pass
+
+
+def resident_view(X):
+    """``X`` (a DeviceCSR) with every resident row counted as owned: what build_pass2 needs to block the replicated
+    datasets of online_iNMF."""
+    v = _ResidentView()
+    v.N, v.g = X.N, X.g
+    v.rowptr, v.colidx, v.vals = X.rowptr, X.colidx, X.vals
+    v.bounds = list(X.bounds)
+    v.own = list(X.bounds)
+    v.n_local = list(X.n_local)
+    v.n_own = list(X.n_local)
+    v.row_base = X.row_base
+    v.own_off = X.row_base
+    v.n_total = X.n_total
+    v.n_own_total = X.n_total
+    return v
+
+
+def window_blocks(cnt, kp, esize):
+    """Cells per block for windows of ``cnt`` cells: the window size itself when its tile fits in shared memory
+    (a window then touches one block when it is aligned and two otherwise), else the smallest equal split that fits."""
+    cap = tile_cap_rows(kp, esize)
+    out = []
+    for c in cnt:
+        c = max(1, int(c))
+        m = -(-c // cap)
+        out.append(-(-c // m))
+    return out
+
+
+def window_stats_work(sell_work_host, blocks, plan, n_global):
+    """Per-step work lists of the sliced pass 2 over the cell blocks that the windows of ``plan`` touch.
+
+    ``blocks`` = BlockedPass.blocks of a build_pass2(..., cbs=...) over all resident cells; ``sell_work_host`` the work
+    array of its sliced form (one row per (block, gene range)).  A window of dataset i is the rows (win_start + q) % n_i,
+    q < count_i: a tail run [start, ...) and, when it wraps, a head run [0, ...).  Every touched block gets a slot of
+    cbs[i] rows in the tile buffer (tail blocks first, then head blocks; dataset i owns slots_i consecutive slots from
+    row region[i]); window row q goes to row ``place[t, out_off_i + q]`` of the buffer = the position of its cell inside
+    its block's slot; the other rows of the slots stay zero and so add nothing.  Built with array operations for all
+    steps at once.  Returns (work [T, items, 8], counts [T], place [T, total], region [N + 1]) or None when a window is
+    longer than its dataset or wraps onto its own first block (not worth a special case: the row kernels take those)."""
+    nb, cbs, blk_off, nch = blocks
+    T, N = plan.shape[0], plan.shape[1] - 1
+    out_off = plan[:, :, 0].astype(np.int64)
+    count = out_off[:, 1:] - out_off[:, :-1]                       # [T, N]
+    total = int(out_off[0, N]) if T else 0
+    cmax = count.max(axis=0) if T else np.zeros(N, np.int64)
+    slots = [(-(-int(cmax[i]) // cbs[i]) + 2) if (nb[i] and cmax[i]) else 0 for i in range(N)]
+    region = np.concatenate([[0], np.cumsum([slots[i] * cbs[i] for i in range(N)])]).astype(np.int64)
+    place = np.zeros((T, max(total, 1)), dtype=np.int64)
+    W3 = sell_work_host[:sum(nb) * nch].reshape(sum(nb), nch, WORK_FIELDS)
+    works, oks = [], []
+    for i in range(N):
+        if slots[i] == 0:
+            continue
+        n, cb, S = int(n_global[i]), int(cbs[i]), slots[i]
+        c = count[:, i]
+        if (c > n).any():
+            return None
+        start = plan[:, i, 2].astype(np.int64) % n
+        e1 = np.minimum(start + c, n)
+        tail = e1 - start
+        head = c - tail
+        b0 = start // cb
+        ntail = np.where(tail > 0, (e1 - 1) // cb - b0 + 1, 0)
+        nhead = np.where(head > 0, (head - 1) // cb + 1, 0)
+        if ((head > 0) & (nhead - 1 >= b0)).any() or (ntail + nhead > S).any():
+            return None
+        q = np.arange(int(cmax[i]), dtype=np.int64)[None, :]
+        pos = np.where(q < tail[:, None], (start - b0 * cb)[:, None] + q, (ntail * cb - tail)[:, None] + q) + region[i]
+        for t in np.unique(c):  # (all steps of a dataset have the same count in practice)
+            sel = np.nonzero(c == t)[0]
+            cols = out_off[sel, i][:, None] + np.arange(int(t), dtype=np.int64)[None, :]
+            place[sel[:, None], cols] = pos[sel, :int(t)]
+        j = np.arange(S, dtype=np.int64)[None, :]
+        blk = np.where(j < ntail[:, None], b0[:, None] + j, j - ntail[:, None])       # [T, S]
+        ok = (j < (ntail + nhead)[:, None]) & (c > 0)[:, None]
+        blk = np.where(ok, blk, 0)
+        w = W3[int(blk_off[i]) + blk].copy()                                          # [T, S, nch, 8]
+        w[..., 2] = (region[i] + j * cb)[:, :, None]     # dense_row0: the block's slot in the tile buffer
+        works.append(w.reshape(T, S * nch, WORK_FIELDS))
+        oks.append(np.repeat(ok, nch, axis=1))
+    if not works:
+        return (np.zeros((T, 1, WORK_FIELDS), dtype=np.int64), np.zeros(T, dtype=np.int64), place, region)
+    work = np.concatenate(works, axis=1)
+    ok = np.concatenate(oks, axis=1)
+    order = np.argsort(~ok, axis=1, kind="stable")
+    work = np.take_along_axis(work, order[:, :, None], axis=1)
+    counts = ok.sum(axis=1).astype(np.int64)
+    keep = int(counts.max()) if T else 0
+    work = np.ascontiguousarray(work[:, :max(keep, 1)])
+    pad = np.arange(work.shape[1])[None, :] >= counts[:, None]
+    work[pad] = 0
+    work[pad, 5] = -1
+    return work, counts, place, region

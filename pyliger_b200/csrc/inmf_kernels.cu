@@ -1247,11 +1247,11 @@ __device__ __forceinline__ void hals_ld_row(const T* __restrict__ p, T (&v)[SLOT
 }
 
 template <typename T, int SLOTS>
-struct HalsGroupedCfg {  // threads per CTA (two CTAs per SM) that leave ~5 register arrays of SLOTS values per lane
+struct HalsGroupedCfg {  // threads per CTA that leave ~5 register arrays of SLOTS values per lane
     static constexpr int WORDS = SLOTS * (int)(sizeof(T) / 4);
-    static constexpr int MAX_THREADS = WORDS <= 4 ? 576 : WORDS <= 8 ? 512 : WORDS <= 12 ? 448 : WORDS <= 16 ? 288
-                                       : WORDS <= 24 ? 224 : 160;
-    static constexpr int CTAS_PER_SM = 2;
+    static constexpr int MAX_THREADS = WORDS <= 8 ? 1024 : WORDS <= 12 ? 896 : WORDS <= 16 ? 576
+                                       : WORDS <= 24 ? 448 : 320;
+    static constexpr int CTAS_PER_SM = 1;  // one large CTA: the matrices are staged once per SM
 };
 
 template <typename T, int NS, int SLOTS>
@@ -1269,19 +1269,21 @@ hals_grouped_kernel(const double* __restrict__ A, const T* __restrict__ B, T* __
     T* inv_a = inv_sa + k;                               // [nsets][k]        1 / ((1 + lambda) A_i[j][j]); 0 for pad sets
     const T one_lam = (T)(1.0 + lambda);
     const int kk = k * k;
-    for (int e = threadIdx.x; e < nsets * k * KP; e += blockDim.x) {
-        const int i = e / (k * KP), rem = e - i * (k * KP), j = rem / KP, pos = rem - j * KP;
-        const int c = (pos % SLOTS) * LPD + pos / SLOTS;  // pos = sub * SLOTS + slot
-        Ap[(size_t)i * stride_a + j * KP + pos] = (i < nall && c < k) ? (T)A[(size_t)i * kk + j * k + c] : T(0);
+    for (int row = warp; row < nsets * k; row += nwarps) {  // rows of the A_i (zero rows for the pad datasets)
+        const int i = row / k, j = row - i * k;
+        for (int pos = lane; pos < KP; pos += 32) {
+            const int c = (pos % SLOTS) * LPD + pos / SLOTS;  // pos = sub * SLOTS + slot
+            Ap[(size_t)i * stride_a + j * KP + pos] = (i < nall && c < k) ? (T)A[(size_t)i * kk + j * k + c] : T(0);
+        }
     }
-    for (int e = threadIdx.x; e < k * KP; e += blockDim.x) {
-        const int j = e / KP, pos = e - j * KP;
-        const int c = (pos % SLOTS) * LPD + pos / SLOTS;
-        double acc = 0.0;
-        if (c < k)
-            for (int i = 0; i < nall; ++i) acc += A[(size_t)i * kk + j * k + c];
-        SAp[e] = (T)acc;
-    }
+    for (int j = warp; j < k; j += nwarps)
+        for (int pos = lane; pos < KP; pos += 32) {
+            const int c = (pos % SLOTS) * LPD + pos / SLOTS;
+            double acc = 0.0;
+            if (c < k)
+                for (int i = 0; i < nall; ++i) acc += A[(size_t)i * kk + j * k + c];
+            SAp[j * KP + pos] = (T)acc;
+        }
     for (int e = threadIdx.x; e < k; e += blockDim.x) {
         double acc = 0.0;
         for (int i = 0; i < nall; ++i) acc += A[(size_t)i * kk + e * k + e];

@@ -902,6 +902,7 @@ class InmfEngine(object):
         self.max_sub = max(hi - lo for lo, hi in self.sub)
         self.H_mb = z(max(sum(hi - lo for lo, hi in self.sub), 1), self.ldm, name="H_mb")
         self.win = None  # blocked pass-1 copy over all resident cells for the mini-batch windows
+        self.win2 = None  # sliced pass-2 copy in window-sized cell blocks for the mini-batch statistics
         self.inv_mb = torch.tensor([1.0 / m for m in self.mbs], dtype=f64, device=dev)
 
     def online_plan(self, total_iters):
@@ -917,7 +918,47 @@ class InmfEngine(object):
             pieces = max([pieces] + [-(-(hi - lo) // max(1, n)) for (lo, hi), n in zip(self.sub, self.X.n_global)])
             work, counts = blocked.window_work(self.X, NB, gbs, plan, pieces)
             self.win = (bp, torch.from_numpy(work).to(self.device), counts)
+            self._plan_window_stats(plan, sms)
         return torch.from_numpy(plan).to(self.device)
+
+    window_stats = True          # mini-batch statistics through the sliced pass 2 over block-aligned windows (fp32)
+    window_stats_max_bytes = 1 << 30
+
+    def _plan_window_stats(self, plan, sms):
+        """Cell-blocked sliced copy of the resident cells (blocks = mini-batch windows) + per-step work lists, so that
+        X_mb' H_mb and H_mb' H_mb of a mini-batch (_online_iNMF.py:563-601) are one gather pass with the window's H in
+        shared memory instead of k atomics per non-zero."""
+        self.win2 = None
+        if not (self.window_stats and self.dtype == torch.float32 and blocked.sell_applies(self.ldm, 4)):
+            return
+        cnt = [hi - lo for lo, hi in self.sub]
+        total = int(sum(cnt))
+        if total == 0 or plan.shape[0] * total * 8 > self.window_stats_max_bytes:
+            return
+        cbs = blocked.window_blocks(cnt, self.ldm, 4)
+        chunks = max(1, min(sms // max(1, self.N), self.g // 128))
+        view = blocked.resident_view(self.X)
+        bp2 = blocked.build_pass2(view, self.ldm, 4, sms, cbs=cbs, chunks=chunks)
+        sp2 = blocked.build_sell(bp2, self.ldm)
+        res = blocked.window_stats_work(sp2.work_host, bp2.blocks, plan, self.X.n_global)
+        del bp2
+        if res is None:
+            return
+        work, counts, place, region = res
+        dev = self.device
+        self.win2 = (sp2, torch.from_numpy(work).to(dev), counts, torch.from_numpy(place).to(dev), total,
+                     self._zeros(max(int(region[-1]), 1), self.ldm, name="H_tiles"))
+
+    def stats_window(self, step):
+        """XHt, HHt of mini-batch ``step`` (all-reduced) from H_mb through the block-aligned window pass."""
+        sp2, work, counts, place, total, Ht = self.win2
+        Ht.zero_()
+        Ht.index_copy_(0, place[step], self.H_mb[:total])
+        self.XHt.zero_()
+        self.HHt.zero_()
+        if int(counts[step]) > 0:
+            self._blocked(sp2, work[step], int(counts[step]), Ht, self.XHt, self.k, self.HHt)
+        self._allreduce(self.XHt, self.HHt)
 
     def online_step(self, seg_desc_t, scales, rollover, n_inner, step=None):
         """One mini-batch: H_mb by BPP, A/B update, HALS on W and V (_online_iNMF.py:416-460).
@@ -931,7 +972,10 @@ class InmfEngine(object):
             self.bpp_H(seg_desc=seg_desc_t, max_rows=self.max_sub, out=self.H_mb)
         else:
             self.solve_H(seg_desc=seg_desc_t, max_rows=self.max_sub, out=self.H_mb)
-        self.stats(seg_desc=seg_desc_t, max_rows=self.max_sub, H=self.H_mb, St=self.XHt, HtH=self.HHt)
+        if step is not None and getattr(self, "win2", None) is not None:
+            self.stats_window(step)
+        else:
+            self.stats(seg_desc=seg_desc_t, max_rows=self.max_sub, H=self.H_mb, St=self.XHt, HtH=self.HHt)
         if len(set(scales)) == 1:
             _lib.call("inmf_update_ab", self.sfx, self.A, self.A_old, self.B, self.B_old, self.HHt, self.XHt,
                       self.inv_mb, float(scales[0]), int(rollover), self.N, self.g, self.k, _stream())

@@ -693,3 +693,46 @@ def test_kernels_write_inside_their_buffers(monkeypatch, dtype, k, det):
     name, raw, ge, n = e._guards[0]
     raw[ge + n] = 0
     assert e.check_guards() == [name]
+
+
+@pytest.mark.parametrize("k,ns,mb,epochs", [(6, [333, 211], 97, 4), (36, [2100, 1300, 900], 1000, 3),
+                                            (20, [1200, 1200], 600, 2), (40, [2000, 9100], 5500, 2)])
+def test_online_window_statistics_equal_row_statistics(k, ns, mb, epochs):
+    """fp32 online_iNMF: the mini-batch statistics X_mb' H_mb, H_mb' H_mb through the block-aligned sliced pass
+    (InmfEngine.window_stats) against the per-row scatter kernel -- ragged windows that straddle two blocks, wrap around
+    the end of a dataset over several epochs, an aligned case (one block per window) and windows larger than a tile."""
+    from pyliger_b200 import online_iNMF
+    from pyliger_b200.engine import InmfEngine
+    from pyliger_b200.synth import make_datasets
+    mats = make_datasets(ns, 300, k, density=0.1, seed0=4100 + k)
+    res = {}
+    old = InmfEngine.window_stats
+    used = []
+    orig = InmfEngine.stats_window
+
+    def counting(self, step):
+        used.append(step)
+        return orig(self, step)
+    try:
+        InmfEngine.stats_window = counting
+        for flag in (True, False):
+            InmfEngine.window_stats = flag
+            lig = _liger(mats)
+            online_iNMF(lig, k=k, value_lambda=5.0, max_epochs=epochs, miniBatch_size=mb, rand_seed=3, dtype="float32",
+                        verbose=False)
+            res[flag] = (lig.W.copy(), [v.copy() for v in lig.V], [h.copy() for h in lig.H],
+                         [a.uns["A"].copy() for a in lig.adata_list], [a.varm["B"].copy() for a in lig.adata_list])
+            if flag:
+                assert used, "the window pass was not taken"
+                n_used = len(used)
+        assert len(used) == n_used
+    finally:
+        InmfEngine.window_stats = old
+        InmfEngine.stats_window = orig
+    a, b = res[True], res[False]
+    assert relerr(a[0], b[0]) < 2e-4
+    for i in range(len(ns)):
+        assert relerr(a[1][i], b[1][i]) < 2e-3
+        assert relerr(a[3][i], b[3][i]) < 1e-4
+        assert relerr(a[4][i], b[4][i]) < 1e-4
+        assert relerr(a[2][i], b[2][i]) < 5e-3
