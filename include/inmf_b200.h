@@ -165,6 +165,17 @@ int32_t inmf_sell_pass_f32(const int64_t* work, int32_t nwork, const int64_t* sl
                            int32_t k, int32_t max_tile_rows, double* gram_out, int64_t part_stride,
                            int64_t gram_part_stride, void* stream);
 
+/* Pass 2 fused with its all-reduce (multi-GPU, cells sharded over the ranks): out_mc / gram_out_mc are MULTICAST
+ * addresses of symmetric buffers bound on every rank (CUDA multicast object over the NVLink switch, e.g.
+ * torch.distributed._symmetric_memory handle.multicast_ptr + offset), same element layout as out / gram_out above.  Every
+ * partial sum is added with multimem.red: the switch performs the add on every rank's copy, so when all ranks' kernels
+ * have completed each copy holds the SUM over the ranks of X' H and H' H -- the statistics of _iNMF_ANLS.py:142-152 over
+ * all cells -- tile by tile while the pass computes, with no separate collective.  The caller orders the ranks: every
+ * copy is zeroed before any rank launches (one cross-rank barrier) and is read after all ranks have finished (another). */
+int32_t inmf_sell_pass_mc_f32(const int64_t* work, int32_t nwork, const int64_t* slice_ptr, const int32_t* rowid,
+                              const void* pairs4, int32_t height, const float* dense, int32_t kp, float* out_mc,
+                              int64_t ldo, int32_t k, int32_t max_tile_rows, double* gram_out_mc, void* stream);
+
 /* Deterministic (bit-reproducible) accumulation.  By default the passes add their per-tile partial sums into the
  * outputs with floating-point atomics, whose order depends on the CTA schedule.  With part_stride > 0 in
  * inmf_sell_pass_f32, `out` (and gram_out, gram_part_stride doubles apart) is an array of partial buffers: work item w

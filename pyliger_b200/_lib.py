@@ -37,7 +37,7 @@ _TYPED = {
 
 EXPORTED_SYMBOLS = ["inmf_version", "inmf_last_error", "inmf_launch_count", "inmf_note_graph_launches", "inmf_bpp_workspace_bytes", "inmf_tc_selftest",
                     "inmf_tc_relayout_f32", "inmf_tc_pass_f32", "inmf_tc_debug_buffer", "inmf_select_count", "inmf_mt19937_uniform", "inmf_blocked_split_f32", "inmf_blocked_wide_f32",
-                    "inmf_sell_pass_f32", "inmf_sell_fill_f32",
+                    "inmf_sell_pass_f32", "inmf_sell_pass_mc_f32", "inmf_sell_fill_f32",
                     "inmf_qn_max_factor", "inmf_qn_knn", "inmf_qn_vote", "inmf_qn_align",
                     "inmf_sell_pass_mixed", "inmf_to_bf16_rows", "inmf_to_bf16_gram", "inmf_set_deterministic"] + [
     "%s_%s" % (n, t) for n in _TYPED for t in ("f32", "f64")
@@ -81,6 +81,8 @@ def load():
     for name in ("inmf_blocked_split_f32", "inmf_blocked_wide_f32"):
         getattr(lib, name).restype = _I32
         getattr(lib, name).argtypes = _TYPED["inmf_blocked_spmm"]
+    lib.inmf_sell_pass_mc_f32.restype = _I32
+    lib.inmf_sell_pass_mc_f32.argtypes = [_PTR, _I32, _PTR, _PTR, _PTR, _I32, _PTR, _I32, _PTR, _I64, _I32, _I32, _PTR, _PTR]
     lib.inmf_sell_pass_f32.restype = _I32
     lib.inmf_sell_pass_f32.argtypes = [_PTR, _I32, _PTR, _PTR, _PTR, _I32, _PTR, _I32, _PTR, _I64, _I32, _I32, _PTR, _I64, _I64,
                                        _PTR]

@@ -380,7 +380,7 @@ __device__ __forceinline__ void warp_row_dot_split(const int2* __restrict__ pl0,
 // H'H of a split tile (columns < 32 in `tmain`, the others in `trem`), same blocking as tile_gram_accumulate.
 __device__ __forceinline__ void split_gram_accumulate(const float* __restrict__ tmain, const float* __restrict__ trem,
                                                       int rs, int rows, int k, double* __restrict__ out,
-                                                      bool plain = false) {
+                                                      int mode = INMF_GRAM_ATOMIC) {
     const int nb = (k + 3) >> 2;
     for (int blk = threadIdx.x; blk < nb * nb; blk += blockDim.x) {
         const int bi = blk / nb, bj = blk % nb;
@@ -407,7 +407,8 @@ __device__ __forceinline__ void split_gram_accumulate(const float* __restrict__ 
             for (int b = 0; b < 4; ++b) {
                 const int i = 4 * bi + a, j = 4 * bj + b;
                 if (i < k && j < k) {
-                    if (plain) out[(size_t)i * k + j] += (double)acc[a][b];
+                    if (mode == INMF_GRAM_PLAIN) out[(size_t)i * k + j] += (double)acc[a][b];
+                    else if (mode == INMF_GRAM_MULTICAST) mc_red_add_f64(&out[(size_t)i * k + j], (double)acc[a][b]);
                     else atomicAdd(&out[(size_t)i * k + j], (double)acc[a][b]);
                 }
             }

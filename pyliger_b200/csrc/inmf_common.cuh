@@ -135,11 +135,20 @@ __device__ __forceinline__ int64_t seg_row(const SegWin& w, int64_t j) {
 // =================================================================================================
 #define GRAM_TILE_ROWS 64
 
-// plain = true: `out` belongs to this CTA alone (a partial buffer of the deterministic mode): every entry is owned by one
-// thread, which adds to it without an atomic.
+// Sum into a MULTICAST address: the add is performed on the copy of every GPU bound to the multicast object (NVLink
+// switch reduction, PTX multimem.red); the caller provides the cross-GPU ordering (barriers around the kernel).
+__device__ __forceinline__ void mc_red_add_f64(double* p, double v) {
+    asm volatile("multimem.red.relaxed.sys.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+#define INMF_GRAM_ATOMIC 0
+#define INMF_GRAM_PLAIN 1
+#define INMF_GRAM_MULTICAST 2
+
+// mode = INMF_GRAM_PLAIN: `out` belongs to this CTA alone (a partial buffer of the deterministic mode): every entry is
+// owned by one thread, which adds to it without an atomic.  INMF_GRAM_MULTICAST: `out` is a multicast address.
 template <typename T>
 __device__ __forceinline__ void tile_gram_accumulate(const T* __restrict__ tile, int ldt, int rows, int k,
-                                                     double* __restrict__ out, double scale, bool plain = false) {
+                                                     double* __restrict__ out, double scale, int mode = INMF_GRAM_ATOMIC) {
     const int nb = (k + 3) >> 2;
     for (int blk = threadIdx.x; blk < nb * nb; blk += blockDim.x) {
         const int bi = blk / nb, bj = blk % nb;
@@ -167,7 +176,8 @@ __device__ __forceinline__ void tile_gram_accumulate(const T* __restrict__ tile,
             for (int b = 0; b < 4; ++b) {
                 const int i = 4 * bi + a, j = 4 * bj + b;
                 if (i < k && j < k) {
-                    if (plain) out[(size_t)i * k + j] += scale * (double)acc[a][b];
+                    if (mode == INMF_GRAM_PLAIN) out[(size_t)i * k + j] += scale * (double)acc[a][b];
+                    else if (mode == INMF_GRAM_MULTICAST) mc_red_add_f64(&out[(size_t)i * k + j], scale * (double)acc[a][b]);
                     else atomicAdd(&out[(size_t)i * k + j], scale * (double)acc[a][b]);
                 }
             }

@@ -1768,25 +1768,26 @@ extern "C" int32_t inmf_blocked_wide_f32(const int64_t* work, int32_t nwork, con
 // =================================================================================================
 // Sliced (SELL-8) passes (sell.cuh)
 // =================================================================================================
-template <int REM>
+template <int REM, bool MC>
 static int32_t sell_pass_one(const int64_t* work, int32_t nwork, const int64_t* slice_ptr, const int32_t* rowid,
                              const void* pairs4, const float* dense, int32_t kp, float* out, int64_t ldo, int32_t k,
                              int32_t max_tile_rows, double* gram_out, int64_t part_stride, int64_t gram_part_stride,
                              void* stream) {
     const size_t smem = 128 + (size_t)max_tile_rows * (32 + REM) * sizeof(float);
     INMF_REQUIRE(smem <= 227 * 1024, "dense tile does not fit in shared memory");
-    INMF_OPTIN_SMEM((sell_pass_kernel<REM>), 227 * 1024);
-    sell_pass_kernel<REM><<<(unsigned)nwork, 1024, smem, (cudaStream_t)stream>>>(
+    INMF_OPTIN_SMEM((sell_pass_kernel<REM, MC>), 227 * 1024);
+    sell_pass_kernel<REM, MC><<<(unsigned)nwork, 1024, smem, (cudaStream_t)stream>>>(
         work, slice_ptr, rowid, reinterpret_cast<const int4*>(pairs4), dense, kp, out, ldo, k, max_tile_rows, gram_out,
         part_stride, gram_part_stride);
     INMF_LAUNCH_CHECK();
     return 0;
 }
-extern "C" int32_t inmf_sell_pass_f32(const int64_t* work, int32_t nwork, const int64_t* slice_ptr,
-                                      const int32_t* rowid, const void* pairs4, int32_t height, const float* dense,
-                                      int32_t kp, float* out, int64_t ldo, int32_t k, int32_t max_tile_rows,
-                                      double* gram_out, int64_t part_stride, int64_t gram_part_stride, void* stream) {
-    INMF_REQUIRE(part_stride >= 0 && gram_part_stride >= 0, "partial strides must be >= 0");
+// MC: out / gram_out are multicast addresses (inmf_sell_pass_mc_f32)
+template <bool MC>
+static int32_t sell_pass_dispatch(const int64_t* work, int32_t nwork, const int64_t* slice_ptr, const int32_t* rowid,
+                                  const void* pairs4, int32_t height, const float* dense, int32_t kp, float* out,
+                                  int64_t ldo, int32_t k, int32_t max_tile_rows, double* gram_out, int64_t part_stride,
+                                  int64_t gram_part_stride, void* stream) {
     INMF_REQUIRE(k >= 1 && k <= INMF_MAX_K, "k must be in [1, 64]");
     INMF_REQUIRE(kp >= 32 && kp >= k && kp % 4 == 0 && kp <= 64, "kp must be a multiple of 4 in [max(k, 32), 64]");
     INMF_REQUIRE(ldo >= k, "ldo must be >= k");
@@ -1797,8 +1798,8 @@ extern "C" int32_t inmf_sell_pass_f32(const int64_t* work, int32_t nwork, const 
     if (height == 33) {
         const size_t smem = 128 + (size_t)max_tile_rows * 40 * sizeof(float);
         INMF_REQUIRE(smem <= 227 * 1024, "dense tile does not fit in shared memory");
-        INMF_OPTIN_SMEM((sell32r_pass_kernel), 227 * 1024);
-        sell32r_pass_kernel<<<(unsigned)nwork, SELL32_THREADS, smem, (cudaStream_t)stream>>>(
+        INMF_OPTIN_SMEM((sell32r_pass_kernel<MC>), 227 * 1024);
+        sell32r_pass_kernel<MC><<<(unsigned)nwork, SELL32_THREADS, smem, (cudaStream_t)stream>>>(
             work, slice_ptr, rowid, reinterpret_cast<const int4*>(pairs4), dense, kp, out, ldo, k, max_tile_rows, gram_out,
             part_stride, gram_part_stride);
         INMF_LAUNCH_CHECK();
@@ -1807,8 +1808,8 @@ extern "C" int32_t inmf_sell_pass_f32(const int64_t* work, int32_t nwork, const 
     if (height == 32) {
         const size_t smem = 128 + (size_t)max_tile_rows * 128;
         INMF_REQUIRE(smem <= 227 * 1024, "dense tile does not fit in shared memory");
-        INMF_OPTIN_SMEM((sell32_pass_kernel), 227 * 1024);
-        sell32_pass_kernel<<<(unsigned)nwork, SELL32_THREADS, smem, (cudaStream_t)stream>>>(
+        INMF_OPTIN_SMEM((sell32_pass_kernel<MC>), 227 * 1024);
+        sell32_pass_kernel<MC><<<(unsigned)nwork, SELL32_THREADS, smem, (cudaStream_t)stream>>>(
             work, slice_ptr, rowid, reinterpret_cast<const int4*>(pairs4), dense, out, ldo, k, gram_out, part_stride,
             gram_part_stride);
         INMF_LAUNCH_CHECK();
@@ -1817,11 +1818,27 @@ extern "C" int32_t inmf_sell_pass_f32(const int64_t* work, int32_t nwork, const 
     const int rem = kp - 32;
 #define INMF_SELL_ARGS \
     work, nwork, slice_ptr, rowid, pairs4, dense, kp, out, ldo, k, max_tile_rows, gram_out, part_stride, gram_part_stride, stream
-    if (rem == 0) return sell_pass_one<0>(INMF_SELL_ARGS);
-    if (rem <= 8) return sell_pass_one<8>(INMF_SELL_ARGS);
-    if (rem <= 16) return sell_pass_one<16>(INMF_SELL_ARGS);
-    return sell_pass_one<32>(INMF_SELL_ARGS);
+    if (rem == 0) return sell_pass_one<0, MC>(INMF_SELL_ARGS);
+    if (rem <= 8) return sell_pass_one<8, MC>(INMF_SELL_ARGS);
+    if (rem <= 16) return sell_pass_one<16, MC>(INMF_SELL_ARGS);
+    return sell_pass_one<32, MC>(INMF_SELL_ARGS);
 #undef INMF_SELL_ARGS
+}
+extern "C" int32_t inmf_sell_pass_f32(const int64_t* work, int32_t nwork, const int64_t* slice_ptr,
+                                      const int32_t* rowid, const void* pairs4, int32_t height, const float* dense,
+                                      int32_t kp, float* out, int64_t ldo, int32_t k, int32_t max_tile_rows,
+                                      double* gram_out, int64_t part_stride, int64_t gram_part_stride, void* stream) {
+    INMF_REQUIRE(part_stride >= 0 && gram_part_stride >= 0, "partial strides must be >= 0");
+    return sell_pass_dispatch<false>(work, nwork, slice_ptr, rowid, pairs4, height, dense, kp, out, ldo, k, max_tile_rows,
+                                     gram_out, part_stride, gram_part_stride, stream);
+}
+extern "C" int32_t inmf_sell_pass_mc_f32(const int64_t* work, int32_t nwork, const int64_t* slice_ptr,
+                                         const int32_t* rowid, const void* pairs4, int32_t height, const float* dense,
+                                         int32_t kp, float* out_mc, int64_t ldo, int32_t k, int32_t max_tile_rows,
+                                         double* gram_out_mc, void* stream) {
+    INMF_REQUIRE(out_mc != nullptr, "out_mc must be a multicast address");
+    return sell_pass_dispatch<true>(work, nwork, slice_ptr, rowid, pairs4, height, dense, kp, out_mc, ldo, k,
+                                    max_tile_rows, gram_out_mc, 0, 0, stream);
 }
 
 // out[i] = part[0][i] + part[1][i] + ... in that order (the deterministic mode's ordered sum of partial buffers).

@@ -110,9 +110,36 @@ __device__ __forceinline__ void red_add2(float* p, float a, float b) {
     asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
 }
 
+// The same adds on a multicast address (every bound GPU's copy receives them: pass 2 fused with its all-reduce).
+__device__ __forceinline__ void mc_red_add(float* p, float v) {
+    asm volatile("multimem.red.relaxed.sys.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+__device__ __forceinline__ void mc_red_add2(float* p, float a, float b) {
+    asm volatile("multimem.red.relaxed.sys.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ void mc_red_add4(float* p, const float (&v)[4]) {
+    asm volatile("multimem.red.relaxed.sys.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v[0]), "f"(v[1]),
+                 "f"(v[2]), "f"(v[3])
+                 : "memory");
+}
+
 // out[col0 .. col0+3] += v[0..3] for the columns < k.  vec = 4: rows are 16-byte aligned, 2: 8-byte aligned, else 1;
-// vec = 0: plain stores (deterministic mode, zeros included).
+// vec = 0: plain stores (deterministic mode, zeros included).  MC: `o` is a multicast address (vec = 1 / 2 / 4).
+template <bool MC = false>
 __device__ __forceinline__ void sell_out4(float* __restrict__ o, int col0, int k, const float (&v)[4], int vec) {
+    if constexpr (MC) {
+        if (vec == 4 && col0 + 4 <= k) {
+            if (v[0] != 0.f || v[1] != 0.f || v[2] != 0.f || v[3] != 0.f) mc_red_add4(o + col0, v);
+        } else if (vec >= 2 && col0 + 4 <= k) {
+            if (v[0] != 0.f || v[1] != 0.f) mc_red_add2(o + col0, v[0], v[1]);
+            if (v[2] != 0.f || v[3] != 0.f) mc_red_add2(o + col0 + 2, v[2], v[3]);
+        } else {
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (col0 + u < k && v[u] != 0.f) mc_red_add(o + col0 + u, v[u]);
+        }
+        return;
+    }
     if (vec == 0) {
 #pragma unroll
         for (int u = 0; u < 4; ++u)
@@ -131,7 +158,7 @@ __device__ __forceinline__ void sell_out4(float* __restrict__ o, int col0, int k
     }
 }
 
-template <int REM>
+template <int REM, bool MC>
 __global__ void __launch_bounds__(1024, 1)
 sell_pass_kernel(const int64_t* __restrict__ work, const int64_t* __restrict__ slice_ptr,
                  const int32_t* __restrict__ rowid, const int4* __restrict__ pairs, const float* __restrict__ dense,
@@ -192,9 +219,11 @@ sell_pass_kernel(const int64_t* __restrict__ work, const int64_t* __restrict__ s
         tR = smem_u32(trem) + (uint32_t)((sub + 4 * par) * 16);
         tR2 = smem_u32(trem) + (uint32_t)((sub + 4 * (1 - par)) * 16);
     }
+    // part_stride > 0: partial buffers (plain stores).  MC: `out` / `gram_out` are multicast addresses
     const int vec_ok = part_stride > 0 ? 0
                        : (((ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0)) ? 4
                        : (((ldo & 1) == 0) && ((reinterpret_cast<uintptr_t>(out) & 7) == 0)) ? 2 : 1;
+    const int gram_mode = MC ? INMF_GRAM_MULTICAST : part_stride > 0 ? INMF_GRAM_PLAIN : INMF_GRAM_ATOMIC;
 
     mbar_wait(bar, 0);
     // H'H of the resident tile (pass 2): done FIRST by the few warps whose threads own an output block, while all
@@ -202,9 +231,9 @@ sell_pass_kernel(const int64_t* __restrict__ work, const int64_t* __restrict__ s
     // and the latency-bound Gram loop costs no tail.
     if (gram_seg >= 0 && gram_out != nullptr) {
         if constexpr (REM == 0)
-            tile_gram_accumulate<float>(tmain, 32, tile_rows, k, gram_out + (size_t)gram_seg * k * k, 1.0, part_stride > 0);
+            tile_gram_accumulate<float>(tmain, 32, tile_rows, k, gram_out + (size_t)gram_seg * k * k, 1.0, gram_mode);
         else
-            split_gram_accumulate(tmain, trem, REM, tile_rows, k, gram_out + (size_t)gram_seg * k * k, part_stride > 0);
+            split_gram_accumulate(tmain, trem, REM, tile_rows, k, gram_out + (size_t)gram_seg * k * k, gram_mode);
     }
     int s = 0;
     if (lane == 0) s = atomicAdd(next_slice, 1);
@@ -259,24 +288,27 @@ sell_pass_kernel(const int64_t* __restrict__ work, const int64_t* __restrict__ s
         if (rid >= 0) {
             float* o = out + (out_row_base + rid) * ldo;
             // even groups: a = factors 4*sub.., b = 16 + 4*sub..; odd groups the other way round
-            sell_out4(o, 4 * sub + 16 * par, k, c.a, vec_ok);
-            sell_out4(o, 4 * sub + 16 * (1 - par), k, c.b, vec_ok);
+            sell_out4<MC>(o, 4 * sub + 16 * par, k, c.a, vec_ok);
+            sell_out4<MC>(o, 4 * sub + 16 * (1 - par), k, c.b, vec_ok);
             if constexpr (REM == 8) {
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
                     if (32 + 2 * sub + u < k) {
                         if (vec_ok == 0) o[32 + 2 * sub + u] = c.r[u];
-                        else if (c.r[u] != 0.f) red_add(o + 32 + 2 * sub + u, c.r[u]);
+                        else if (c.r[u] != 0.f) {
+                            if constexpr (MC) mc_red_add(o + 32 + 2 * sub + u, c.r[u]);
+                            else red_add(o + 32 + 2 * sub + u, c.r[u]);
+                        }
                     }
                 }
             } else if constexpr (REM == 16) {
                 float q[4] = {c.r[0], c.r[1], c.r[2], c.r[3]};
-                sell_out4(o, 32 + 4 * sub, k, q, vec_ok);
+                sell_out4<MC>(o, 32 + 4 * sub, k, q, vec_ok);
             } else if constexpr (REM == 32) {
                 float q[4] = {c.r[0], c.r[1], c.r[2], c.r[3]};
                 float t4[4] = {c.r[4], c.r[5], c.r[6], c.r[7]};
-                sell_out4(o, 32 + 4 * sub + 16 * par, k, q, vec_ok);
-                sell_out4(o, 32 + 4 * sub + 16 * (1 - par), k, t4, vec_ok);
+                sell_out4<MC>(o, 32 + 4 * sub + 16 * par, k, q, vec_ok);
+                sell_out4<MC>(o, 32 + 4 * sub + 16 * (1 - par), k, t4, vec_ok);
             }
         }
         s = sn;
@@ -301,6 +333,7 @@ sell_pass_kernel(const int64_t* __restrict__ work, const int64_t* __restrict__ s
 // =====================================================================================================
 #define SELL32_THREADS 512
 
+template <bool MC>
 __global__ void __launch_bounds__(SELL32_THREADS, 1)
 sell32_pass_kernel(const int64_t* __restrict__ work, const int64_t* __restrict__ slice_ptr,
                    const int32_t* __restrict__ rowid, const int4* __restrict__ pairs, const float* __restrict__ dense,
@@ -340,13 +373,15 @@ sell32_pass_kernel(const int64_t* __restrict__ work, const int64_t* __restrict__
     uint32_t tb[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) tb[j] = smem_u32(tile) + (uint32_t)(((lane + j) & 7) * 16);
+    // part_stride > 0: partial buffers (plain stores).  MC: `out` / `gram_out` are multicast addresses
     const int vec_ok = part_stride > 0 ? 0
                        : (((ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0)) ? 4
                        : (((ldo & 1) == 0) && ((reinterpret_cast<uintptr_t>(out) & 7) == 0)) ? 2 : 1;
+    const int gram_mode = MC ? INMF_GRAM_MULTICAST : part_stride > 0 ? INMF_GRAM_PLAIN : INMF_GRAM_ATOMIC;
 
     mbar_wait(bar, 0);
     if (gram_seg >= 0 && gram_out != nullptr)  // first, by the warps that own output blocks (see sell_pass_kernel)
-        tile_gram_accumulate<float>(tile, 32, tile_rows, k, gram_out + (size_t)gram_seg * k * k, 1.0, part_stride > 0);
+        tile_gram_accumulate<float>(tile, 32, tile_rows, k, gram_out + (size_t)gram_seg * k * k, 1.0, gram_mode);
     int s = 0;
     if (lane == 0) s = atomicAdd(next_slice, 1);
     s = __shfl_sync(INMF_FULL_MASK, s, 0);
@@ -398,7 +433,7 @@ sell32_pass_kernel(const int64_t* __restrict__ work, const int64_t* __restrict__
         if (rid >= 0) {
             float* o = out + (out_row_base + rid) * ldo;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) sell_out4(o, ((lane + c) & 7) * 4, k, acc[c], vec_ok);
+            for (int c = 0; c < 8; ++c) sell_out4<MC>(o, ((lane + c) & 7) * 4, k, acc[c], vec_ok);
         }
         s = sn;
         base = nbase;
@@ -418,6 +453,7 @@ sell32_pass_kernel(const int64_t* __restrict__ work, const int64_t* __restrict__
 // (row mod 4) == (l / 2 + j) mod 4 while its supply of that residue class lasts -- the four even (odd) lanes of a
 // phase then hit four different positions.  Conflicts remain only where a row runs out of a class early.
 // =====================================================================================================
+template <bool MC>
 __global__ void __launch_bounds__(SELL32_THREADS, 1)
 sell32r_pass_kernel(const int64_t* __restrict__ work, const int64_t* __restrict__ slice_ptr,
                     const int32_t* __restrict__ rowid, const int4* __restrict__ pairs, const float* __restrict__ dense,
@@ -458,12 +494,14 @@ sell32r_pass_kernel(const int64_t* __restrict__ work, const int64_t* __restrict_
     for (int j = 0; j < 8; ++j) tb[j] = smem_u32(tmain) + (uint32_t)(((lane + j) & 7) * 16);
     const uint32_t rA = smem_u32(trem) + (uint32_t)((lane & 1) * 16);
     const uint32_t rB = smem_u32(trem) + (uint32_t)((1 - (lane & 1)) * 16);
+    // part_stride > 0: partial buffers (plain stores).  MC: `out` / `gram_out` are multicast addresses
     const int vec_ok = part_stride > 0 ? 0
                        : (((ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0)) ? 4
                        : (((ldo & 1) == 0) && ((reinterpret_cast<uintptr_t>(out) & 7) == 0)) ? 2 : 1;
+    const int gram_mode = MC ? INMF_GRAM_MULTICAST : part_stride > 0 ? INMF_GRAM_PLAIN : INMF_GRAM_ATOMIC;
     mbar_wait(bar, 0);
     if (gram_seg >= 0 && gram_out != nullptr)
-        split_gram_accumulate(tmain, trem, 8, tile_rows, k, gram_out + (size_t)gram_seg * k * k, part_stride > 0);
+        split_gram_accumulate(tmain, trem, 8, tile_rows, k, gram_out + (size_t)gram_seg * k * k, gram_mode);
     int s = 0;
     if (lane == 0) s = atomicAdd(next_slice, 1);
     s = __shfl_sync(INMF_FULL_MASK, s, 0);
@@ -520,9 +558,9 @@ sell32r_pass_kernel(const int64_t* __restrict__ work, const int64_t* __restrict_
         if (rid >= 0) {
             float* o = out + (out_row_base + rid) * ldo;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) sell_out4(o, ((lane + c) & 7) * 4, k, acc[c], vec_ok);
-            sell_out4(o, 32 + 4 * (lane & 1), k, ra, vec_ok);        // even lanes: ra = factors 32..35, rb = 36..39
-            sell_out4(o, 32 + 4 * (1 - (lane & 1)), k, rb, vec_ok);
+            for (int c = 0; c < 8; ++c) sell_out4<MC>(o, ((lane + c) & 7) * 4, k, acc[c], vec_ok);
+            sell_out4<MC>(o, 32 + 4 * (lane & 1), k, ra, vec_ok);        // even lanes: ra = factors 32..35, rb = 36..39
+            sell_out4<MC>(o, 32 + 4 * (1 - (lane & 1)), k, rb, vec_ok);
         }
         s = sn;
         base = nbase;

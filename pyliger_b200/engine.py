@@ -351,6 +351,8 @@ class InmfEngine(object):
                     self.pass2 = blocked.build_pass2(X, self.ldm, esize, sms)
                     if sell:
                         self.pass2 = blocked.build_sell(self.pass2, self.ldm)
+        if self.world > 1 and self.use_blocked and self.need_stats and dt == torch.float32 and not self.use_tc:
+            self._setup_fused_reduce()
         self.tc1 = self.tc2 = None
         if self.use_tc and X.n_own_total > 0:
             sms = torch.cuda.get_device_properties(dev).multi_processor_count
@@ -364,6 +366,48 @@ class InmfEngine(object):
                 self.dc2_lo = torch.empty_like(self.dc2_hi)
 
     coalesce_allreduce = True
+
+    # Multi-GPU: pass 2 fused with the all-reduce of its outputs.  St / H'H live in symmetric memory bound to a multicast
+    # object of the NVLink switch; the pass adds every partial sum with multimem.red, so each rank's copy receives the
+    # sum over all ranks while the pass is still computing, and no NCCL collective follows (inmf_sell_pass_mc_f32).
+    # Falls back to pass + NCCL all-reduce where symmetric memory / multicast is not available.
+    fused_reduce = True
+    mc = None
+    fused_reduce_error = None
+
+    def _setup_fused_reduce(self):
+        """Collective over the ranks (every rank of a multi-GPU engine with blocked statistics passes calls it)."""
+        self.mc = None
+        N, g, k, dev = self.N, self.g, self.k, self.device
+        p = self.pass2
+        eligible = int(self.fused_reduce and isinstance(p, blocked.SellPass) and p.height in (8, 32, 33)
+                       and not self.deterministic and not self.mixed and self.guard_elems == 0)
+        flag = torch.tensor([eligible], dtype=torch.int32, device=dev)
+        torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) != 1:
+            return
+        ok = 0
+        try:
+            import torch.distributed._symmetric_memory as symm
+            group = self.group if self.group is not None else torch.distributed.group.WORLD
+            n_st = (N * g * k * 4 + 255) // 256 * 256
+            buf = symm.empty(n_st + N * k * k * 8, dtype=torch.uint8, device=dev)
+            hdl = symm.rendezvous(buf, group)
+            mcp = int(getattr(hdl, "multicast_ptr", 0) or 0)
+            if mcp:
+                buf.zero_()
+                ok = 1
+            else:
+                self.fused_reduce_error = "no multicast support"
+        except Exception as e:  # symmetric memory not available in this process / on this fabric
+            self.fused_reduce_error = repr(e)
+        flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+        torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) != 1:  # all ranks or none
+            return
+        self.St = buf[:N * g * k * 4].view(torch.float32).view(N, g, k)
+        self.HtH = buf[n_st:n_st + N * k * k * 8].view(torch.float64).view(N, k, k)
+        self.mc = (hdl, buf, mcp, mcp + n_st)
 
     def _allreduce(self, *tensors):
         """SUM over the ranks.  Tensors of one dtype go out as ONE coalesced NCCL launch; different dtypes (fp32 St +
@@ -528,6 +572,13 @@ class InmfEngine(object):
                 _lib.call("inmf_gram_rows", self.sfx, H, self.ldm, self.seg_full, nseg, max_rows, HtH, k, _stream())
             elif full and self.pass2 is not None:
                 p = self.pass2
+                if reduce and self.mc is not None and St is self.St and HtH is self.HtH:
+                    hdl, _, st_mc, hth_mc = self.mc
+                    hdl.barrier(channel=0)  # every rank's copy is zero before the first add arrives
+                    _lib.call("inmf_sell_pass_mc_f32", "", p.work, p.nwork, p.slice_ptr, p.rowid, p.pairs4, p.height, H,
+                              self.ldm, st_mc, k, k, p.max_tile_rows, hth_mc, _stream())
+                    hdl.barrier(channel=1)  # every rank's adds have landed
+                    return
                 self._blocked(p, p.work, p.nwork, H, St, k, HtH)
             else:
                 _lib.call("inmf_stats", self.sfx, X.rowptr, X.colidx, X.vals, H, self.ldm, St, HtH, self.g, seg_desc,

@@ -143,6 +143,9 @@ def optimize_ALS(
         if print_obj:
             print("Objective: {}".format(best_obj))
     info["bpp"] = engine.bpp_report()
+    info["fused_reduce"] = engine.mc is not None  # pass 2 fused with its all-reduce (multi-GPU, NVLink multicast)
+    if engine.fused_reduce_error:
+        info["fused_reduce_error"] = engine.fused_reduce_error
     info["best_objective"] = best_obj
 
     final_H, final_Wt, final_Vt = best

@@ -39,8 +39,25 @@ def main():
         werr = np.linalg.norm(lig.W.T - want["W"]) / np.linalg.norm(want["W"])
         good = rel.max() < otol and herr < ftol and werr < ftol and lig.H[0].shape == want["H"][0].shape
         ok &= bool(good)
-        print("rank %d/%d ALS %s: obj rel err %.2e, H err %.2e, W err %.2e -> %s" % (
-            rank, world, dtype, rel.max(), herr, werr, "OK" if good else "FAIL"), flush=True)
+        print("rank %d/%d ALS %s: obj rel err %.2e, H err %.2e, W err %.2e -> %s (fused pass 2 + all-reduce: %s%s)" % (
+            rank, world, dtype, rel.max(), herr, werr, "OK" if good else "FAIL", info.get("fused_reduce"),
+            (", " + info["fused_reduce_error"][:200]) if info.get("fused_reduce_error") else ""), flush=True)
+    # the fused path against pass 2 + NCCL all-reduce on a k = 40 shape (one-lane-per-row kernel with remainder tile)
+    from pyliger_b200.engine import InmfEngine
+    mats40 = make_datasets([2100, 1500], 500, 40, density=0.1, seed0=6100)
+    res = {}
+    for fused in (True, False):
+        InmfEngine.fused_reduce = fused
+        lig = liger_from_matrices(mats40)
+        info = optimize_ALS(lig, 40, lam, 1e-6, 4, rand_seed=1, dtype="float32", return_info=True, progress=False)
+        res[fused] = (np.array(info["objectives"][0]), lig.W.copy(), info.get("fused_reduce"))
+    InmfEngine.fused_reduce = True
+    rel = np.abs(res[True][0] - res[False][0]) / res[False][0]
+    werr = np.linalg.norm(res[True][1] - res[False][1]) / np.linalg.norm(res[False][1])
+    good = rel.max() < 1e-5 and werr < 1e-3 and res[False][2] is False
+    ok &= bool(good)
+    print("rank %d/%d k=40 fused (%s) vs NCCL: obj rel diff %.2e, W diff %.2e -> %s" % (
+        rank, world, res[True][2], rel.max(), werr, "OK" if good else "FAIL"), flush=True)
     wo = orc.online(mats, k, lam, 2, 1, 300, 1000, 1)
     lig = liger_from_matrices(mats)
     online_iNMF(lig, k=k, value_lambda=lam, max_epochs=2, miniBatch_size=300, verbose=False)
