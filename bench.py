@@ -237,9 +237,13 @@ def kernel_breakdown(eng, warm, reps):
         evs[1].record()
         eng.bpp_H(mask=eng.mask_H, warm=warm, clear=eng.H_alt)
         evs[2].record()
-        eng.stats(reduce=False)
-        evs[3].record()
-        eng.reduce_stats()  # (includes the wait for the slowest rank)
+        if eng.mc is not None:  # fused: the pass adds into every rank's copy (includes the two cross-rank barriers)
+            eng.stats()
+            evs[3].record()
+        else:
+            eng.stats(reduce=False)
+            evs[3].record()
+            eng.reduce_stats()  # (includes the wait for the slowest rank)
         evs[4].record()
         eng.solve_V(warm=warm)
         evs[5].record()
@@ -319,6 +323,7 @@ def leg_c4(ctx, steps):
            "nnz_per_cell": nnz_local / cells_local, "gpu_launches": int(launches),
            "objective_monotone": bool(np.all(np.diff(objs) <= 1e-6 * abs(objs[0]))),
            "roofline": roofline_block(acc, ms_step, cells_local, nnz_local, k, 4, "C4"),
+           "fused_reduce": eng.mc is not None,
            "bpp_H": eng.bpp_report()["H"], "seconds": {"generate": round(t_gen, 2), "setup": round(t_setup, 2)}}
     del eng, mats
     torch.cuda.empty_cache()
@@ -527,6 +532,9 @@ def main():
                     help="headline workload: C2 (default, weak scaling) or C4 (8 x 250k cells sharded over the ranks)")
     ap.add_argument("--cells", type=int, default=0, help="cells per dataset per GPU (default: the config's)")
     ap.add_argument("--graph", type=int, default=1, help="1: CUDA-graphed warm iterations (the engine default), 0: eager")
+    ap.add_argument("--fused-reduce", type=int, default=1,
+                    help="N > 1: 1 = pass 2 adds into multicast-bound symmetric buffers (no separate all-reduce; the "
+                         "engine default where the fabric supports it), 0 = pass 2 + NCCL all-reduce")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline legs")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="headline only (skip the c2 cold / fp64, C3, C4, C5 legs)")
@@ -550,6 +558,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     InmfEngine.use_graph = bool(args.graph)
+    InmfEngine.fused_reduce = bool(args.fused_reduce)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -620,6 +629,7 @@ def main():
     log("rank %d: objectives first/last %.6e %.6e monotone=%s bpp=%s" % (rank, objs[1], objs[-1], mono,
                                                                        eng.bpp_report()["H"]))
     acc = kernel_breakdown(eng, warm, 5)
+    fused = eng.mc is not None
     roofline = roofline_block(acc, ms_per_step, cells_local, nnz_local, k, esize,
                               args.config if args.dtype == "f32" else None)
     extra = {}
@@ -721,7 +731,11 @@ def main():
                                   "is the throughput mode, the fp64 default is in extra.c2_warm_f64)",
                        "l2": "inputs larger than L2 (CSR %.0f MB per GPU streamed twice per step)" % (
                            nnz_local * (esize + 4) / 1e6),
-                       "parallelism": "cells sharded over %d GPU(s), all-reduce of k x k and genes x k statistics" % world},
+                       "parallelism": "cells sharded over %d GPU(s), %s" % (
+                           world, "single GPU" if world == 1 else (
+                               "pass 2 adds its k x k and genes x k statistics into every rank's copy through the "
+                               "NVLink switch (multimem.red, no separate all-reduce)" if fused else
+                               "NCCL all-reduce of the k x k and genes x k statistics"))},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
             "objective_monotone": mono, "extra": extra,
         }

@@ -165,16 +165,23 @@ int32_t inmf_sell_pass_f32(const int64_t* work, int32_t nwork, const int64_t* sl
                            int32_t k, int32_t max_tile_rows, double* gram_out, int64_t part_stride,
                            int64_t gram_part_stride, void* stream);
 
-/* Pass 2 fused with its all-reduce (multi-GPU, cells sharded over the ranks): out_mc / gram_out_mc are MULTICAST
- * addresses of symmetric buffers bound on every rank (CUDA multicast object over the NVLink switch, e.g.
- * torch.distributed._symmetric_memory handle.multicast_ptr + offset), same element layout as out / gram_out above.  Every
- * partial sum is added with multimem.red: the switch performs the add on every rank's copy, so when all ranks' kernels
- * have completed each copy holds the SUM over the ranks of X' H and H' H -- the statistics of _iNMF_ANLS.py:142-152 over
- * all cells -- tile by tile while the pass computes, with no separate collective.  The caller orders the ranks: every
- * copy is zeroed before any rank launches (one cross-rank barrier) and is read after all ranks have finished (another). */
+/* Pass 2 fused with its all-reduce (multi-GPU, cells sharded over the ranks; the all-reduce of X' H and H' H over the
+ * ranks is what makes _iNMF_ANLS.py:142-152 see all cells).  Same arguments as inmf_sell_pass_f32 with ldo == k; partial
+ * sums are accumulated in the rank's own `out` / `gram_out` as there.  In addition the work items that add into one
+ * (dataset, gene range) share an arrival counter, work[w][6] = counter id and work[w][7] = (first row << 32) | end row of
+ * the range (rows relative to out_row_base); the CTA that arrives last at a counter adds the finished range (and, for the
+ * range whose items carry gram_seg >= 0, the dataset's k x k block of gram_out) into the MULTICAST copy with
+ * multimem.red: the NVLink switch performs the add on every rank's sum buffer while the rest of the pass is still
+ * computing, and no separate collective follows.
+ *   mc_args -> device struct { float* out_mc; double* gram_mc; int32_t* counters; const int32_t* expected; }:
+ *   multicast addresses of the symmetric sum buffers (e.g. torch.distributed._symmetric_memory multicast_ptr + offset;
+ *   same layouts as out / gram_out), one zero-initialised counter per range (reset by the last arriver) and the number of
+ *   work items per counter.
+ * The caller orders the ranks: every rank's sum buffer is zero before any rank launches (one cross-rank barrier), and is
+ * read after all ranks' kernels have completed (another). */
 int32_t inmf_sell_pass_mc_f32(const int64_t* work, int32_t nwork, const int64_t* slice_ptr, const int32_t* rowid,
-                              const void* pairs4, int32_t height, const float* dense, int32_t kp, float* out_mc,
-                              int64_t ldo, int32_t k, int32_t max_tile_rows, double* gram_out_mc, void* stream);
+                              const void* pairs4, int32_t height, const float* dense, int32_t kp, float* out, int32_t k,
+                              int32_t max_tile_rows, double* gram_out, const void* mc_args, void* stream);
 
 /* Deterministic (bit-reproducible) accumulation.  By default the passes add their per-tile partial sums into the
  * outputs with floating-point atomics, whose order depends on the CTA schedule.  With part_stride > 0 in

@@ -82,7 +82,7 @@ def load():
         getattr(lib, name).restype = _I32
         getattr(lib, name).argtypes = _TYPED["inmf_blocked_spmm"]
     lib.inmf_sell_pass_mc_f32.restype = _I32
-    lib.inmf_sell_pass_mc_f32.argtypes = [_PTR, _I32, _PTR, _PTR, _PTR, _I32, _PTR, _I32, _PTR, _I64, _I32, _I32, _PTR, _PTR]
+    lib.inmf_sell_pass_mc_f32.argtypes = [_PTR, _I32, _PTR, _PTR, _PTR, _I32, _PTR, _I32, _PTR, _I32, _I32, _PTR, _PTR, _PTR]
     lib.inmf_sell_pass_f32.restype = _I32
     lib.inmf_sell_pass_f32.argtypes = [_PTR, _I32, _PTR, _PTR, _PTR, _I32, _PTR, _I32, _PTR, _I64, _I32, _I32, _PTR, _I64, _I64,
                                        _PTR]

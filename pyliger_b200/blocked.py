@@ -124,7 +124,7 @@ class BlockedPass(object):
 class SellPass(object):
     """Sliced form of a BlockedPass (csrc/sell.cuh): rows of every work item sorted by length, 8 per slice."""
     __slots__ = ("work", "nwork", "slice_ptr", "rowid", "pairs4", "max_tile_rows", "nnz", "padded", "height", "nparts",
-                 "work_host")
+                 "work_host", "row_lo", "row_hi")
 
 
 SELL_HEIGHT_KP32 = 32  # slice height at kp == 32: 32 (one lane per row) or 8 (four lanes per row)
@@ -190,6 +190,7 @@ def build_sell(bp, kp, height=None):
     work[:, 5] = W[:, 6]
     work[:, 6] = W[:, 7]
     sp.nparts = int(W[:, 7].max()) + 1
+    sp.row_lo, sp.row_hi = W[:, 3].copy(), W[:, 4].copy()  # output rows of every item, relative to its out_row_base
     sp.work_host = work
     sp.work = torch.from_numpy(work).to(dev)
     return sp

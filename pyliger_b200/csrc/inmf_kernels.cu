@@ -1772,22 +1772,22 @@ template <int REM, bool MC>
 static int32_t sell_pass_one(const int64_t* work, int32_t nwork, const int64_t* slice_ptr, const int32_t* rowid,
                              const void* pairs4, const float* dense, int32_t kp, float* out, int64_t ldo, int32_t k,
                              int32_t max_tile_rows, double* gram_out, int64_t part_stride, int64_t gram_part_stride,
-                             void* stream) {
+                             const SellMcArgs* mc, void* stream) {
     const size_t smem = 128 + (size_t)max_tile_rows * (32 + REM) * sizeof(float);
     INMF_REQUIRE(smem <= 227 * 1024, "dense tile does not fit in shared memory");
     INMF_OPTIN_SMEM((sell_pass_kernel<REM, MC>), 227 * 1024);
     sell_pass_kernel<REM, MC><<<(unsigned)nwork, 1024, smem, (cudaStream_t)stream>>>(
         work, slice_ptr, rowid, reinterpret_cast<const int4*>(pairs4), dense, kp, out, ldo, k, max_tile_rows, gram_out,
-        part_stride, gram_part_stride);
+        part_stride, gram_part_stride, mc);
     INMF_LAUNCH_CHECK();
     return 0;
 }
-// MC: out / gram_out are multicast addresses (inmf_sell_pass_mc_f32)
+// MC: finished gene ranges are added into the multicast copies (inmf_sell_pass_mc_f32)
 template <bool MC>
 static int32_t sell_pass_dispatch(const int64_t* work, int32_t nwork, const int64_t* slice_ptr, const int32_t* rowid,
                                   const void* pairs4, int32_t height, const float* dense, int32_t kp, float* out,
                                   int64_t ldo, int32_t k, int32_t max_tile_rows, double* gram_out, int64_t part_stride,
-                                  int64_t gram_part_stride, void* stream) {
+                                  int64_t gram_part_stride, const SellMcArgs* mc, void* stream) {
     INMF_REQUIRE(k >= 1 && k <= INMF_MAX_K, "k must be in [1, 64]");
     INMF_REQUIRE(kp >= 32 && kp >= k && kp % 4 == 0 && kp <= 64, "kp must be a multiple of 4 in [max(k, 32), 64]");
     INMF_REQUIRE(ldo >= k, "ldo must be >= k");
@@ -1801,7 +1801,7 @@ static int32_t sell_pass_dispatch(const int64_t* work, int32_t nwork, const int6
         INMF_OPTIN_SMEM((sell32r_pass_kernel<MC>), 227 * 1024);
         sell32r_pass_kernel<MC><<<(unsigned)nwork, SELL32_THREADS, smem, (cudaStream_t)stream>>>(
             work, slice_ptr, rowid, reinterpret_cast<const int4*>(pairs4), dense, kp, out, ldo, k, max_tile_rows, gram_out,
-            part_stride, gram_part_stride);
+            part_stride, gram_part_stride, mc);
         INMF_LAUNCH_CHECK();
         return 0;
     }
@@ -1811,13 +1811,13 @@ static int32_t sell_pass_dispatch(const int64_t* work, int32_t nwork, const int6
         INMF_OPTIN_SMEM((sell32_pass_kernel<MC>), 227 * 1024);
         sell32_pass_kernel<MC><<<(unsigned)nwork, SELL32_THREADS, smem, (cudaStream_t)stream>>>(
             work, slice_ptr, rowid, reinterpret_cast<const int4*>(pairs4), dense, out, ldo, k, gram_out, part_stride,
-            gram_part_stride);
+            gram_part_stride, mc);
         INMF_LAUNCH_CHECK();
         return 0;
     }
     const int rem = kp - 32;
 #define INMF_SELL_ARGS \
-    work, nwork, slice_ptr, rowid, pairs4, dense, kp, out, ldo, k, max_tile_rows, gram_out, part_stride, gram_part_stride, stream
+    work, nwork, slice_ptr, rowid, pairs4, dense, kp, out, ldo, k, max_tile_rows, gram_out, part_stride, gram_part_stride, mc, stream
     if (rem == 0) return sell_pass_one<0, MC>(INMF_SELL_ARGS);
     if (rem <= 8) return sell_pass_one<8, MC>(INMF_SELL_ARGS);
     if (rem <= 16) return sell_pass_one<16, MC>(INMF_SELL_ARGS);
@@ -1830,15 +1830,15 @@ extern "C" int32_t inmf_sell_pass_f32(const int64_t* work, int32_t nwork, const 
                                       double* gram_out, int64_t part_stride, int64_t gram_part_stride, void* stream) {
     INMF_REQUIRE(part_stride >= 0 && gram_part_stride >= 0, "partial strides must be >= 0");
     return sell_pass_dispatch<false>(work, nwork, slice_ptr, rowid, pairs4, height, dense, kp, out, ldo, k, max_tile_rows,
-                                     gram_out, part_stride, gram_part_stride, stream);
+                                     gram_out, part_stride, gram_part_stride, nullptr, stream);
 }
 extern "C" int32_t inmf_sell_pass_mc_f32(const int64_t* work, int32_t nwork, const int64_t* slice_ptr,
                                          const int32_t* rowid, const void* pairs4, int32_t height, const float* dense,
-                                         int32_t kp, float* out_mc, int64_t ldo, int32_t k, int32_t max_tile_rows,
-                                         double* gram_out_mc, void* stream) {
-    INMF_REQUIRE(out_mc != nullptr, "out_mc must be a multicast address");
-    return sell_pass_dispatch<true>(work, nwork, slice_ptr, rowid, pairs4, height, dense, kp, out_mc, ldo, k,
-                                    max_tile_rows, gram_out_mc, 0, 0, stream);
+                                         int32_t kp, float* out, int32_t k, int32_t max_tile_rows, double* gram_out,
+                                         const void* mc_args, void* stream) {
+    INMF_REQUIRE(mc_args != nullptr, "mc_args (device struct of multicast addresses and counters) is required");
+    return sell_pass_dispatch<true>(work, nwork, slice_ptr, rowid, pairs4, height, dense, kp, out, k, k, max_tile_rows,
+                                    gram_out, 0, 0, reinterpret_cast<const SellMcArgs*>(mc_args), stream);
 }
 
 // out[i] = part[0][i] + part[1][i] + ... in that order (the deterministic mode's ordered sum of partial buffers).

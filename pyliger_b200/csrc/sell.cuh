@@ -123,23 +123,68 @@ __device__ __forceinline__ void mc_red_add4(float* p, const float (&v)[4]) {
                  : "memory");
 }
 
-// out[col0 .. col0+3] += v[0..3] for the columns < k.  vec = 4: rows are 16-byte aligned, 2: 8-byte aligned, else 1;
-// vec = 0: plain stores (deterministic mode, zeros included).  MC: `o` is a multicast address (vec = 1 / 2 / 4).
-template <bool MC = false>
-__device__ __forceinline__ void sell_out4(float* __restrict__ o, int col0, int k, const float (&v)[4], int vec) {
-    if constexpr (MC) {
-        if (vec == 4 && col0 + 4 <= k) {
-            if (v[0] != 0.f || v[1] != 0.f || v[2] != 0.f || v[3] != 0.f) mc_red_add4(o + col0, v);
-        } else if (vec >= 2 && col0 + 4 <= k) {
-            if (v[0] != 0.f || v[1] != 0.f) mc_red_add2(o + col0, v[0], v[1]);
-            if (v[2] != 0.f || v[3] != 0.f) mc_red_add2(o + col0 + 2, v[2], v[3]);
-        } else {
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (col0 + u < k && v[u] != 0.f) mc_red_add(o + col0 + u, v[u]);
-        }
-        return;
+// ---- pass 2 fused with its all-reduce (MC kernels) --------------------------------------------------------------
+// Partial sums are accumulated in the rank's own `out` exactly as in the single-GPU pass (L2 atomics).  The work items
+// that add into one (dataset, gene range) share an arrival counter; the CTA that arrives LAST knows the range is
+// final on this rank and adds it -- contiguous, 16 bytes per lane -- into the multicast copy, i.e. into every rank's
+// sum buffer through the NVLink switch, while other CTAs are still computing.  (Adding every partial sum through the
+// switch instead was measured at ~37 GB/s per GPU, 7x slower than the pass itself: the switch wants few large adds.)
+struct SellMcArgs {
+    float* out_mc;         // multicast address of the sum buffer, same layout as `out` (ldo == k)
+    double* gram_mc;       // multicast address of the k x k sums, same layout as gram_out
+    int* counters;         // one per (dataset, gene range), zero before the first launch (the last arriver resets it)
+    const int* expected;   // work items per counter
+};
+
+__device__ __forceinline__ void sell_mc_push(const int64_t* __restrict__ wd, const float* __restrict__ out, int64_t ldo,
+                                             int k, const double* __restrict__ gram_out,
+                                             const SellMcArgs* __restrict__ mc, int* flag_smem) {
+    __threadfence();  // this thread's adds are performed before the arrival is counted
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int id = (int)wd[6];
+        const int old = atomicAdd(&mc->counters[id], 1);
+        const int last = old == mc->expected[id] - 1;
+        if (last) mc->counters[id] = 0;
+        *flag_smem = last;
     }
+    __syncthreads();
+    if (!*flag_smem) return;
+    __threadfence();
+    const int64_t lo = wd[7] >> 32, hi = wd[7] & 0xffffffffll;
+    const size_t beg = (size_t)(wd[4] + lo) * ldo, n = (size_t)(hi - lo) * ldo;
+    const float* src = out + beg;
+    float* dst = mc->out_mc + beg;
+    size_t head = ((16 - (reinterpret_cast<uintptr_t>(src) & 15)) & 15) >> 2;
+    if (head > n) head = n;
+    for (size_t i = threadIdx.x; i < head; i += blockDim.x) {
+        const float v = __ldcg(src + i);
+        if (v != 0.f) mc_red_add(dst + i, v);
+    }
+    const size_t n4 = (n - head) >> 2;
+    const float4* s4 = reinterpret_cast<const float4*>(src + head);
+    float* d4 = dst + head;
+    for (size_t i = threadIdx.x; i < n4; i += blockDim.x) {
+        const float4 t = __ldcg(s4 + i);
+        const float v[4] = {t.x, t.y, t.z, t.w};
+        if (t.x != 0.f || t.y != 0.f || t.z != 0.f || t.w != 0.f) mc_red_add4(d4 + 4 * i, v);
+    }
+    for (size_t i = head + 4 * n4 + threadIdx.x; i < n; i += blockDim.x) {
+        const float v = __ldcg(src + i);
+        if (v != 0.f) mc_red_add(dst + i, v);
+    }
+    if (wd[5] >= 0 && gram_out != nullptr) {  // (the items that add a tile Gram are exactly those of the first range)
+        const size_t gb = (size_t)wd[5] * k * k;
+        for (int i = threadIdx.x; i < k * k; i += blockDim.x) {
+            const double v = __ldcg(gram_out + gb + i);
+            if (v != 0.0) mc_red_add_f64(mc->gram_mc + gb + i, v);
+        }
+    }
+}
+
+// out[col0 .. col0+3] += v[0..3] for the columns < k.  vec = 4: rows are 16-byte aligned, 2: 8-byte aligned, else 1;
+// vec = 0: plain stores (deterministic mode, zeros included).
+__device__ __forceinline__ void sell_out4(float* __restrict__ o, int col0, int k, const float (&v)[4], int vec) {
     if (vec == 0) {
 #pragma unroll
         for (int u = 0; u < 4; ++u)
@@ -163,7 +208,8 @@ __global__ void __launch_bounds__(1024, 1)
 sell_pass_kernel(const int64_t* __restrict__ work, const int64_t* __restrict__ slice_ptr,
                  const int32_t* __restrict__ rowid, const int4* __restrict__ pairs, const float* __restrict__ dense,
                  int KP, float* __restrict__ out, int64_t ldo, int k, int max_tile_rows,
-                 double* __restrict__ gram_out, int64_t part_stride, int64_t gram_part_stride) {
+                 double* __restrict__ gram_out, int64_t part_stride, int64_t gram_part_stride,
+                 const SellMcArgs* __restrict__ mc) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
     int* next_slice = reinterpret_cast<int*>(smem_raw + 16);
@@ -219,11 +265,11 @@ sell_pass_kernel(const int64_t* __restrict__ work, const int64_t* __restrict__ s
         tR = smem_u32(trem) + (uint32_t)((sub + 4 * par) * 16);
         tR2 = smem_u32(trem) + (uint32_t)((sub + 4 * (1 - par)) * 16);
     }
-    // part_stride > 0: partial buffers (plain stores).  MC: `out` / `gram_out` are multicast addresses
+    // part_stride > 0: partial buffers (plain stores)
     const int vec_ok = part_stride > 0 ? 0
                        : (((ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0)) ? 4
                        : (((ldo & 1) == 0) && ((reinterpret_cast<uintptr_t>(out) & 7) == 0)) ? 2 : 1;
-    const int gram_mode = MC ? INMF_GRAM_MULTICAST : part_stride > 0 ? INMF_GRAM_PLAIN : INMF_GRAM_ATOMIC;
+    const int gram_mode = part_stride > 0 ? INMF_GRAM_PLAIN : INMF_GRAM_ATOMIC;
 
     mbar_wait(bar, 0);
     // H'H of the resident tile (pass 2): done FIRST by the few warps whose threads own an output block, while all
@@ -288,33 +334,33 @@ sell_pass_kernel(const int64_t* __restrict__ work, const int64_t* __restrict__ s
         if (rid >= 0) {
             float* o = out + (out_row_base + rid) * ldo;
             // even groups: a = factors 4*sub.., b = 16 + 4*sub..; odd groups the other way round
-            sell_out4<MC>(o, 4 * sub + 16 * par, k, c.a, vec_ok);
-            sell_out4<MC>(o, 4 * sub + 16 * (1 - par), k, c.b, vec_ok);
+            sell_out4(o, 4 * sub + 16 * par, k, c.a, vec_ok);
+            sell_out4(o, 4 * sub + 16 * (1 - par), k, c.b, vec_ok);
             if constexpr (REM == 8) {
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
                     if (32 + 2 * sub + u < k) {
                         if (vec_ok == 0) o[32 + 2 * sub + u] = c.r[u];
                         else if (c.r[u] != 0.f) {
-                            if constexpr (MC) mc_red_add(o + 32 + 2 * sub + u, c.r[u]);
-                            else red_add(o + 32 + 2 * sub + u, c.r[u]);
+                            red_add(o + 32 + 2 * sub + u, c.r[u]);
                         }
                     }
                 }
             } else if constexpr (REM == 16) {
                 float q[4] = {c.r[0], c.r[1], c.r[2], c.r[3]};
-                sell_out4<MC>(o, 32 + 4 * sub, k, q, vec_ok);
+                sell_out4(o, 32 + 4 * sub, k, q, vec_ok);
             } else if constexpr (REM == 32) {
                 float q[4] = {c.r[0], c.r[1], c.r[2], c.r[3]};
                 float t4[4] = {c.r[4], c.r[5], c.r[6], c.r[7]};
-                sell_out4<MC>(o, 32 + 4 * sub + 16 * par, k, q, vec_ok);
-                sell_out4<MC>(o, 32 + 4 * sub + 16 * (1 - par), k, t4, vec_ok);
+                sell_out4(o, 32 + 4 * sub + 16 * par, k, q, vec_ok);
+                sell_out4(o, 32 + 4 * sub + 16 * (1 - par), k, t4, vec_ok);
             }
         }
         s = sn;
         base = nbase;
         lim = nlim;
     }
+    if constexpr (MC) sell_mc_push(wd, out, ldo, k, gram_out, mc, next_slice + 1);
 }
 
 // =====================================================================================================
@@ -338,7 +384,7 @@ __global__ void __launch_bounds__(SELL32_THREADS, 1)
 sell32_pass_kernel(const int64_t* __restrict__ work, const int64_t* __restrict__ slice_ptr,
                    const int32_t* __restrict__ rowid, const int4* __restrict__ pairs, const float* __restrict__ dense,
                    float* __restrict__ out, int64_t ldo, int k, double* __restrict__ gram_out, int64_t part_stride,
-                   int64_t gram_part_stride) {
+                   int64_t gram_part_stride, const SellMcArgs* __restrict__ mc) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
     int* next_slice = reinterpret_cast<int*>(smem_raw + 16);
@@ -373,11 +419,11 @@ sell32_pass_kernel(const int64_t* __restrict__ work, const int64_t* __restrict__
     uint32_t tb[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) tb[j] = smem_u32(tile) + (uint32_t)(((lane + j) & 7) * 16);
-    // part_stride > 0: partial buffers (plain stores).  MC: `out` / `gram_out` are multicast addresses
+    // part_stride > 0: partial buffers (plain stores)
     const int vec_ok = part_stride > 0 ? 0
                        : (((ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0)) ? 4
                        : (((ldo & 1) == 0) && ((reinterpret_cast<uintptr_t>(out) & 7) == 0)) ? 2 : 1;
-    const int gram_mode = MC ? INMF_GRAM_MULTICAST : part_stride > 0 ? INMF_GRAM_PLAIN : INMF_GRAM_ATOMIC;
+    const int gram_mode = part_stride > 0 ? INMF_GRAM_PLAIN : INMF_GRAM_ATOMIC;
 
     mbar_wait(bar, 0);
     if (gram_seg >= 0 && gram_out != nullptr)  // first, by the warps that own output blocks (see sell_pass_kernel)
@@ -433,12 +479,13 @@ sell32_pass_kernel(const int64_t* __restrict__ work, const int64_t* __restrict__
         if (rid >= 0) {
             float* o = out + (out_row_base + rid) * ldo;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) sell_out4<MC>(o, ((lane + c) & 7) * 4, k, acc[c], vec_ok);
+            for (int c = 0; c < 8; ++c) sell_out4(o, ((lane + c) & 7) * 4, k, acc[c], vec_ok);
         }
         s = sn;
         base = nbase;
         lim = nlim;
     }
+    if constexpr (MC) sell_mc_push(wd, out, ldo, k, gram_out, mc, next_slice + 1);
 }
 
 // =====================================================================================================
@@ -458,7 +505,8 @@ __global__ void __launch_bounds__(SELL32_THREADS, 1)
 sell32r_pass_kernel(const int64_t* __restrict__ work, const int64_t* __restrict__ slice_ptr,
                     const int32_t* __restrict__ rowid, const int4* __restrict__ pairs, const float* __restrict__ dense,
                     int KP, float* __restrict__ out, int64_t ldo, int k, int max_tile_rows,
-                    double* __restrict__ gram_out, int64_t part_stride, int64_t gram_part_stride) {
+                    double* __restrict__ gram_out, int64_t part_stride, int64_t gram_part_stride,
+                    const SellMcArgs* __restrict__ mc) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
     int* next_slice = reinterpret_cast<int*>(smem_raw + 16);
@@ -494,11 +542,11 @@ sell32r_pass_kernel(const int64_t* __restrict__ work, const int64_t* __restrict_
     for (int j = 0; j < 8; ++j) tb[j] = smem_u32(tmain) + (uint32_t)(((lane + j) & 7) * 16);
     const uint32_t rA = smem_u32(trem) + (uint32_t)((lane & 1) * 16);
     const uint32_t rB = smem_u32(trem) + (uint32_t)((1 - (lane & 1)) * 16);
-    // part_stride > 0: partial buffers (plain stores).  MC: `out` / `gram_out` are multicast addresses
+    // part_stride > 0: partial buffers (plain stores)
     const int vec_ok = part_stride > 0 ? 0
                        : (((ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0)) ? 4
                        : (((ldo & 1) == 0) && ((reinterpret_cast<uintptr_t>(out) & 7) == 0)) ? 2 : 1;
-    const int gram_mode = MC ? INMF_GRAM_MULTICAST : part_stride > 0 ? INMF_GRAM_PLAIN : INMF_GRAM_ATOMIC;
+    const int gram_mode = part_stride > 0 ? INMF_GRAM_PLAIN : INMF_GRAM_ATOMIC;
     mbar_wait(bar, 0);
     if (gram_seg >= 0 && gram_out != nullptr)
         split_gram_accumulate(tmain, trem, 8, tile_rows, k, gram_out + (size_t)gram_seg * k * k, gram_mode);
@@ -558,14 +606,15 @@ sell32r_pass_kernel(const int64_t* __restrict__ work, const int64_t* __restrict_
         if (rid >= 0) {
             float* o = out + (out_row_base + rid) * ldo;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) sell_out4<MC>(o, ((lane + c) & 7) * 4, k, acc[c], vec_ok);
-            sell_out4<MC>(o, 32 + 4 * (lane & 1), k, ra, vec_ok);        // even lanes: ra = factors 32..35, rb = 36..39
-            sell_out4<MC>(o, 32 + 4 * (1 - (lane & 1)), k, rb, vec_ok);
+            for (int c = 0; c < 8; ++c) sell_out4(o, ((lane + c) & 7) * 4, k, acc[c], vec_ok);
+            sell_out4(o, 32 + 4 * (lane & 1), k, ra, vec_ok);        // even lanes: ra = factors 32..35, rb = 36..39
+            sell_out4(o, 32 + 4 * (1 - (lane & 1)), k, rb, vec_ok);
         }
         s = sn;
         base = nbase;
         lim = nlim;
     }
+    if constexpr (MC) sell_mc_push(wd, out, ldo, k, gram_out, mc, next_slice + 1);
 }
 
 // =====================================================================================================

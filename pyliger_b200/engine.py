@@ -367,10 +367,11 @@ class InmfEngine(object):
 
     coalesce_allreduce = True
 
-    # Multi-GPU: pass 2 fused with the all-reduce of its outputs.  St / H'H live in symmetric memory bound to a multicast
-    # object of the NVLink switch; the pass adds every partial sum with multimem.red, so each rank's copy receives the
-    # sum over all ranks while the pass is still computing, and no NCCL collective follows (inmf_sell_pass_mc_f32).
-    # Falls back to pass + NCCL all-reduce where symmetric memory / multicast is not available.
+    # Multi-GPU: pass 2 fused with the all-reduce of its outputs (inmf_sell_pass_mc_f32).  The sums over the ranks,
+    # self.St / self.HtH, live in symmetric memory bound to a multicast object of the NVLink switch; the pass accumulates
+    # this rank's partial sums in St_part / HtH_part and the CTA that completes a (dataset, gene range) adds that range
+    # into every rank's copy with multimem.red while the rest of the pass is still running.  No NCCL collective
+    # follows.  Falls back to pass + NCCL all-reduce where symmetric memory / multicast is not available.
     fused_reduce = True
     mc = None
     fused_reduce_error = None
@@ -405,9 +406,18 @@ class InmfEngine(object):
         torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN, group=self.group)
         if int(flag.item()) != 1:  # all ranks or none
             return
+        self.St_part, self.HtH_part = self.St, self.HtH
         self.St = buf[:N * g * k * 4].view(torch.float32).view(N, g, k)
         self.HtH = buf[n_st:n_st + N * k * k * 8].view(torch.float64).view(N, k, k)
-        self.mc = (hdl, buf, mcp, mcp + n_st)
+        W = p.work_host.copy()
+        _, cid, expected = np.unique(W[:, 4] * (g + 1) + p.row_lo, return_inverse=True, return_counts=True)
+        W[:, 6] = cid
+        W[:, 7] = (p.row_lo.astype(np.int64) << 32) | p.row_hi.astype(np.int64)
+        work_mc = torch.from_numpy(W).to(dev)
+        expected_t = torch.from_numpy(expected.astype(np.int32)).to(dev)
+        counters = torch.zeros(len(expected), dtype=torch.int32, device=dev)
+        args = torch.tensor([mcp, mcp + n_st, counters.data_ptr(), expected_t.data_ptr()], dtype=torch.int64, device=dev)
+        self.mc = (hdl, buf, work_mc, args, (expected_t, counters))
 
     def _allreduce(self, *tensors):
         """SUM over the ranks.  Tensors of one dtype go out as ONE coalesced NCCL launch; different dtypes (fp32 St +
@@ -573,10 +583,12 @@ class InmfEngine(object):
             elif full and self.pass2 is not None:
                 p = self.pass2
                 if reduce and self.mc is not None and St is self.St and HtH is self.HtH:
-                    hdl, _, st_mc, hth_mc = self.mc
-                    hdl.barrier(channel=0)  # every rank's copy is zero before the first add arrives
-                    _lib.call("inmf_sell_pass_mc_f32", "", p.work, p.nwork, p.slice_ptr, p.rowid, p.pairs4, p.height, H,
-                              self.ldm, st_mc, k, k, p.max_tile_rows, hth_mc, _stream())
+                    hdl, _, work_mc, args = self.mc[:4]
+                    self.St_part.zero_()
+                    self.HtH_part.zero_()
+                    hdl.barrier(channel=0)  # every rank's sum buffer is zero before the first add arrives
+                    _lib.call("inmf_sell_pass_mc_f32", "", work_mc, p.nwork, p.slice_ptr, p.rowid, p.pairs4, p.height, H,
+                              self.ldm, self.St_part, k, p.max_tile_rows, self.HtH_part, args, _stream())
                     hdl.barrier(channel=1)  # every rank's adds have landed
                     return
                 self._blocked(p, p.work, p.nwork, H, St, k, HtH)
