@@ -291,6 +291,39 @@ def roofline_block(acc, ms_per_step, cells_local, nnz_local, k, esize, traffic_k
                      "frac": b_als * cells_local / (ms_per_step * 1e-3) / 1e9 / peak}}
 
 
+def fused_leg(ctx, mats, k, lam, state, steps, warmup, warm, cells_total, fused_on, acc_main):
+    """The same loop with the OTHER reduction mode (fused pass 2 + multimem.red when the headline used NCCL, and the
+    other way round), so both are measured in one run."""
+    import torch
+    from pyliger_b200.engine import InmfEngine
+    old = InmfEngine.fused_reduce
+    InmfEngine.fused_reduce = bool(fused_on)
+    try:
+        eng = InmfEngine(mats, k, lam, dtype=torch.float32, device=ctx.dev, presharded=ctx.world > 1)
+        if state is not None:
+            eng.set_als_state(*state)
+            eng.initial_objective()
+        else:
+            eng.draw_als_state(0, h_stream=ctx.rank if ctx.world > 1 else None)
+            eng.initial_objective()
+        ms, launches, objs = timed_als(ctx, eng, steps, warmup, warm, None)
+        acc = kernel_breakdown(eng, warm, 3)
+        out = {"what": "the same loop with fused_reduce=%s (pass 2 %s)" % (
+                   bool(fused_on), "adds finished gene ranges into every rank's sum buffer with multimem.red, two cross-rank "
+                   "barriers, no collective" if fused_on else "followed by an NCCL all-reduce"),
+               "active": eng.mc is not None, "error": eng.fused_reduce_error,
+               "value": cells_total * steps / (ms * 1e-3), "unit": "cell-iters/s", "ms_per_step": ms / steps,
+               "steps": steps, "warmup": warmup, "gpu_launches": int(launches),
+               "pass2_plus_reduction_ms": round(acc["pass2"] + acc["allreduce"], 4),
+               "other_mode_pass2_plus_reduction_ms": round(acc_main["pass2"] + acc_main["allreduce"], 4),
+               "last_objective": objs[-1] if objs else None}
+        del eng
+        torch.cuda.empty_cache()
+        return out
+    finally:
+        InmfEngine.fused_reduce = old
+
+
 def leg_c4(ctx, steps):
     """configs[3]: 8 x 250k cells x 5k genes, k = 40, the cells sharded over the ranks; data generated on the device."""
     import torch
@@ -325,7 +358,12 @@ def leg_c4(ctx, steps):
            "roofline": roofline_block(acc, ms_step, cells_local, nnz_local, k, 4, "C4"),
            "fused_reduce": eng.mc is not None,
            "bpp_H": eng.bpp_report()["H"], "seconds": {"generate": round(t_gen, 2), "setup": round(t_setup, 2)}}
-    del eng, mats
+    fused_main = eng.mc is not None
+    del eng
+    torch.cuda.empty_cache()
+    if ctx.world > 1 and ctx.fused_leg:
+        out["fused_reduce_leg"] = fused_leg(ctx, mats, k, lam, None, steps, 3, True, cells_total, not fused_main, acc)
+    del mats
     torch.cuda.empty_cache()
     return out
 
@@ -532,13 +570,14 @@ def main():
                     help="headline workload: C2 (default, weak scaling) or C4 (8 x 250k cells sharded over the ranks)")
     ap.add_argument("--cells", type=int, default=0, help="cells per dataset per GPU (default: the config's)")
     ap.add_argument("--graph", type=int, default=1, help="1: CUDA-graphed warm iterations (the engine default), 0: eager")
-    ap.add_argument("--fused-reduce", type=int, default=1,
-                    help="N > 1: 1 = pass 2 adds into multicast-bound symmetric buffers (no separate all-reduce; the "
-                         "engine default where the fabric supports it), 0 = pass 2 + NCCL all-reduce")
+    ap.add_argument("--fused-reduce", type=int, default=0,
+                    help="N > 1: 0 = pass 2 + NCCL all-reduce (the engine default), 1 = pass 2 adds its finished gene "
+                         "ranges into multicast-bound symmetric sum buffers (no separate all-reduce); the other mode is "
+                         "measured in extra.c2_fused_reduce / c4_strong.fused_reduce_leg")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline legs")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="headline only (skip the c2 cold / fp64, C3, C4, C5 legs)")
-    ap.add_argument("--extra", default="cold,mixed,f64,c4,c3,c5,parity", help="which extra legs to run")
+    ap.add_argument("--extra", default="cold,mixed,f64,c4,c3,c5,parity,fused", help="which extra legs to run")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -565,6 +604,7 @@ def main():
         torch.distributed.init_process_group("nccl", device_id=dev)
     ctx = Ctx()
     ctx.rank, ctx.world, ctx.dev, ctx.lib = rank, world, dev, _lib
+    ctx.fused_leg = "fused" in [e for e in args.extra.split(",") if e] and not args.no_extra
 
     def barrier():
         torch.cuda.synchronize()
@@ -645,6 +685,9 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "gpu_launches": int(launches_c)}
     del eng
     torch.cuda.empty_cache()
+    if world > 1 and "fused" in extras and args.dtype == "f32":
+        extra["c2_fused_reduce"] = fused_leg(ctx, mats, k, lam, (W0, V0, H0), args.steps, args.warmup, warm, cells_total,
+                                             not fused, acc)
     if "mixed" in extras and args.dtype == "f32" and k <= 32:
         engm = InmfEngine(mats, k, lam, dtype="mixed", device=dev, presharded=world > 1)
         engm.set_als_state(W0, V0, H0)

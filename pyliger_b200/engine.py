@@ -371,8 +371,11 @@ class InmfEngine(object):
     # self.St / self.HtH, live in symmetric memory bound to a multicast object of the NVLink switch; the pass accumulates
     # this rank's partial sums in St_part / HtH_part and the CTA that completes a (dataset, gene range) adds that range
     # into every rank's copy with multimem.red while the rest of the pass is still running.  No NCCL collective
-    # follows.  Falls back to pass + NCCL all-reduce where symmetric memory / multicast is not available.
-    fused_reduce = True
+    # follows.  Opt-in: measured on 2 GPUs it only matches pass 2 + NCCL all-reduce (C2 0.870 vs 0.861 ms per iteration:
+    # two cross-rank barriers and the extra clear cost what the collective's launch did), and with more than two ranks the
+    # switch applies the ranks' adds to each copy in arrival order, so the copies can differ in the last bit -- the
+    # objective is then taken from rank 0 (one 8-byte broadcast) to keep the ranks' stopping decisions identical.
+    fused_reduce = False
     mc = None
     fused_reduce_error = None
 
@@ -406,7 +409,9 @@ class InmfEngine(object):
         torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN, group=self.group)
         if int(flag.item()) != 1:  # all ranks or none
             return
-        self.St_part, self.HtH_part = self.St, self.HtH
+        part = torch.zeros(n_st + N * k * k * 8, dtype=torch.uint8, device=dev)  # one clear for both partial buffers
+        self.St_part = part[:N * g * k * 4].view(torch.float32).view(N, g, k)
+        self.HtH_part = part[n_st:n_st + N * k * k * 8].view(torch.float64).view(N, k, k)
         self.St = buf[:N * g * k * 4].view(torch.float32).view(N, g, k)
         self.HtH = buf[n_st:n_st + N * k * k * 8].view(torch.float64).view(N, k, k)
         W = p.work_host.copy()
@@ -417,7 +422,7 @@ class InmfEngine(object):
         expected_t = torch.from_numpy(expected.astype(np.int32)).to(dev)
         counters = torch.zeros(len(expected), dtype=torch.int32, device=dev)
         args = torch.tensor([mcp, mcp + n_st, counters.data_ptr(), expected_t.data_ptr()], dtype=torch.int64, device=dev)
-        self.mc = (hdl, buf, work_mc, args, (expected_t, counters))
+        self.mc = (hdl, buf, work_mc, args, part, (expected_t, counters))
 
     def _allreduce(self, *tensors):
         """SUM over the ranks.  Tensors of one dtype go out as ONE coalesced NCCL launch; different dtypes (fp32 St +
@@ -569,9 +574,19 @@ class InmfEngine(object):
         St = self.St if St is None else St
         HtH = self.HtH if HtH is None else HtH
         nseg = self.N if nseg is None else nseg
+        X, k = self.X, self.k
+        if full and reduce and self.mc is not None and St is self.St and HtH is self.HtH:
+            hdl, buf, work_mc, args, part = self.mc[:5]
+            p = self.pass2
+            part.zero_()
+            buf.zero_()
+            hdl.barrier(channel=0)  # every rank's sum buffer is zero before the first add arrives
+            _lib.call("inmf_sell_pass_mc_f32", "", work_mc, p.nwork, p.slice_ptr, p.rowid, p.pairs4, p.height, H,
+                      self.ldm, self.St_part, k, p.max_tile_rows, self.HtH_part, args, _stream())
+            hdl.barrier(channel=1)  # every rank's adds have landed
+            return
         St.zero_()
         HtH.zero_()
-        X, k = self.X, self.k
         if max_rows > 0:
             if full and self.tc2 is not None:
                 t = self.tc2
@@ -582,15 +597,6 @@ class InmfEngine(object):
                 _lib.call("inmf_gram_rows", self.sfx, H, self.ldm, self.seg_full, nseg, max_rows, HtH, k, _stream())
             elif full and self.pass2 is not None:
                 p = self.pass2
-                if reduce and self.mc is not None and St is self.St and HtH is self.HtH:
-                    hdl, _, work_mc, args = self.mc[:4]
-                    self.St_part.zero_()
-                    self.HtH_part.zero_()
-                    hdl.barrier(channel=0)  # every rank's sum buffer is zero before the first add arrives
-                    _lib.call("inmf_sell_pass_mc_f32", "", work_mc, p.nwork, p.slice_ptr, p.rowid, p.pairs4, p.height, H,
-                              self.ldm, self.St_part, k, p.max_tile_rows, self.HtH_part, args, _stream())
-                    hdl.barrier(channel=1)  # every rank's adds have landed
-                    return
                 self._blocked(p, p.work, p.nwork, H, St, k, HtH)
             else:
                 _lib.call("inmf_stats", self.sfx, X.rowptr, X.colidx, X.vals, H, self.ldm, St, HtH, self.g, seg_desc,
@@ -689,6 +695,9 @@ class InmfEngine(object):
         finally:
             if self.deterministic:
                 _lib.load().inmf_set_deterministic(prev)
+        if self.mc is not None and self.world > 2:  # the ranks' copies of the sums may differ in the last bit
+            torch.distributed.broadcast(self.obj, src=torch.distributed.get_global_rank(self.group, 0)
+                                        if self.group is not None else 0, group=self.group)
         return self.obj
 
     # ------------------------------------------------------------------ ALS
