@@ -694,34 +694,50 @@ extern "C" int32_t inmf_sqnorm_f64(const int64_t* rowptr, const double* vals, co
 // =================================================================================================
 // V / W right-hand sides from statistics (warp per gene)
 // =================================================================================================
-// out[lane], out[lane+32] of  row(1 x k) * C(k x k)   with row distributed over lanes.
+// out[lane], out[lane+32] of  row(1 x k) * C(k x k)   with row distributed over lanes; C staged in shared memory as T
+// (the global fp64 matrix was read once per gene before: 19 / 34 us per call at C2 for a few hundred thousand FMAs).
 template <typename T>
-__device__ __forceinline__ void row_times_sym(const double* __restrict__ C, int k, T v0, T v1, T& o0, T& o1) {
+__device__ __forceinline__ void row_times_sym(const T* __restrict__ C, int k, T v0, T v1, T& o0, T& o1) {
     const int lane = threadIdx.x & 31;
+    const int c0 = lane < k ? lane : 0, c1 = lane + 32 < k ? lane + 32 : 0;
     T a0 = T(0), a1 = T(0);
-    for (int a = 0; a < k; ++a) {
-        const T va = __shfl_sync(INMF_FULL_MASK, (a < 32) ? v0 : v1, a & 31);
-        if (lane < k) a0 += va * (T)C[(size_t)a * k + lane];
-        if (lane + 32 < k) a1 += va * (T)C[(size_t)a * k + lane + 32];
+    const int k32 = k < 32 ? k : 32;
+#pragma unroll 4
+    for (int a = 0; a < k32; ++a) {
+        const T va = __shfl_sync(INMF_FULL_MASK, v0, a);
+        a0 = fma(va, C[a * k + c0], a0);
+        if (k > 32) a1 = fma(va, C[a * k + c1], a1);
+    }
+    for (int a = 32; a < k; ++a) {
+        const T va = __shfl_sync(INMF_FULL_MASK, v1, a - 32);
+        a0 = fma(va, C[a * k + c0], a0);
+        a1 = fma(va, C[a * k + c1], a1);
     }
     o0 = a0;
     o1 = a1;
 }
 
 template <typename T>
-__global__ void rhs_v_kernel(const T* __restrict__ St, const T* __restrict__ Wt, const double* __restrict__ HtH,
-                             T* __restrict__ Rv, double* __restrict__ Gv, double lambda, int64_t g, int k) {
+__global__ void __launch_bounds__(256) rhs_v_kernel(const T* __restrict__ St, const T* __restrict__ Wt,
+                                                    const double* __restrict__ HtH, T* __restrict__ Rv,
+                                                    double* __restrict__ Gv, double lambda, int64_t g, int k) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    T* Cs = reinterpret_cast<T*>(smem_raw);
     const int s = blockIdx.y;
     const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const double* C = HtH + (size_t)s * k * k;
-    if (blockIdx.x == 0)
-        for (int t = threadIdx.x; t < k * k; t += blockDim.x) Gv[(size_t)s * k * k + t] = (1.0 + lambda) * C[t];
+    for (int t = threadIdx.x; t < k * k; t += blockDim.x) {
+        const double c = C[t];
+        Cs[t] = (T)c;
+        if (blockIdx.x == 0) Gv[(size_t)s * k * k + t] = (1.0 + lambda) * c;
+    }
+    __syncthreads();
     for (int64_t c = (int64_t)blockIdx.x * nwarps + warp; c < g; c += (int64_t)gridDim.x * nwarps) {
         const T* w = Wt + c * k;
         const T w0 = (lane < k) ? w[lane] : T(0);
         const T w1 = (lane + 32 < k) ? w[lane + 32] : T(0);
         T o0, o1;
-        row_times_sym<T>(C, k, w0, w1, o0, o1);
+        row_times_sym<T>(Cs, k, w0, w1, o0, o1);
         const T* sr = St + ((size_t)s * g + c) * k;
         T* out = Rv + ((size_t)s * g + c) * k;
         if (lane < k) out[lane] = sr[lane] - o0;
@@ -729,31 +745,57 @@ __global__ void rhs_v_kernel(const T* __restrict__ St, const T* __restrict__ Wt,
     }
 }
 
+// CS_SMEM: all nseg matrices fit in shared memory; otherwise they are staged one dataset at a time.
 template <typename T>
-__global__ void rhs_w_kernel(const T* __restrict__ St, const T* __restrict__ Vt, const double* __restrict__ HtH,
-                             T* __restrict__ Rw, double* __restrict__ Gw, int nseg, int64_t g, int k) {
+__global__ void __launch_bounds__(256) rhs_w_kernel(const T* __restrict__ St, const T* __restrict__ Vt,
+                                                    const double* __restrict__ HtH, T* __restrict__ Rw,
+                                                    double* __restrict__ Gw, int nseg, int64_t g, int k, int stage) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    T* Cs = reinterpret_cast<T*>(smem_raw);
     const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kk = k * k;
     if (blockIdx.x == 0)
-        for (int t = threadIdx.x; t < k * k; t += blockDim.x) {
+        for (int t = threadIdx.x; t < kk; t += blockDim.x) {
             double acc = 0.0;
-            for (int s = 0; s < nseg; ++s) acc += HtH[(size_t)s * k * k + t];
+            for (int s = 0; s < nseg; ++s) acc += HtH[(size_t)s * kk + t];
             Gw[t] = acc;
         }
-    for (int64_t c = (int64_t)blockIdx.x * nwarps + warp; c < g; c += (int64_t)gridDim.x * nwarps) {
-        T r0 = T(0), r1 = T(0);
-        for (int s = 0; s < nseg; ++s) {
-            const T* v = Vt + ((size_t)s * g + c) * k;
-            const T v0 = (lane < k) ? v[lane] : T(0);
-            const T v1 = (lane + 32 < k) ? v[lane + 32] : T(0);
-            T o0, o1;
-            row_times_sym<T>(HtH + (size_t)s * k * k, k, v0, v1, o0, o1);
-            const T* sr = St + ((size_t)s * g + c) * k;
-            if (lane < k) r0 += sr[lane] - o0;
-            if (lane + 32 < k) r1 += sr[lane + 32] - o1;
+    // every warp keeps the partial sums of its genes in registers across the staging rounds (GENES_PER_WARP each)
+    constexpr int GPW = 4;
+    const int64_t per_cta = (int64_t)nwarps * GPW;
+    for (int64_t base = (int64_t)blockIdx.x * per_cta; base < g; base += (int64_t)gridDim.x * per_cta) {
+        T r0[GPW], r1[GPW];
+#pragma unroll
+        for (int u = 0; u < GPW; ++u) r0[u] = r1[u] = T(0);
+        for (int s0 = 0; s0 < nseg; s0 += stage) {
+            const int ns = (nseg - s0 < stage) ? (nseg - s0) : stage;
+            __syncthreads();
+            for (int t = threadIdx.x; t < ns * kk; t += blockDim.x) Cs[t] = (T)HtH[(size_t)s0 * kk + t];
+            __syncthreads();
+#pragma unroll
+            for (int u = 0; u < GPW; ++u) {
+                const int64_t c = base + (int64_t)warp * GPW + u;
+                if (c >= g) continue;  // (warp-uniform)
+                for (int s = 0; s < ns; ++s) {
+                    const T* v = Vt + ((size_t)(s0 + s) * g + c) * k;
+                    const T v0 = (lane < k) ? v[lane] : T(0);
+                    const T v1 = (lane + 32 < k) ? v[lane + 32] : T(0);
+                    T o0, o1;
+                    row_times_sym<T>(Cs + (size_t)s * kk, k, v0, v1, o0, o1);
+                    const T* sr = St + ((size_t)(s0 + s) * g + c) * k;
+                    if (lane < k) r0[u] += sr[lane] - o0;
+                    if (lane + 32 < k) r1[u] += sr[lane + 32] - o1;
+                }
+            }
         }
-        T* out = Rw + c * k;
-        if (lane < k) out[lane] = r0;
-        if (lane + 32 < k) out[lane + 32] = r1;
+#pragma unroll
+        for (int u = 0; u < GPW; ++u) {
+            const int64_t c = base + (int64_t)warp * GPW + u;
+            if (c >= g) continue;
+            T* out = Rw + c * k;
+            if (lane < k) out[lane] = r0[u];
+            if (lane + 32 < k) out[lane + 32] = r1[u];
+        }
     }
 }
 
@@ -761,10 +803,10 @@ template <typename T>
 static int32_t rhs_v_launch(const T* St, const T* Wt, const double* HtH, T* Rv, double* Gv, double lambda,
                             int32_t nseg, int64_t g, int32_t k, void* stream) {
     INMF_REQUIRE(k >= 1 && k <= INMF_MAX_K && nseg >= 1 && g >= 1, "bad shape");
-    int64_t blocks = (g + 7) / 8;
+    int64_t blocks = (g + 31) / 32;  // four genes per warp: the staging of C is amortised
     if (blocks > inmf_num_sms() * 8) blocks = inmf_num_sms() * 8;
-    rhs_v_kernel<T><<<dim3((unsigned)blocks, (unsigned)nseg), 256, 0, (cudaStream_t)stream>>>(St, Wt, HtH, Rv, Gv,
-                                                                                               lambda, g, k);
+    rhs_v_kernel<T><<<dim3((unsigned)blocks, (unsigned)nseg), 256, (size_t)k * k * sizeof(T), (cudaStream_t)stream>>>(
+        St, Wt, HtH, Rv, Gv, lambda, g, k);
     INMF_LAUNCH_CHECK();
     return 0;
 }
@@ -772,9 +814,14 @@ template <typename T>
 static int32_t rhs_w_launch(const T* St, const T* Vt, const double* HtH, T* Rw, double* Gw, int32_t nseg,
                             int64_t g, int32_t k, void* stream) {
     INMF_REQUIRE(k >= 1 && k <= INMF_MAX_K && nseg >= 1 && g >= 1, "bad shape");
-    int64_t blocks = (g + 7) / 8;
+    int64_t blocks = (g + 31) / 32;
     if (blocks > inmf_num_sms() * 8) blocks = inmf_num_sms() * 8;
-    rhs_w_kernel<T><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(St, Vt, HtH, Rw, Gw, nseg, g, k);
+    int stage = (int)((size_t)(64 * 1024) / ((size_t)k * k * sizeof(T)));  // datasets staged at a time (<= 64 KB)
+    if (stage < 1) stage = 1;
+    if (stage > nseg) stage = nseg;
+    const size_t smem = (size_t)stage * k * k * sizeof(T);
+    INMF_OPTIN_SMEM((rhs_w_kernel<T>), 64 * 1024);
+    rhs_w_kernel<T><<<(unsigned)blocks, 256, smem, (cudaStream_t)stream>>>(St, Vt, HtH, Rw, Gw, nseg, g, k, stage);
     INMF_LAUNCH_CHECK();
     return 0;
 }

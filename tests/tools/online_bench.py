@@ -115,7 +115,11 @@ def main():
             else:
                 eng.rhs_H(seg_desc=plan[it], max_rows=eng.max_sub, out=eng.H_mb)
             ev[2].record(); eng.bpp_H(seg_desc=plan[it], max_rows=eng.max_sub, out=eng.H_mb)
-            ev[3].record(); eng.stats(seg_desc=plan[it], max_rows=eng.max_sub, H=eng.H_mb, St=eng.XHt, HtH=eng.HHt)
+            ev[3].record()
+            if eng.win2 is not None:  # the block-aligned window pass the real step uses
+                eng.stats_window(it)
+            else:
+                eng.stats(seg_desc=plan[it], max_rows=eng.max_sub, H=eng.H_mb, St=eng.XHt, HtH=eng.HHt)
             ev[4].record()
             _lib.call("inmf_update_ab", eng.sfx, eng.A, eng.A_old, eng.B, eng.B_old, eng.HHt, eng.XHt, eng.inv_mb,
                       0.5, 0, eng.N, eng.g, eng.k, _stream())
