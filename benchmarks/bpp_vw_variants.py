@@ -65,6 +65,22 @@ def main():
     eng.bpp_stats.zero_()
     eng.solve_V(warm=True)
     out["V_report"] = eng.bpp_report()["V"]
+    eng.bpp_stats.zero_()
+    eng.solve_W(warm=True)
+    out["W_report"] = eng.bpp_report()["W"]
+    out["W_passive_mean"] = float((eng.Wt > 0).sum().item()) / eng.Wt.shape[0]
+    out["V_passive_mean"] = float((eng.Vt > 0).sum().item()) / (eng.Vt.shape[0] * eng.Vt.shape[1])
+    # latency of the W solve against the number of columns (is it one column's latency?)
+    import types
+    for frac in (1.0, 0.25):
+        gsub = int(eng.g * frac)
+        seg = torch.tensor([0, gsub], dtype=torch.int64, device=dev)
+        def solve_sub():
+            _lib.call("inmf_bpp", eng.sfx, eng.Gw, eng.Rw, k, eng.Wt, k, None, 0, eng.mask_W, eng._vw(True), seg, 1, gsub, k,
+                      eng.bpp_stats[2], *_lib.ws_args(eng.ws_W), _stream())
+        out["W_bpp_only_%d_cols" % gsub] = timed(solve_sub)
+    out["rhs_w_only"] = timed(lambda: _lib.call("inmf_rhs_w", eng.sfx, eng.St, eng.Vt, eng.HtH, eng.Rw, eng.Gw, eng.N, eng.g, k, _stream()))
+    out["rhs_v_only"] = timed(lambda: _lib.call("inmf_rhs_v", eng.sfx, eng.St, eng.Wt, eng.HtH, eng.Rv, eng.Gv, eng.lam, eng.N, eng.g, k, _stream()))
     print(json.dumps(out))
 
 

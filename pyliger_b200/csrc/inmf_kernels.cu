@@ -106,16 +106,40 @@ __global__ void __launch_bounds__(BPP_THREADS, COMP ? BPP_COMP_MIN_BLOCKS : BPP_
     const int lane = threadIdx.x & 31;
     if ((int64_t)blockIdx.x * nwarps >= ncols) return;
 
+    // the first column's right-hand side and start set are requested before the staging of G, and every next column's
+    // before the current one is solved: the global-load latency otherwise sits in front of every column
+    const int64_t stride = (int64_t)gridDim.x * nwarps;
+    int64_t c = (int64_t)blockIdx.x * nwarps + warp;
+    int64_t col_n = 0;
+    T r0_n = T(0), r1_n = T(0);
+    uint64_t P_n = 0ull;
+    auto fetch = [&](int64_t cc) {
+        col_n = c_begin + (list ? (int64_t)list[(size_t)seg * list_cap + cc] : cc);
+        const T* r = R + col_n * ldr;
+        r0_n = (lane < k) ? r[lane] : T(0);
+        r1_n = (lane + 32 < k) ? r[lane + 32] : T(0);
+        P_n = ((warm & 1) && mask) ? mask[col_n] : 0ull;
+    };
+    if (c < ncols) fetch(c);
+
     const int ldg = k | 1;
     T* Gs = smem;
     const double* Gseg = G + (size_t)seg * k * k;
-    for (int t = threadIdx.x; t < k * k; t += blockDim.x) Gs[(t / k) * ldg + (t % k)] = (T)Gseg[t];
+#pragma unroll 4
+    for (int row = warp; row < k; row += nwarps) {
+        if (lane < k) Gs[row * ldg + lane] = (T)Gseg[row * k + lane];
+        if (lane + 32 < k) Gs[row * ldg + lane + 32] = (T)Gseg[row * k + lane + 32];
+    }
     size_t goff = ((size_t)k * ldg + 3) & ~(size_t)3;
     const T* Gis = nullptr;  // shared copy of G^-1 (full-passive-set solve), if provided and valid
     if (Ginv != nullptr) {
         const double* Iseg = Ginv + (size_t)seg * k * k;
         T* Gi = smem + goff;
-        for (int t = threadIdx.x; t < k * k; t += blockDim.x) Gi[(t / k) * ldg + (t % k)] = (T)Iseg[t];
+#pragma unroll 4
+        for (int row = warp; row < k; row += nwarps) {
+            if (lane < k) Gi[row * ldg + lane] = (T)Iseg[row * k + lane];
+            if (lane + 32 < k) Gi[row * ldg + lane + 32] = (T)Iseg[row * k + lane + 32];
+        }
         if (Iseg[0] == Iseg[0]) Gis = Gi;
         goff *= 2;
     }
@@ -125,12 +149,11 @@ __global__ void __launch_bounds__(BPP_THREADS, COMP ? BPP_COMP_MIN_BLOCKS : BPP_
     __syncwarp();
 
     long long n_notconv = 0, n_fact = 0, n_backup = 0, n_fail = 0, n_rounds = 0, max_rounds = 0, n_cols = 0;
-    for (int64_t c = (int64_t)blockIdx.x * nwarps + warp; c < ncols; c += (int64_t)gridDim.x * nwarps) {
-        const int64_t col = c_begin + (list ? (int64_t)list[(size_t)seg * list_cap + c] : c);
-        const T* r = R + col * ldr;
-        const T r0 = (lane < k) ? r[lane] : T(0);
-        const T r1 = (lane + 32 < k) ? r[lane + 32] : T(0);
-        uint64_t P = ((warm & 1) && mask) ? mask[col] : 0ull;
+    for (; c < ncols; c += stride) {
+        const int64_t col = col_n;
+        const T r0 = r0_n, r1 = r1_n;
+        uint64_t P = P_n;
+        if (c + stride < ncols) fetch(c + stride);
         T x0, x1, y0, y1;
         BppCounters cnt = {0, 0, 0, 0, true, {0, 0, 0, 0, 0, 0}};
         bpp_column<T, COMP>(Gs, Gis, ldg, sc, k, r0, r1, P, (warm & 1) != 0, (warm & 2) != 0, x0, x1, y0, y1, cnt);
@@ -323,8 +346,13 @@ static int32_t bpp_launch(const double* G, const T* R, int64_t ldr, T* X, int64_
     INMF_OPTIN_SMEM((bpp_kernel<T, true>), 227 * 1024);
     // Grid: about two waves of resident CTAs over ALL segments, each warp striding over its share of the columns,
     // so that the per-CTA staging of G (and G^-1) into shared memory is amortised over many columns.
+    // Small batches (the gene-side solves: a few columns per warp) get ONE wave: with two, half of the CTAs stage G only
+    // after the first half has finished, and the staging is as long as the few columns a warp then solves (ncu, C2 V
+    // solve, 12 000 columns: 22 % of the stall samples on the fp64 -> T conversion of the staged G).
     int64_t blocks = (max_seg_cols + nwarps - 1) / nwarps;
-    int64_t cap = ((int64_t)inmf_num_sms() * 2 * BPP_MIN_BLOCKS + nseg - 1) / nseg;
+    const int64_t one_wave = (int64_t)inmf_num_sms() * BPP_MIN_BLOCKS;
+    const int waves = ((int64_t)nseg * max_seg_cols >= one_wave * nwarps * 16) ? 2 : 1;
+    int64_t cap = (one_wave * waves + nseg - 1) / nseg;
     if (cap < 1) cap = 1;
     if (blocks > cap) blocks = cap;
     if (ginv_ws != nullptr) {
