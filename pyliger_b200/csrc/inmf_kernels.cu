@@ -773,7 +773,9 @@ __global__ void __launch_bounds__(256) rhs_v_kernel(const T* __restrict__ St, co
     }
 }
 
-// CS_SMEM: all nseg matrices fit in shared memory; otherwise they are staged one dataset at a time.
+// One gene per warp; the H'H of up to `stage` datasets are staged in shared memory at a time, and a gene's rows of
+// V_s / St_s for all staged datasets are requested before any of them is used (the loads are independent).
+#define RHS_W_MAX_STAGE 8
 template <typename T>
 __global__ void __launch_bounds__(256) rhs_w_kernel(const T* __restrict__ St, const T* __restrict__ Vt,
                                                     const double* __restrict__ HtH, T* __restrict__ Rw,
@@ -782,47 +784,45 @@ __global__ void __launch_bounds__(256) rhs_w_kernel(const T* __restrict__ St, co
     T* Cs = reinterpret_cast<T*>(smem_raw);
     const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kk = k * k;
-    if (blockIdx.x == 0)
+    if (blockIdx.x == gridDim.x - 1)  // (the last CTA has the fewest genes)
         for (int t = threadIdx.x; t < kk; t += blockDim.x) {
             double acc = 0.0;
             for (int s = 0; s < nseg; ++s) acc += HtH[(size_t)s * kk + t];
             Gw[t] = acc;
         }
-    // every warp keeps the partial sums of its genes in registers across the staging rounds (GENES_PER_WARP each)
-    constexpr int GPW = 4;
-    const int64_t per_cta = (int64_t)nwarps * GPW;
-    for (int64_t base = (int64_t)blockIdx.x * per_cta; base < g; base += (int64_t)gridDim.x * per_cta) {
-        T r0[GPW], r1[GPW];
-#pragma unroll
-        for (int u = 0; u < GPW; ++u) r0[u] = r1[u] = T(0);
+    const bool has0 = lane < k, has1 = lane + 32 < k;
+    for (int64_t base = (int64_t)blockIdx.x * nwarps; base < g; base += (int64_t)gridDim.x * nwarps) {
+        const int64_t c = base + warp;
+        T r0 = T(0), r1 = T(0);
         for (int s0 = 0; s0 < nseg; s0 += stage) {
             const int ns = (nseg - s0 < stage) ? (nseg - s0) : stage;
+            T v0[RHS_W_MAX_STAGE], v1[RHS_W_MAX_STAGE], q0[RHS_W_MAX_STAGE], q1[RHS_W_MAX_STAGE];
+#pragma unroll
+            for (int s = 0; s < RHS_W_MAX_STAGE; ++s) {
+                v0[s] = v1[s] = q0[s] = q1[s] = T(0);
+                if (s < ns && c < g) {
+                    const size_t o = ((size_t)(s0 + s) * g + c) * k;
+                    if (has0) { v0[s] = Vt[o + lane]; q0[s] = St[o + lane]; }
+                    if (has1) { v1[s] = Vt[o + lane + 32]; q1[s] = St[o + lane + 32]; }
+                }
+            }
             __syncthreads();
             for (int t = threadIdx.x; t < ns * kk; t += blockDim.x) Cs[t] = (T)HtH[(size_t)s0 * kk + t];
             __syncthreads();
 #pragma unroll
-            for (int u = 0; u < GPW; ++u) {
-                const int64_t c = base + (int64_t)warp * GPW + u;
-                if (c >= g) continue;  // (warp-uniform)
-                for (int s = 0; s < ns; ++s) {
-                    const T* v = Vt + ((size_t)(s0 + s) * g + c) * k;
-                    const T v0 = (lane < k) ? v[lane] : T(0);
-                    const T v1 = (lane + 32 < k) ? v[lane + 32] : T(0);
+            for (int s = 0; s < RHS_W_MAX_STAGE; ++s) {
+                if (s < ns) {
                     T o0, o1;
-                    row_times_sym<T>(Cs + (size_t)s * kk, k, v0, v1, o0, o1);
-                    const T* sr = St + ((size_t)(s0 + s) * g + c) * k;
-                    if (lane < k) r0[u] += sr[lane] - o0;
-                    if (lane + 32 < k) r1[u] += sr[lane + 32] - o1;
+                    row_times_sym<T>(Cs + (size_t)s * kk, k, v0[s], v1[s], o0, o1);
+                    r0 += q0[s] - o0;
+                    r1 += q1[s] - o1;
                 }
             }
         }
-#pragma unroll
-        for (int u = 0; u < GPW; ++u) {
-            const int64_t c = base + (int64_t)warp * GPW + u;
-            if (c >= g) continue;
+        if (c < g) {
             T* out = Rw + c * k;
-            if (lane < k) out[lane] = r0[u];
-            if (lane + 32 < k) out[lane + 32] = r1[u];
+            if (has0) out[lane] = r0;
+            if (has1) out[lane + 32] = r1;
         }
     }
 }
@@ -831,7 +831,7 @@ template <typename T>
 static int32_t rhs_v_launch(const T* St, const T* Wt, const double* HtH, T* Rv, double* Gv, double lambda,
                             int32_t nseg, int64_t g, int32_t k, void* stream) {
     INMF_REQUIRE(k >= 1 && k <= INMF_MAX_K && nseg >= 1 && g >= 1, "bad shape");
-    int64_t blocks = (g + 31) / 32;  // four genes per warp: the staging of C is amortised
+    int64_t blocks = (g + 15) / 16;  // two genes per warp: the staging of C is amortised, the loads stay parallel
     if (blocks > inmf_num_sms() * 8) blocks = inmf_num_sms() * 8;
     rhs_v_kernel<T><<<dim3((unsigned)blocks, (unsigned)nseg), 256, (size_t)k * k * sizeof(T), (cudaStream_t)stream>>>(
         St, Wt, HtH, Rv, Gv, lambda, g, k);
@@ -842,10 +842,11 @@ template <typename T>
 static int32_t rhs_w_launch(const T* St, const T* Vt, const double* HtH, T* Rw, double* Gw, int32_t nseg,
                             int64_t g, int32_t k, void* stream) {
     INMF_REQUIRE(k >= 1 && k <= INMF_MAX_K && nseg >= 1 && g >= 1, "bad shape");
-    int64_t blocks = (g + 31) / 32;
+    int64_t blocks = (g + 7) / 8;
     if (blocks > inmf_num_sms() * 8) blocks = inmf_num_sms() * 8;
     int stage = (int)((size_t)(64 * 1024) / ((size_t)k * k * sizeof(T)));  // datasets staged at a time (<= 64 KB)
     if (stage < 1) stage = 1;
+    if (stage > RHS_W_MAX_STAGE) stage = RHS_W_MAX_STAGE;
     if (stage > nseg) stage = nseg;
     const size_t smem = (size_t)stage * k * k * sizeof(T);
     INMF_OPTIN_SMEM((rhs_w_kernel<T>), 64 * 1024);
