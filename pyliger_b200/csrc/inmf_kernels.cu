@@ -40,50 +40,57 @@ extern "C" const char* inmf_last_error(void) { return g_inmf_err; }
 // rcond_min times the largest diagonal entry (the Gauss-Jordan pivots of an SPD matrix are its successive Schur
 // complements: a cheap conditioning proxy) marks the inverse invalid (NaN in element 0) and the solver falls
 // back to the Cholesky paths, whose accuracy depends on cond(G_PP) only.
-// Two barriers per elimination step: every thread first READS what its elements need from the unmodified matrix
-// (a[i][p], a[p][j], a[p][p]), then all write.  Up to 4 elements per thread (k*k <= 4096, 1024 threads).
+// Every thread keeps its (up to 4) elements in registers; an elimination step only needs row p and column p of the
+// current matrix, which their owners publish (double-buffered) while they compute step p - 1: one barrier per step.
 __global__ void __launch_bounds__(1024) ginv_kernel(const double* __restrict__ G, double* __restrict__ Ginv, int k,
                                                     double rcond_min) {
-    extern __shared__ double ginv_a[];
+    __shared__ double rowbuf[2][INMF_MAX_K], colbuf[2][INMF_MAX_K], diag[INMF_MAX_K];
     const int seg = blockIdx.x;
     const int t = threadIdx.x, nt = blockDim.x;
     const int kk = k * k;
     int ei[4], ej[4];
+    double a[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
         const int e = t + u * nt;
         ei[u] = e < kk ? e / k : -1;
         ej[u] = e < kk ? e - (e / k) * k : 0;
+        a[u] = e < kk ? G[(size_t)seg * kk + e] : 0.0;
+        if (ei[u] >= 0) {
+            if (ei[u] == ej[u]) diag[ei[u]] = a[u];
+            if (ei[u] == 0) rowbuf[0][ej[u]] = a[u];
+            if (ej[u] == 0) colbuf[0][ei[u]] = a[u];
+        }
     }
-    for (int e = t; e < kk; e += nt) ginv_a[e] = G[(size_t)seg * kk + e];
     __syncthreads();
     double dmax = 0.0;
-    for (int p = 0; p < k; ++p) dmax = fmax(dmax, ginv_a[p * k + p]);
+    for (int p = 0; p < k; ++p) dmax = fmax(dmax, diag[p]);
     const double floor_piv = rcond_min * dmax;
     bool ok = true;
     for (int p = 0; p < k; ++p) {
-        const double piv = ginv_a[p * k + p];  // uniform: all threads see the same value, so the break is too
+        const int b = p & 1;
+        const double piv = rowbuf[b][p];  // uniform: all threads see the same value, so the break is too
         if (!(piv > floor_piv)) {
             ok = false;
             break;
         }
         const double rp = 1.0 / piv;
-        double nv[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int i = ei[u], j = ej[u];
             if (i < 0) continue;
-            const double prow = ((j == p) ? 1.0 : ginv_a[p * k + j]) * rp;
-            nv[u] = (i == p) ? prow : ((j == p) ? 0.0 : ginv_a[i * k + j]) - ginv_a[i * k + p] * prow;
+            const double prow = ((j == p) ? 1.0 : rowbuf[b][j]) * rp;
+            const double nv = (i == p) ? prow : ((j == p) ? 0.0 : a[u]) - colbuf[b][i] * prow;
+            a[u] = nv;
+            if (i == p + 1) rowbuf[b ^ 1][j] = nv;
+            if (j == p + 1) colbuf[b ^ 1][i] = nv;
         }
         __syncthreads();
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-            if (ei[u] >= 0) ginv_a[ei[u] * k + ej[u]] = nv[u];
-        __syncthreads();
     }
-    for (int e = t; e < kk; e += nt)
-        Ginv[(size_t)seg * kk + e] = ok ? ginv_a[e] : __longlong_as_double(0x7ff8000000000000ll);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+        if (ei[u] >= 0)
+            Ginv[(size_t)seg * kk + t + u * nt] = ok ? a[u] : __longlong_as_double(0x7ff8000000000000ll);
 }
 
 // COMP kernels (k > 31) are limited to <= 5 CTAs per SM by their shared-memory scratch anyway: give them the registers.
@@ -358,7 +365,7 @@ static int32_t bpp_launch(const double* G, const T* R, int64_t ldr, T* X, int64_
     if (ginv_ws != nullptr) {
         // the inverse is used in T arithmetic: accept it only while cond(G) * eps(T) stays small
         const double rcond_min = sizeof(T) == 4 ? 1e-4 : 1e-10;
-        ginv_kernel<<<(unsigned)nseg, 1024, (size_t)k * k * sizeof(double), st>>>(G, ginv_ws, k, rcond_min);
+        ginv_kernel<<<(unsigned)nseg, 1024, 0, st>>>(G, ginv_ws, k, rcond_min);
         INMF_LAUNCH_CHECK();
     }
     const bool comp_kernel = k > BPP_FAST_MAX_P || ((warm & 2) && ginv_ws != nullptr);
