@@ -391,11 +391,9 @@ static int32_t bpp_launch(const double* G, const T* R, int64_t ldr, T* X, int64_
         else rc = bpp16_launch_one<T, 4>(INMF_BPP16_ARGS);
 #undef INMF_BPP16_ARGS
         if (rc != 0) return rc;
-        // the deferred columns: a small grid is enough (usually none); CTAs without work leave at once
-        int64_t lblocks = blocks;
-        const int64_t lcap = ((int64_t)inmf_num_sms() * 2 + nseg - 1) / nseg;
-        if (lblocks > lcap) lblocks = lcap;
-        blocks = lblocks;
+        // the deferred columns: the same grid as a full solve -- CTAs without work leave at once, before staging G, and
+        // at k = 40 a real warm-started H solve defers a quarter of its columns (C4: 0.78 M of 2.75 M), which a small
+        // grid (2 CTAs per SM) solved at a third of the kernel's throughput
     }
     dim3 grid((unsigned)blocks, (unsigned)nseg);
     if (comp_kernel)
