@@ -12,7 +12,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT, PROF = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
-OURS = re.compile(r"sell(32h?)?_(pass|fill|fill_parity)_kernel|bpp16_kernel|to_bf16_(rows|gram)_kernel|reduce_parts_kernel|"
+OURS = re.compile(r"sell(32[hr]?)?_(pass|fill|fill_parity|fill_residue)_kernel|hals_grouped_kernel|bpp16_kernel|to_bf16_(rows|gram)_kernel|reduce_parts_kernel|"
                   r"hals_h_kernel|qn_\w+_kernel|"
                   r"blocked_(spmm|split|wide)_kernel|bpp_kernel|ginv_kernel|rhs_[vw]_kernel|prep_kernel|objective_kernel|"
                   r"sqnorm_kernel|combine_g_kernel|blockfmt[12]_kernel|mt19937_uniform_kernel|gram_rows_kernel|"
@@ -58,9 +58,18 @@ def launches():
     print("\n".join(out))
 
 
+def _summary(stem):
+    """Text summary of gpurun_out/<stem>.ncu-rep: made on the GPU box (<stem>.summary.txt, the reports are too large to
+    travel back) or here when the report itself is present."""
+    txt, rep = os.path.join(OUT, stem + ".summary.txt"), os.path.join(OUT, stem + ".ncu-rep")
+    if os.path.exists(rep):
+        return subprocess.run([sys.executable, os.path.join(ROOT, "benchmarks", "ncu_summary.py"), rep],
+                              capture_output=True, text=True).stdout
+    return open(txt).read() if os.path.exists(txt) else ""
+
+
 def full():
-    body = subprocess.run([sys.executable, os.path.join(ROOT, "benchmarks", "ncu_summary.py"),
-                           os.path.join(OUT, "r2_prof.ncu-rep")], capture_output=True, text=True).stdout
+    body = _summary("r2_prof")
     hdr = ("# Round 2 (final build): ncu --set full --clock-control none --import-source on "
            "-k 'regex:sell32_pass|bpp16_kernel' -s 13 -c 3 -- python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e "
            "--no-extra --graph 0\n"
@@ -82,6 +91,25 @@ def full():
     print(hdr + body[:3000])
 
 
+def extra_reports():
+    for rep, dst, hdr in (
+            ("r2_prof_c4.ncu-rep", "r2_ncu_c4_passes.txt",
+             "# Round 2 (final build): ncu --set full --clock-control none -k regex:sell32r_pass -s 4 -c 2 -- python "
+             "benchmarks/pass_variants.py --config C4 --variants sell\n# the one-lane-per-row kernel for 32 < k <= 40 "
+             "([rows x 32] + [rows x 8] tile, residue-ordered non-zeros) on a C4 slice (250 k cells x 5 k genes, k = 40): "
+             "pass 1 then pass 2\n"),
+            ("r2_prof_online.ncu-rep", "r2_ncu_online.txt",
+             "# Round 2 (final build): ncu --set full --clock-control none -k 'regex:hals_grouped|sell32r_pass|blocked_split' "
+             "-s 12 -c 3 -- python tests/tools/online_bench.py --cells 10000 --cpu-cells 0\n# kernels of one online_iNMF "
+             "mini-batch step at the C3 shape (8 datasets, 5 k genes, k = 40, 5 000-cell mini-batches): window right-hand "
+             "sides, block-aligned window statistics, grouped HALS sweep (whichever three launches come first after the skip)\n")):
+        body = _summary(rep[:-len(".ncu-rep")])
+        if not body:
+            continue
+        open(os.path.join(PROF, dst), "w").write(hdr + body)
+        print(hdr + body[:1500])
+
+
 def copies():
     for src, dst in (("r2_bench_n1.json", "r2_bench_n1.json"), ("r2_bench_ref.json", "r2_bench_reference_arm.json"),
                      ("r2_bench_n2.json", "r2_bench_n2.json"), ("r2_bench_n8.json", "r2_bench_n8.json")):
@@ -93,6 +121,6 @@ def copies():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["launches", "full", "copies"]
+    which = sys.argv[1:] or ["launches", "full", "extra", "copies"]
     for w in which:
-        {"launches": launches, "full": full, "copies": copies}[w]()
+        {"launches": launches, "full": full, "extra": extra_reports, "copies": copies}[w]()
