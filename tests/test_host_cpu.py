@@ -546,3 +546,57 @@ def test_sharded_gene_solve_chunks_partition_the_columns(world, N, g):
     e = InmfEngine.__new__(InmfEngine)
     e.world, e.rank, e._chunks = 1, 0, {}
     assert e._solve_chunk(10, 5) is None
+
+
+def test_window_statistics_work_lists_place_every_window_row_in_its_block():
+    """blocked.window_stats_work (the online step's block-aligned statistics pass): for random dataset / mini-batch sizes,
+    ranks and step counts, every window row lands at the position of its cell inside the slot of its block, no two rows
+    share a position, every touched block is listed with all its gene ranges exactly once, and nothing else is listed."""
+    from pyliger_b200 import blocked
+    from pyliger_b200.engine import online_windows
+    rng = np.random.RandomState(0)
+    checked = 0
+    for trial in range(120):
+        N = rng.randint(1, 4)
+        ns = [int(rng.randint(40, 400)) for _ in range(N)]
+        mbs = [int(rng.randint(5, min(ns[i], 90))) for i in range(N)]
+        world = rng.randint(1, 3)
+        rank = rng.randint(0, world)
+        sub = [((m * rank) // world, (m * (rank + 1)) // world) for m in mbs]
+        T = rng.randint(1, 40)
+        row_base = np.concatenate([[0], np.cumsum(ns)])
+        plan = online_windows(T, mbs, sub, ns, row_base)
+        cnt = [hi - lo for lo, hi in sub]
+        cbs = [-(-max(c, 1) // (-(-max(c, 1) // 64))) for c in cnt]   # blocks of at most 64 cells
+        nb = [-(-n // c) for n, c in zip(ns, cbs)]
+        blk_off = np.concatenate([[0], np.cumsum(nb)]).astype(np.int64)
+        nch, tb = 3, int(blk_off[-1])
+        W = np.zeros((tb * nch, 8), dtype=np.int64)
+        W[:, 0] = np.arange(tb * nch)                                 # item id in the slice_begin field
+        W[:, 3] = np.repeat([min(cbs[s], ns[s] - b * cbs[s]) for s in range(N) for b in range(nb[s])], nch)
+        res = blocked.window_stats_work(W, (nb, cbs, blk_off, nch), plan, ns)
+        if res is None:   # a window wrapping onto its own first block: the row kernels take the run
+            continue
+        work, counts, place, region = res
+        for t in range(T):
+            slots = {}
+            for r in range(counts[t]):
+                blk = work[t, r, 0] // nch
+                s = int(np.searchsorted(blk_off[1:], blk, side="right"))
+                slots.setdefault(int(work[t, r, 2]), []).append((s, int(blk - blk_off[s]), int(work[t, r, 3])))
+            assert all(len(v) == nch and len(set(v)) == 1 for v in slots.values())
+            seen, touched = set(), set()
+            for i in range(N):
+                for q in range(cnt[i]):
+                    row = (plan[t, i, 2] + q) % ns[i]
+                    pos = int(place[t, plan[t, i, 0] + q])
+                    assert pos not in seen and region[i] <= pos < region[i + 1]
+                    seen.add(pos)
+                    base = [b0 for b0, v in slots.items() if b0 <= pos < b0 + cbs[i] and v[0][0] == i]
+                    assert len(base) == 1
+                    s_, b_, rows_ = slots[base[0]][0]
+                    assert b_ == row // cbs[i] and pos - base[0] == row - b_ * cbs[i] and pos - base[0] < rows_
+                    touched.add(base[0])
+            assert touched == set(slots)
+            checked += 1
+    assert checked > 500
