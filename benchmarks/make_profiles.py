@@ -112,7 +112,8 @@ def extra_reports():
 
 def copies():
     for src, dst in (("r2_bench_n1.json", "r2_bench_n1.json"), ("r2_bench_ref.json", "r2_bench_reference_arm.json"),
-                     ("r2_bench_n2.json", "r2_bench_n2.json"), ("r2_bench_n8.json", "r2_bench_n8.json")):
+                     ("r2_bench_n2.json", "r2_bench_n2.json"), ("r2_bench_n4.json", "r2_bench_n4.json"),
+                     ("r2_bench_n8.json", "r2_bench_n8.json")):
         p = os.path.join(OUT, src)
         if os.path.exists(p):
             lines = [l for l in open(p).read().splitlines() if l.startswith("{")]
