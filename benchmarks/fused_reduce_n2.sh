@@ -1,3 +1,6 @@
+#!/bin/bash
+# 2-GPU comparison of the two reduction modes (run under gpurun --gpus 2): bench.py with --fused-reduce 1 / 0, C2 + C4.
+# Results: profiles/r2_fused_reduce_n2.txt.
 RUN="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511"
 for f in 1 0; do for g in 1 0; do
 timeout 400 $RUN bench.py --gpus 2 --no-cpu --no-e2e --extra c4 --fused-reduce $f --graph $g > gpurun_out/n2_f${f}_g${g}.json 2> gpurun_out/n2_f${f}_g${g}.err; echo "fused=$f graph=$g rc=$?"

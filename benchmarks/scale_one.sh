@@ -1,3 +1,5 @@
+#!/bin/bash
+# usage: benchmarks/scale_one.sh N   (under gpurun --gpus N): the bench line at N GPUs -> gpurun_out/r2_bench_nN.json
 N=$1
 RUN="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29544"
 timeout 700 $RUN bench.py --gpus $N --no-cpu --extra c4,c3,parity,fused > gpurun_out/r2_bench_n$N.json 2> gpurun_out/r2_bench_n$N.err; echo rc=$?
