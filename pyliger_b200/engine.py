@@ -241,6 +241,7 @@ class InmfEngine(object):
         self.n_prev = int(n_prev)
         self._chunks = {}
         self._parts = {}
+        self._guards = []
         if self.deterministic and (resolve_dtype(dtype) != torch.float32 or is_mixed(dtype)):
             raise ValueError("deterministic=True is implemented for dtype='float32' (the sliced passes)")
         with torch.cuda.device(self.device):
@@ -262,14 +263,13 @@ class InmfEngine(object):
         n = int(np.prod(shape))
         raw = torch.full((n + 2 * ge,), self._GUARD[dtype], dtype=dtype, device=self.device)
         raw[ge:ge + n] = 0
-        self.__dict__.setdefault("_guards", []).append((name or "buffer%d" % len(self.__dict__.get("_guards", [])),
-                                                        raw, ge, n))
+        self._guards.append((name or "buffer%d" % len(self._guards), raw, ge, n))
         return raw[ge:ge + n].view(*shape)
 
     def check_guards(self):
         """Names of the guarded buffers with a modified band (empty list = no out-of-bounds write seen)."""
         bad = []
-        for name, raw, ge, n in self.__dict__.get("_guards", []):
+        for name, raw, ge, n in self._guards:
             ref = torch.full((ge,), self._GUARD[raw.dtype], dtype=raw.dtype, device=raw.device)
             if not (torch.equal(raw[:ge], ref) and torch.equal(raw[ge + n:], ref)):
                 bad.append(name)
@@ -1006,6 +1006,10 @@ class InmfEngine(object):
         cnt = [hi - lo for lo, hi in self.sub]
         total = int(sum(cnt))
         if total == 0 or plan.shape[0] * total * 8 > self.window_stats_max_bytes:
+            return
+        # a third copy of the resident cells (8 bytes per non-zero, twice that while it is built): only with room to spare
+        free_bytes = torch.cuda.mem_get_info(self.device)[0]
+        if 3 * 8 * int(self.X.nnz) > free_bytes // 2:
             return
         cbs = blocked.window_blocks(cnt, self.ldm, 4)
         chunks = max(1, min(sms // max(1, self.N), self.g // 128))

@@ -685,7 +685,7 @@ def test_kernels_write_inside_their_buffers(monkeypatch, dtype, k, det):
     if dtype != "mixed" and not det:
         iNMF_HALS(_liger(mats), k, max_iters=4, rand_seed=1, dtype=dtype, verbose=False)
         online_iNMF(_liger(mats), k=k, miniBatch_size=600, max_epochs=2, rand_seed=1, dtype=dtype, verbose=False)
-    assert engines and all(e.__dict__.get("_guards") for e in engines)
+    assert engines and all(e._guards for e in engines)
     for e in engines:
         assert e.check_guards() == []
     # the check itself sees a stray write
