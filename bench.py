@@ -569,7 +569,9 @@ def main():
     ap.add_argument("--config", default="C2", choices=["C2", "C4"],
                     help="headline workload: C2 (default, weak scaling) or C4 (8 x 250k cells sharded over the ranks)")
     ap.add_argument("--cells", type=int, default=0, help="cells per dataset per GPU (default: the config's)")
-    ap.add_argument("--graph", type=int, default=1, help="1: CUDA-graphed warm iterations (the engine default), 0: eager")
+    ap.add_argument("--graph", type=int, default=-1,
+                    help="-1: the engine's policy (CUDA-graphed warm iterations when N > 1, eager launches on one GPU), "
+                         "1: graphs from the first warm iteration, 0: eager")
     ap.add_argument("--fused-reduce", type=int, default=0,
                     help="N > 1: 0 = pass 2 + NCCL all-reduce (the engine default), 1 = pass 2 adds its finished gene "
                          "ranges into multicast-bound symmetric sum buffers (no separate all-reduce); the other mode is "
@@ -596,7 +598,7 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
-    InmfEngine.use_graph = bool(args.graph)
+    InmfEngine.use_graph = None if args.graph < 0 else bool(args.graph)
     InmfEngine.fused_reduce = bool(args.fused_reduce)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)

@@ -800,19 +800,36 @@ class InmfEngine(object):
     # -- "body" (H solve ... objective + its copy to pinned memory) and "pass 1" (right-hand sides into the other
     # buffer) -- and replayed: one launch call instead of ~20 per iteration and no gaps between dependent kernels.
     # At C4 on 8 GPUs the eager loop lost 0.48 ms of a 2.87 ms iteration to launch gaps and rank skew.
-    use_graph = True
+    # use_graph: None = policy (on when the cells are sharded over several GPUs, where the replay also removes the
+    # launch skew between the ranks; off on one GPU, where the host keeps ahead of the GPU anyway and a 20 - 100
+    # iteration call does not earn back the capture: measured 38.9 vs 40.9 ms for the 20-iteration public call at C2,
+    # 100.3 vs 102 - 116 ms for 100 iterations), True = from the first warm iteration on, False = never.
+    use_graph = None
     _graph_eager_warm = 0       # eager warm iterations seen (everything lazily allocated exists after the first)
     _graphs = None
+    _capture_stream = None
+
+    def _graphs_enabled(self):
+        return (self.world > 1) if self.use_graph is None else bool(self.use_graph)
 
     def _graph_capture(self, key, fn):
         """Capture fn() (nothing runs); None if this stack cannot capture it -- the caller then runs fn() eagerly and
-        graphs stay off (the results are the same either way)."""
+        graphs stay off (the results are the same either way).  Captured directly on a side stream: the
+        torch.cuda.graph() context would also empty the caching allocator, which costs the NEXT call its cudaMallocs."""
         g = torch.cuda.CUDAGraph()
-        torch.cuda.synchronize(self.device)
+        if self._capture_stream is None:
+            self._capture_stream = torch.cuda.Stream(self.device)
+        side, cur = self._capture_stream, torch.cuda.current_stream(self.device)
         n0 = _lib.launch_count()
         try:
-            with torch.cuda.graph(g):
-                fn()
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                g.capture_begin()
+                try:
+                    fn()
+                finally:
+                    g.capture_end()
+            cur.wait_stream(side)
         except Exception as e:
             import warnings
             warnings.warn("pyliger_b200: CUDA-graph capture of the ALS iteration failed (%s); running eagerly" % (e,))
@@ -849,9 +866,9 @@ class InmfEngine(object):
         can be swapped on the host side for the second pair), so that no capture lands in a later iteration."""
         saved = (self.H, self.H_alt, self._clean_ptr)
         for _ in range(2):
-            if self.use_graph and ("body", self.H.data_ptr()) not in self._graphs:
+            if self._graphs_enabled() and ("body", self.H.data_ptr()) not in self._graphs:
                 self._graph_capture(("body", self.H.data_ptr()), self._fn_body)
-            if self.use_graph and ("pass1", self.H.data_ptr()) not in self._graphs:
+            if self._graphs_enabled() and ("pass1", self.H.data_ptr()) not in self._graphs:
                 self._graph_capture(("pass1", self.H.data_ptr()), self._fn_pass1)
             self.H, self.H_alt = self.H_alt, self.H
         self.H, self.H_alt, self._clean_ptr = saved
@@ -888,7 +905,7 @@ class InmfEngine(object):
     def als_iteration_value(self, warm=False, speculate=False):
         """als_iteration() + host value of the objective; with ``speculate`` the next pass 1 overlaps the read-back
         (call als_cancel() if no further iteration follows)."""
-        if (self.use_graph and warm and self._graph_eager_warm >= 1 and self.pass1 is not None and self.pass2 is not None
+        if (self._graphs_enabled() and warm and self._graph_eager_warm >= 1 and self.pass1 is not None and self.pass2 is not None
                 and self.H_alt is not None and not self.use_tc):
             if self._graphs is None:
                 self._graphs = {}
