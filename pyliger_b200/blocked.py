@@ -196,6 +196,18 @@ def build_sell(bp, kp, height=None):
     return sp
 
 
+def mc_work(sp, g):
+    """Work array of the fused pass 2 + all-reduce (inmf_sell_pass_mc_f32) for the sliced pass ``sp`` over datasets of
+    ``g`` genes: the items that add into one (dataset, gene range) share an arrival counter -- field 6 = counter id,
+    field 7 = (first row << 32) | end row of the range, rows relative to out_row_base.  Returns (work, expected) with
+    expected[c] = number of items of counter c."""
+    W = sp.work_host.copy()
+    _, cid, expected = np.unique(W[:, 4] * (g + 1) + sp.row_lo, return_inverse=True, return_counts=True)
+    W[:, 6] = cid
+    W[:, 7] = (sp.row_lo.astype(np.int64) << 32) | sp.row_hi.astype(np.int64)
+    return W, expected.astype(np.int32)
+
+
 def sell_applies(kp, esize):
     return SELL and esize == 4 and 32 <= kp <= 64
 

@@ -414,12 +414,9 @@ class InmfEngine(object):
         self.HtH_part = part[n_st:n_st + N * k * k * 8].view(torch.float64).view(N, k, k)
         self.St = buf[:N * g * k * 4].view(torch.float32).view(N, g, k)
         self.HtH = buf[n_st:n_st + N * k * k * 8].view(torch.float64).view(N, k, k)
-        W = p.work_host.copy()
-        _, cid, expected = np.unique(W[:, 4] * (g + 1) + p.row_lo, return_inverse=True, return_counts=True)
-        W[:, 6] = cid
-        W[:, 7] = (p.row_lo.astype(np.int64) << 32) | p.row_hi.astype(np.int64)
+        W, expected = blocked.mc_work(p, g)
         work_mc = torch.from_numpy(W).to(dev)
-        expected_t = torch.from_numpy(expected.astype(np.int32)).to(dev)
+        expected_t = torch.from_numpy(expected).to(dev)
         counters = torch.zeros(len(expected), dtype=torch.int32, device=dev)
         args = torch.tensor([mcp, mcp + n_st, counters.data_ptr(), expected_t.data_ptr()], dtype=torch.int64, device=dev)
         self.mc = (hdl, buf, work_mc, args, part, (expected_t, counters))

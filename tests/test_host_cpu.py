@@ -600,3 +600,48 @@ def test_window_statistics_work_lists_place_every_window_row_in_its_block():
             assert touched == set(slots)
             checked += 1
     assert checked > 500
+
+
+def test_fused_reduction_counters_partition_the_work_items():
+    """blocked.mc_work (pass 2 fused with its all-reduce): every work item belongs to exactly one (dataset, gene range)
+    counter, all items of a counter cover the same rows of the same dataset, the counters' ranges tile every dataset's
+    genes exactly once, expected[] counts the items, and the items that add a tile Gram (gram_seg >= 0) are exactly those
+    of the first range of their dataset."""
+    from pyliger_b200 import blocked
+
+    class SP(object):
+        pass
+    rng = np.random.RandomState(3)
+    for trial in range(50):
+        N, g = rng.randint(1, 5), int(rng.randint(40, 900))
+        nb = [int(rng.randint(0, 6)) for _ in range(N)]
+        nch = int(rng.randint(1, 5))
+        per = -(-g // nch)
+        glo = np.arange(0, g, per)
+        rows = []
+        for s in range(N):
+            for b in range(nb[s]):
+                for ci, lo in enumerate(glo):
+                    rows.append([0, 0, 0, 0, s * g, s if ci == 0 else -1, b, 0, lo, min(g, lo + per)])
+        if not rows:
+            continue
+        rows = np.asarray(rows, dtype=np.int64)
+        rng.shuffle(rows)
+        sp = SP()
+        sp.work_host, sp.row_lo, sp.row_hi = rows[:, :8].copy(), rows[:, 8].copy(), rows[:, 9].copy()
+        W, expected = blocked.mc_work(sp, g)
+        assert expected.sum() == len(W) and W[:, 6].min() == 0 and W[:, 6].max() == len(expected) - 1
+        cover = {}
+        for c in range(len(expected)):
+            items = W[W[:, 6] == c]
+            assert len(items) == expected[c]
+            assert len(set(map(tuple, items[:, [4, 7]]))) == 1          # one dataset, one row range
+            lo, hi = int(items[0, 7] >> 32), int(items[0, 7] & 0xffffffff)
+            s = int(items[0, 4]) // g
+            cover.setdefault(s, []).append((lo, hi))
+            assert ((items[:, 5] >= 0) == (lo == 0)).all() and (items[items[:, 5] >= 0, 5] == s).all()
+            assert expected[c] == nb[s]
+        for s, ranges in cover.items():
+            ranges.sort()
+            assert ranges[0][0] == 0 and ranges[-1][1] == g
+            assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
