@@ -19,6 +19,11 @@ pyliger_b200.optimize_ALS (warm-started BPP; fp32 is the throughput mode, fp64 t
                 (cell-visits/s) and the final H pass (cells/s, HBM fraction)
   c5_bpp        configs[4]: batched nnlsm_blockpivot, 10 M columns, k in {20, 40, 60}, cold and warm (N = 1 only)
   parity_vs_1gpu (N > 1) the row-sharded N-rank run against the 1-rank run of the same small problem, same process
+  c2_fused_reduce / c4_strong.fused_reduce_leg (N > 1) the same loops with the OTHER reduction mode: pass 2 fused with its
+                all-reduce (multimem.red into multicast-bound sum buffers) when the headline used NCCL, and vice versa
+
+Launch policy: the engine default (`--graph -1`): eager launches on one GPU, CUDA-graphed warm iterations at N > 1;
+`--graph 1` / `--graph 0` force either.
 
 One JSON line on stdout from rank 0.  See DESIGN.md "Measurement" for how every field is obtained.
 """
